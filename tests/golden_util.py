@@ -1,0 +1,40 @@
+"""Helpers shared by the tests: load reference fixtures (tests/golden, generated from the
+unmodified reference by oracle/refbuild/make_golden.py) and build the matching oracle problem."""
+import hashlib
+import os
+
+import numpy as np
+
+from oracle import elliptic_ref as er
+from oracle.mesh_box import build_box_hex_mesh, masked_global_ids
+from oracle.ogs_ref import SIGNED, ogs_setup_all
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FULL = ["hex_n3_e3_jacobi", "hex_n7_e2_jacobi", "hex_n2_e4_periodic", "hex_n1_e5_none"]
+DIGEST = ["hex_n7_e3_bp5", "hex_n4_e10_jacobi", "hex_n4_e10_none"]
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLD, name + ".npz")))
+
+
+def sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+
+
+class Problem:
+    """Oracle-side restatement of mesh + masked ogs for a golden config."""
+
+    def __init__(self, g, geometry=True):
+        N, n, flag = (int(v) for v in g["config"])
+        self.N, self.n, self.flag = N, n, flag
+        self.Nq = N + 1
+        self.lam = float(g["lambda"][0])
+        self.mesh = build_box_hex_mesh(N, n, n, n, boundary_flag=flag, geometry=geometry)
+        self.mapB, self.ids = masked_global_ids(self.mesh)
+        self.ogs = ogs_setup_all([self.ids], SIGNED, True)[0]
+        self.G2L = self.ogs.global_to_local()
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300))

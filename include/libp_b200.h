@@ -1,0 +1,244 @@
+/*
+ * libp_b200.h - C ABI of the B200-native elliptic hot path for libParanumal.
+ *
+ * Every entry point replaces one reference interface on the path
+ *   elliptic_t::Operator -> ogs_t / halo_t -> linAlg_t -> LinearSolver::pcg -> precon_t
+ * (file:line citations are relative to the libParanumal 0.5.0 tree).  The reference reaches
+ * these through C++ virtuals and occa::kernel functors; the shim a maintainer adds on the
+ * reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; device pointers are CUDA device addresses
+ *     (deviceMemory<T>::ptr(), include/memory.hpp:322-327)
+ *   - dlong = int32, hlong = int64, dfloat = pfloat = double   (include/types.h:31-64)
+ *   - every function returns LIBP_SUCCESS (0) or LIBP_ERROR (-1)  (include/utils.hpp:48-49);
+ *     libp_last_error() returns the thread-local message; the C++ shim turns non-zero into
+ *     LIBP_FORCE_ABORT so the reference's throw-libp::exception behaviour is kept
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream)
+ *   - one caller thread per GPU, Start/Finish pairs in order on one handle (the reference's
+ *     own threading contract)
+ */
+#ifndef LIBP_B200_H
+#define LIBP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LIBP_SUCCESS 0
+#define LIBP_ERROR (-1)
+
+typedef int32_t libp_dlong;
+typedef int64_t libp_hlong;
+typedef double libp_dfloat;
+
+/* ogs enums: include/ogs.hpp:178-199 (same numeric values) */
+typedef enum { LIBP_FLOAT = 0, LIBP_DOUBLE = 1, LIBP_INT32 = 2, LIBP_INT64 = 3 } libp_type_t;
+typedef enum { LIBP_ADD = 0, LIBP_MUL = 1, LIBP_MAX = 2, LIBP_MIN = 3 } libp_op_t;
+typedef enum { LIBP_SYM = 0, LIBP_NOTRANS = 1, LIBP_TRANS = 2 } libp_transpose_t;
+typedef enum { LIBP_UNSIGNED = 0, LIBP_SIGNED = 1, LIBP_HALO = 2 } libp_kind_t;
+
+typedef struct libp_comm_s* libp_comm_t;
+typedef struct libp_ogs_s* libp_ogs_t;
+typedef struct libp_elliptic_s* libp_elliptic_t;
+typedef struct libp_pcg_s* libp_pcg_t;
+typedef struct libp_precon_s* libp_precon_t;
+
+/* ------------------------------------------------------------------ runtime / errors */
+const char* libp_last_error(void);
+/* Library build info: "sm_100a;<git describe or date>" */
+const char* libp_b200_version(void);
+/* Select the CUDA device of this process (platform_t device selection,
+ * libs/core/platformDeviceConfig.cpp:33-179: device_id = local rank). */
+int libp_b200_init(int device_id);
+/* Blocks until `stream` has drained (platform_t::finish, include/platform.hpp). */
+int libp_b200_finish(void* stream);
+
+/* ------------------------------------------------------------------ communicator
+ * Replaces comm_t (include/comm.hpp:95-...) on this path.
+ * Host-side collectives are needed only at setup (ogsBase_t::Setup uses Alltoall / Alltoallv /
+ * Allreduce / Scan); they are supplied by the embedding program as callbacks so the library
+ * has no MPI dependency: the reference shim fills them with MPI_*, the Python harness with
+ * torch.distributed (gloo).  With size==1 they may be NULL.
+ * Data-path collectives (halo exchange, dot products) run on NCCL over NVLink.           */
+typedef struct {
+  void* ctx;
+  /* every rank sends `bytes_per_rank` bytes to each rank (MPI_Alltoall of bytes) */
+  int (*alltoall)(void* ctx, const void* send, void* recv, size_t bytes_per_rank);
+  /* MPI_Alltoallv of bytes: counts/offsets are in bytes, arrays of length size */
+  int (*alltoallv)(void* ctx, const void* send, const int64_t* send_counts, const int64_t* send_offsets,
+                   void* recv, const int64_t* recv_counts, const int64_t* recv_offsets);
+  /* in-place allreduce of n int64 values; op: LIBP_ADD / LIBP_MAX / LIBP_MIN */
+  int (*allreduce_i64)(void* ctx, int64_t* inout, int n, int op);
+  /* in-place allreduce of n doubles (host); used by setup-time eigenvalue estimates */
+  int (*allreduce_f64)(void* ctx, double* inout, int n, int op);
+} libp_host_collectives_t;
+
+int libp_comm_create(int rank, int size, const libp_host_collectives_t* host, libp_comm_t* comm);
+int libp_comm_free(libp_comm_t comm);
+int libp_comm_rank(libp_comm_t comm, int* rank, int* size);
+/* NCCL bootstrap: rank 0 calls libp_comm_nccl_unique_id (128 bytes), the embedding program
+ * broadcasts it (MPI_Bcast / torch.distributed), every rank calls libp_comm_nccl_init. */
+int libp_comm_nccl_unique_id(void* uid128);
+int libp_comm_nccl_init(libp_comm_t comm, const void* uid128);
+
+/* ------------------------------------------------------------------ ogs
+ * ogs::ogs_t::Setup (include/ogs.hpp:216-226; libs/ogs/ogsSetup.cpp:43-190).
+ * `ids` (host, length N): 0 = ignored, sign = flag.  When `unique` the array is rewritten
+ * with the owner copy positive (ogsSetup.cpp:138-141), using glibc rand() exactly like the
+ * reference (ogsSetup.cpp:268-274) so maps are bit-identical in the same call sequence.   */
+int libp_ogs_setup(libp_dlong N, libp_hlong* ids, libp_comm_t comm, int kind, int unique, int verbose,
+                   libp_ogs_t* ogs);
+int libp_ogs_free(libp_ogs_t ogs);
+
+typedef struct {
+  libp_dlong N, Ngather, NlocalT, NlocalP, NhaloT, NhaloP, Nhalo;
+  libp_hlong NgatherGlobal;
+  int gather_defined;
+  /* pairwise exchange shape (libs/ogs/ogsPairwise.cpp:194-415) */
+  int NranksSendN, NranksSendT, NranksRecvN, NranksRecvT;
+  libp_dlong NsendN, NsendT, NrecvN, NrecvT;
+} libp_ogs_info_t;
+int libp_ogs_info(libp_ogs_t ogs, libp_ogs_info_t* info);
+
+/* Host copies of the maps for the bit-exact check.  which: 0 = gatherLocal, 1 = gatherHalo,
+ * 2 = exchange postmpi (ogsPairwise.cpp:283-336).  Pointers stay owned by the handle.
+ * nrows = NrowsT of that operator; rowStarts* have nrows+1 entries.                        */
+int libp_ogs_maps(libp_ogs_t ogs, int which, libp_dlong* NrowsN, libp_dlong* NrowsT,
+                  const libp_dlong** rowStartsN, const libp_dlong** rowStartsT,
+                  const libp_dlong** colIdsN, const libp_dlong** colIdsT);
+/* Pairwise send lists / per-neighbour counts (host).  trans selects N (NOTRANS) or T lists. */
+int libp_ogs_exchange_lists(libp_ogs_t ogs, int trans, libp_dlong* Nsend, const libp_dlong** sendIds,
+                            int* NranksSend, const int** sendRanks, const int** sendCounts, const int** sendOffsets,
+                            int* NranksRecv, const int** recvRanks, const int** recvCounts, const int** recvOffsets);
+/* ogs_t::SetupGlobalToLocalMapping (libs/ogs/ogsSetup.cpp:862-886): host array of N dlong. */
+int libp_ogs_global_to_local(libp_ogs_t ogs, libp_dlong* GlobalToLocal);
+
+/* Device apply (include/ogs.hpp:228-344; libs/ogs/ogs.cpp:39-488).  gv is the gathered vector
+ * [NlocalT | NhaloP | ...], v the local vector of N*k entries, k interleaved values per node. */
+int libp_ogs_gather(libp_ogs_t ogs, void* gv, const void* v, int k, int type, int op, int trans, void* stream);
+int libp_ogs_gather_start(libp_ogs_t ogs, void* gv, const void* v, int k, int type, int op, int trans, void* stream);
+int libp_ogs_gather_finish(libp_ogs_t ogs, void* gv, const void* v, int k, int type, int op, int trans, void* stream);
+int libp_ogs_scatter(libp_ogs_t ogs, void* v, const void* gv, int k, int type, int trans, void* stream);
+int libp_ogs_scatter_start(libp_ogs_t ogs, void* v, const void* gv, int k, int type, int trans, void* stream);
+int libp_ogs_scatter_finish(libp_ogs_t ogs, void* v, const void* gv, int k, int type, int trans, void* stream);
+int libp_ogs_gather_scatter(libp_ogs_t ogs, void* v, int k, int type, int op, int trans, void* stream);
+int libp_ogs_gather_scatter_start(libp_ogs_t ogs, void* v, int k, int type, int op, int trans, void* stream);
+int libp_ogs_gather_scatter_finish(libp_ogs_t ogs, void* v, int k, int type, int op, int trans, void* stream);
+
+/* halo_t built by SetupFromGather (libs/ogs/ogsSetup.cpp:888-916) on the same handle:
+ * ExchangeStart/Finish (libs/ogs/ogsHalo.cpp:46-143) send v[NlocalT : NlocalT+NhaloP] and fill
+ * v[NlocalT+NhaloP : NlocalT+NhaloT].                                                     */
+int libp_halo_exchange_start(libp_ogs_t ogs, void* v, int k, int type, void* stream);
+int libp_halo_exchange_finish(libp_ogs_t ogs, void* v, int k, int type, void* stream);
+int libp_halo_exchange(libp_ogs_t ogs, void* v, int k, int type, void* stream);
+
+/* ------------------------------------------------------------------ ellipticAx Hex3D
+ * ellipticPartialAxHex3D (solvers/elliptic/okl/ellipticAxHex3D.okl:156-295), same argument
+ * meaning and order (S, MM are unused by the reference kernel and dropped):
+ *   AqL[e,:] = A_e * q[GlobalToLocal[e,:]]   for e in elementList[0:Nelements]
+ * elementList==NULL means e = 0..Nelements-1; GlobalToLocal==NULL gives the element-local twin
+ * ellipticAxHex3D (:28-152).  Nq = N+1 in [2, 9].                                         */
+int libp_ax_hex3d(int Nq, libp_dlong Nelements, const libp_dlong* elementList, const libp_dlong* GlobalToLocal,
+                  const libp_dfloat* wJ, const libp_dfloat* ggeo, const libp_dfloat* D, libp_dfloat lambda,
+                  const libp_dfloat* q, libp_dfloat* AqL, void* stream);
+/* Fused variant: the gather (ogs Add, Trans) is folded into the epilogue, Aq[GlobalToLocal]
+ * += A_e q.  Aq must be zeroed by the caller (libp_elliptic_operator does).               */
+int libp_ax_hex3d_gather(int Nq, libp_dlong Nelements, const libp_dlong* elementList, const libp_dlong* GlobalToLocal,
+                         const libp_dfloat* wJ, const libp_dfloat* ggeo, const libp_dfloat* D, libp_dfloat lambda,
+                         const libp_dfloat* q, libp_dfloat* Aq, void* stream);
+
+/* ------------------------------------------------------------------ elliptic_t::Operator (C0)
+ * solvers/elliptic/src/ellipticOperator.cpp:31-106.  All pointers are device pointers that
+ * stay owned by the caller (mesh.o_*, o_GlobalToLocal).                                    */
+typedef struct {
+  int Nq;
+  libp_dlong Nelements;
+  libp_dlong NlocalGatherElements, NglobalGatherElements;
+  const libp_dlong* localGatherElementList;  /* device */
+  const libp_dlong* globalGatherElementList; /* device */
+  const libp_dlong* GlobalToLocal;           /* device, Nelements*Np */
+  const libp_dfloat* wJ;                     /* device, Nelements*Np */
+  const libp_dfloat* ggeo;                   /* device, Nelements*6*Np */
+  const libp_dfloat* D;                      /* device, Nq*Nq row-major D[i*Nq+m] */
+  libp_dfloat lambda;
+  libp_ogs_t ogsMasked;
+  /* 0: reference data flow  (partial Ax -> AqL -> ogs gather), bit-reproducible summation order
+   * 1: fused Ax+gather epilogue (FP64 atomics, no AqL round trip)                           */
+  int mode;
+} libp_elliptic_desc_t;
+int libp_elliptic_create(const libp_elliptic_desc_t* desc, libp_elliptic_t* op);
+int libp_elliptic_free(libp_elliptic_t op);
+/* o_q and o_Aq are gathered vectors of Ndofs+Nhalo entries; the Nhalo tail of o_q is
+ * overwritten by the halo exchange exactly like the reference.         */
+int libp_elliptic_operator(libp_elliptic_t op, libp_dfloat* q, libp_dfloat* Aq, void* stream);
+
+/* ------------------------------------------------------------------ linAlg_t
+ * include/linAlg.hpp:52-120; kernels libs/linAlg/okl/linAlg*.okl.  beta==0 variants never read y. */
+int libp_linalg_set(libp_dlong N, libp_dfloat alpha, libp_dfloat* a, void* stream);
+int libp_linalg_add(libp_dlong N, libp_dfloat alpha, libp_dfloat* a, void* stream);
+int libp_linalg_scale(libp_dlong N, libp_dfloat alpha, libp_dfloat* a, void* stream);
+int libp_linalg_axpy(libp_dlong N, libp_dfloat alpha, const libp_dfloat* x, libp_dfloat beta, libp_dfloat* y, void* stream);
+int libp_linalg_zaxpy(libp_dlong N, libp_dfloat alpha, const libp_dfloat* x, libp_dfloat beta, const libp_dfloat* y,
+                      libp_dfloat* z, void* stream);
+int libp_linalg_amx(libp_dlong N, libp_dfloat alpha, const libp_dfloat* a, libp_dfloat* x, void* stream);
+int libp_linalg_amxpy(libp_dlong N, libp_dfloat alpha, const libp_dfloat* a, const libp_dfloat* x, libp_dfloat beta,
+                      libp_dfloat* y, void* stream);
+int libp_linalg_zamxpy(libp_dlong N, libp_dfloat alpha, const libp_dfloat* a, const libp_dfloat* x, libp_dfloat beta,
+                       const libp_dfloat* y, libp_dfloat* z, void* stream);
+int libp_linalg_adx(libp_dlong N, libp_dfloat alpha, const libp_dfloat* a, libp_dfloat* x, void* stream);
+int libp_linalg_adxpy(libp_dlong N, libp_dfloat alpha, const libp_dfloat* a, const libp_dfloat* x, libp_dfloat beta,
+                      libp_dfloat* y, void* stream);
+int libp_linalg_zadxpy(libp_dlong N, libp_dfloat alpha, const libp_dfloat* a, const libp_dfloat* x, libp_dfloat beta,
+                       const libp_dfloat* y, libp_dfloat* z, void* stream);
+/* Reductions (libs/linAlg/linAlg.cpp:104-224): deterministic two-level device reduction, then
+ * NCCL all-reduce when comm has size>1; the result is returned to the host (blocking), as the
+ * reference does.  comm may be NULL (single rank).                                          */
+int libp_linalg_min(libp_dlong N, const libp_dfloat* a, libp_comm_t comm, void* stream, libp_dfloat* result);
+int libp_linalg_max(libp_dlong N, const libp_dfloat* a, libp_comm_t comm, void* stream, libp_dfloat* result);
+int libp_linalg_sum(libp_dlong N, const libp_dfloat* a, libp_comm_t comm, void* stream, libp_dfloat* result);
+int libp_linalg_norm2(libp_dlong N, const libp_dfloat* a, libp_comm_t comm, void* stream, libp_dfloat* result);
+int libp_linalg_inner_prod(libp_dlong N, const libp_dfloat* x, const libp_dfloat* y, libp_comm_t comm, void* stream,
+                           libp_dfloat* result);
+int libp_linalg_weighted_norm2(libp_dlong N, const libp_dfloat* w, const libp_dfloat* a, libp_comm_t comm, void* stream,
+                               libp_dfloat* result);
+int libp_linalg_weighted_inner_prod(libp_dlong N, const libp_dfloat* w, const libp_dfloat* x, const libp_dfloat* y,
+                                    libp_comm_t comm, void* stream, libp_dfloat* result);
+
+/* ------------------------------------------------------------------ precon_t
+ * operator_t::Operator(o_r, o_Mr) implementations (include/precon.hpp:190-210).            */
+/* IdentityPrecon (include/precon.hpp) */
+int libp_precon_identity_create(libp_dlong N, libp_precon_t* precon);
+/* JacobiPrecon (solvers/elliptic/src/ellipticPreconJacobi.cpp:30-51): invDiagA is a device
+ * array of Ndofs entries, copied.  allNeumann -> ZeroMean on the output (ellipticZeroMean.cpp). */
+int libp_precon_jacobi_create(libp_dlong Ndofs, const libp_dfloat* invDiagA, int allNeumann,
+                              libp_hlong NglobalDofs, libp_comm_t comm, libp_precon_t* precon);
+int libp_precon_apply(libp_precon_t precon, const libp_dfloat* r, libp_dfloat* Mr, void* stream);
+int libp_precon_free(libp_precon_t precon);
+
+/* ------------------------------------------------------------------ LinearSolver::pcg
+ * linearSolverBase_t ctor (include/linearSolver.hpp:88-95) + pcg (libs/linearSolver/
+ * linearSolverPCG.cpp:35-171).  stopping: 0 = ABS/REL-INITRESID (default), 1 = ABS/REL-RHS-2NORM. */
+typedef int (*libp_operator_fn)(void* ctx, libp_dfloat* in, libp_dfloat* out, void* stream);
+
+int libp_pcg_create(libp_dlong N, libp_dlong Nhalo, int flexible, int stopping, libp_comm_t comm, libp_pcg_t* pcg);
+int libp_pcg_free(libp_pcg_t pcg);
+/* Generic path: A and M are callbacks (an un-replaced reference operator still works).
+ * Returns the iteration count in *iters.  Same control flow, scalars on the host.          */
+int libp_pcg_solve_cb(libp_pcg_t pcg, libp_operator_fn A, void* Actx, libp_operator_fn M, void* Mctx,
+                      libp_dfloat* x, libp_dfloat* r, libp_dfloat tol, int maxit, int verbose, void* stream, int* iters);
+/* Native fast path: both operators are library handles; vector updates are fused with their
+ * dot products and alpha/beta stay on the device (no host sync inside the iteration other
+ * than the convergence read-back every `check_every` iterations; 1 = reference behaviour). */
+int libp_pcg_solve(libp_pcg_t pcg, libp_elliptic_t A, libp_precon_t M, libp_dfloat* x, libp_dfloat* r,
+                   libp_dfloat tol, int maxit, int verbose, void* stream, int* iters);
+/* Residual norms sqrt(r.r) recorded by the last solve: [0] initial, [i] after iteration i. */
+int libp_pcg_residual_history(libp_pcg_t pcg, const libp_dfloat** hist, int* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIBP_B200_H */

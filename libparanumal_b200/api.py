@@ -1,0 +1,429 @@
+"""Host-side mirror of the reference interfaces on the elliptic hot path, over the C ABI.
+
+Names and argument meaning follow libParanumal (comm_t, ogs::ogs_t / halo_t, linAlg_t,
+elliptic_t::Operator, LinearSolver::pcg, precon_t) so the tests read like the reference's use of
+them.  torch is used only for device memory (tensors hand their data_ptr() to the library), the
+current CUDA stream, and torch.distributed for the setup-time host collectives / NCCL bootstrap.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from ._lib import (ADD, DOUBLE, FLOAT, HALO, INT32, INT64, MAX, MIN, MUL, NOTRANS, SIGNED, SYM, TRANS,
+                   UNSIGNED, check)
+
+_TYPE_OF = {torch.float32: FLOAT, torch.float64: DOUBLE, torch.int32: INT32, torch.int64: INT64}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream) if torch.cuda.is_available() else C.c_void_p(0)
+
+
+def _ptr(t):
+    if t is None:
+        return C.c_void_p(0)
+    if isinstance(t, torch.Tensor):
+        assert t.is_contiguous()
+        return C.c_void_p(t.data_ptr())
+    if isinstance(t, np.ndarray):
+        assert t.flags["C_CONTIGUOUS"]
+        return C.c_void_p(t.ctypes.data)
+    return C.c_void_p(int(t))
+
+
+def init(device_id=0):
+    """platform_t device selection."""
+    check(L.load().libp_b200_init(int(device_id)))
+    torch.cuda.set_device(device_id)
+
+
+def version():
+    return L.load().libp_b200_version().decode()
+
+
+# --------------------------------------------------------------------------- comm_t
+class Comm:
+    """comm_t: rank/size + setup-time host collectives (torch.distributed, any backend that works on
+    CPU tensors, e.g. gloo) + NCCL for the data path."""
+
+    def __init__(self, rank=0, size=1, group=None):
+        self.rank, self.size, self.group = rank, size, group
+        self._h = C.c_void_p()
+        self._cb = None
+        host = None
+        if size > 1:
+            import torch.distributed as dist
+
+            def a2a(ctx, send, recv, nbytes):
+                try:
+                    s = torch.from_numpy(np.ctypeslib.as_array(C.cast(send, C.POINTER(C.c_uint8)), (nbytes * size,)).copy())
+                    r = torch.empty_like(s)
+                    self._gloo_a2a(r, s, [nbytes] * size, [nbytes] * size)
+                    C.memmove(recv, r.numpy().ctypes.data, nbytes * size)
+                    return 0
+                except Exception as e:  # pragma: no cover
+                    print("host alltoall failed:", e)
+                    return 1
+
+            def a2av(ctx, send, sc, so, recv, rc, ro):
+                try:
+                    scl = [int(sc[i]) for i in range(size)]
+                    sol = [int(so[i]) for i in range(size)]
+                    rcl = [int(rc[i]) for i in range(size)]
+                    rol = [int(ro[i]) for i in range(size)]
+                    stot = max((o + c for o, c in zip(sol, scl)), default=0)
+                    rtot = max((o + c for o, c in zip(rol, rcl)), default=0)
+                    sarr = np.ctypeslib.as_array(C.cast(send, C.POINTER(C.c_uint8)), (max(stot, 1),))
+                    outs = self._gloo_a2a_lists([torch.from_numpy(sarr[o:o + c].copy()) for o, c in zip(sol, scl)], rcl)
+                    if rtot:
+                        rarr = np.ctypeslib.as_array(C.cast(recv, C.POINTER(C.c_uint8)), (rtot,))
+                        for o, c, t in zip(rol, rcl, outs):
+                            if c:
+                                rarr[o:o + c] = t.numpy()
+                    return 0
+                except Exception as e:  # pragma: no cover
+                    print("host alltoallv failed:", e)
+                    return 1
+
+            def ar_i64(ctx, buf, n, op):
+                try:
+                    arr = np.ctypeslib.as_array(buf, (n,))
+                    t = torch.from_numpy(arr.copy())
+                    dist.all_reduce(t, op={ADD: dist.ReduceOp.SUM, MAX: dist.ReduceOp.MAX, MIN: dist.ReduceOp.MIN}[op],
+                                    group=self.group)
+                    arr[:] = t.numpy()
+                    return 0
+                except Exception as e:  # pragma: no cover
+                    print("host allreduce failed:", e)
+                    return 1
+
+            def ar_f64(ctx, buf, n, op):
+                try:
+                    arr = np.ctypeslib.as_array(buf, (n,))
+                    t = torch.from_numpy(arr.copy())
+                    dist.all_reduce(t, op={ADD: dist.ReduceOp.SUM, MAX: dist.ReduceOp.MAX, MIN: dist.ReduceOp.MIN}[op],
+                                    group=self.group)
+                    arr[:] = t.numpy()
+                    return 0
+                except Exception as e:  # pragma: no cover
+                    print("host allreduce failed:", e)
+                    return 1
+
+            self._cb = (L.HostCollectives.ALLTOALL(a2a), L.HostCollectives.ALLTOALLV(a2av),
+                        L.HostCollectives.ALLREDUCE_I64(ar_i64), L.HostCollectives.ALLREDUCE_F64(ar_f64))
+            host = L.HostCollectives(None, *self._cb)
+        check(L.load().libp_comm_create(rank, size, C.byref(host) if host is not None else None, C.byref(self._h)))
+
+    # gloo has no all_to_all: emulate with all_gather of sizes + broadcast-free pairwise send/recv
+    def _gloo_a2a_lists(self, send_list, recv_counts):
+        import torch.distributed as dist
+        size, rank = self.size, self.rank
+        outs = [torch.empty(c, dtype=torch.uint8) for c in recv_counts]
+        outs[rank] = send_list[rank].clone()
+        reqs = []
+        for peer in range(size):
+            if peer == rank:
+                continue
+            if recv_counts[peer]:
+                reqs.append(dist.irecv(outs[peer], src=dist.get_global_rank(self.group, peer) if self.group else peer,
+                                       group=self.group))
+        for peer in range(size):
+            if peer == rank:
+                continue
+            if send_list[peer].numel():
+                reqs.append(dist.isend(send_list[peer], dst=dist.get_global_rank(self.group, peer) if self.group else peer,
+                                       group=self.group))
+        for r in reqs:
+            r.wait()
+        return outs
+
+    def _gloo_a2a(self, r, s, scounts, rcounts):
+        chunks = list(torch.split(s, scounts))
+        outs = self._gloo_a2a_lists(chunks, rcounts)
+        r.copy_(torch.cat(outs))
+
+    def init_nccl(self):
+        """NCCL bootstrap: rank 0 creates the unique id, torch.distributed broadcasts it."""
+        if self.size == 1:
+            return
+        import torch.distributed as dist
+        uid = np.zeros(128, dtype=np.uint8)
+        if self.rank == 0:
+            check(L.load().libp_comm_nccl_unique_id(_ptr(uid)))
+        t = torch.from_numpy(uid)
+        if dist.get_backend(self.group) == "nccl":
+            tc = t.cuda()
+            dist.broadcast(tc, src=dist.get_global_rank(self.group, 0) if self.group else 0, group=self.group)
+            t = tc.cpu()
+        else:
+            dist.broadcast(t, src=dist.get_global_rank(self.group, 0) if self.group else 0, group=self.group)
+        uid = t.numpy().copy()
+        check(L.load().libp_comm_nccl_init(self._h, _ptr(uid)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def free(self):
+        if self._h:
+            L.load().libp_comm_free(self._h)
+            self._h = C.c_void_p()
+
+
+# --------------------------------------------------------------------------- ogs_t / halo_t
+class Ogs:
+    """ogs::ogs_t (include/ogs.hpp:216-344) + the gathered halo_t built from it."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        self.comm = None
+
+    def Setup(self, N, ids, comm, kind=SIGNED, unique=False, verbose=False):
+        """ids: numpy int64 array of N entries; rewritten in place when unique (like the reference)."""
+        assert isinstance(ids, np.ndarray) and ids.dtype == np.int64 and ids.flags["C_CONTIGUOUS"]
+        assert ids.size == N
+        self.comm = comm
+        check(L.load().libp_ogs_setup(int(N), _ptr(ids), comm.handle, int(kind), int(bool(unique)), int(verbose),
+                                      C.byref(self._h)))
+        info = L.OgsInfo()
+        check(L.load().libp_ogs_info(self._h, C.byref(info)))
+        self.info = info
+        for f, _ in L.OgsInfo._fields_:
+            setattr(self, f, getattr(info, f))
+        return self
+
+    @property
+    def handle(self):
+        return self._h
+
+    def maps(self, which):
+        """which: 'local' | 'halo' | 'postmpi' -> dict of numpy copies of the CSR maps."""
+        w = {"local": 0, "halo": 1, "postmpi": 2}[which]
+        nN, nT = C.c_int(), C.c_int()
+        ps = [C.c_void_p() for _ in range(4)]
+        check(L.load().libp_ogs_maps(self._h, w, C.byref(nN), C.byref(nT), *[C.byref(p) for p in ps]))
+
+        def arr(p, n):
+            if n == 0 or not p.value:
+                return np.zeros(n, dtype=np.int32)
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int32)), (n,)).copy()
+
+        rsN = arr(ps[0], nT.value + 1)
+        rsT = arr(ps[1], nT.value + 1)
+        return dict(NrowsN=nN.value, NrowsT=nT.value, rowStartsN=rsN, rowStartsT=rsT,
+                    colIdsN=arr(ps[2], int(rsN[-1])), colIdsT=arr(ps[3], int(rsT[-1])))
+
+    def exchange_lists(self, trans):
+        ns = C.c_int()
+        nrs, nrr = C.c_int(), C.c_int()
+        p = [C.c_void_p() for _ in range(7)]
+        check(L.load().libp_ogs_exchange_lists(self._h, int(trans), C.byref(ns), C.byref(p[0]), C.byref(nrs),
+                                               C.byref(p[1]), C.byref(p[2]), C.byref(p[3]), C.byref(nrr),
+                                               C.byref(p[4]), C.byref(p[5]), C.byref(p[6])))
+
+        def arr(pp, n):
+            if n == 0 or not pp.value:
+                return np.zeros(n, dtype=np.int32)
+            return np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_int32)), (n,)).copy()
+
+        return dict(sendIds=arr(p[0], ns.value), sendRanks=arr(p[1], nrs.value), sendCounts=arr(p[2], nrs.value),
+                    sendOffsets=arr(p[3], nrs.value + 1), recvRanks=arr(p[4], nrr.value),
+                    recvCounts=arr(p[5], nrr.value), recvOffsets=arr(p[6], nrr.value + 1))
+
+    def SetupGlobalToLocalMapping(self):
+        out = np.empty(self.N, dtype=np.int32)
+        check(L.load().libp_ogs_global_to_local(self._h, _ptr(out)))
+        return out
+
+    # device apply on torch tensors
+    def Gather(self, gv, v, k=1, op=ADD, trans=TRANS):
+        check(L.load().libp_ogs_gather(self._h, _ptr(gv), _ptr(v), k, _TYPE_OF[v.dtype], op, trans, _stream()))
+
+    def GatherStart(self, gv, v, k=1, op=ADD, trans=TRANS):
+        check(L.load().libp_ogs_gather_start(self._h, _ptr(gv), _ptr(v), k, _TYPE_OF[v.dtype], op, trans, _stream()))
+
+    def GatherFinish(self, gv, v, k=1, op=ADD, trans=TRANS):
+        check(L.load().libp_ogs_gather_finish(self._h, _ptr(gv), _ptr(v), k, _TYPE_OF[v.dtype], op, trans, _stream()))
+
+    def Scatter(self, v, gv, k=1, trans=NOTRANS):
+        check(L.load().libp_ogs_scatter(self._h, _ptr(v), _ptr(gv), k, _TYPE_OF[v.dtype], trans, _stream()))
+
+    def GatherScatter(self, v, k=1, op=ADD, trans=SYM):
+        check(L.load().libp_ogs_gather_scatter(self._h, _ptr(v), k, _TYPE_OF[v.dtype], op, trans, _stream()))
+
+    def ExchangeStart(self, v, k=1):
+        check(L.load().libp_halo_exchange_start(self._h, _ptr(v), k, _TYPE_OF[v.dtype], _stream()))
+
+    def ExchangeFinish(self, v, k=1):
+        check(L.load().libp_halo_exchange_finish(self._h, _ptr(v), k, _TYPE_OF[v.dtype], _stream()))
+
+    def Exchange(self, v, k=1):
+        check(L.load().libp_halo_exchange(self._h, _ptr(v), k, _TYPE_OF[v.dtype], _stream()))
+
+    def Free(self):
+        if self._h:
+            L.load().libp_ogs_free(self._h)
+            self._h = C.c_void_p()
+
+
+# --------------------------------------------------------------------------- kernels
+def ax_hex3d(Nq, Nelements, elementList, GlobalToLocal, wJ, ggeo, D, lam, q, AqL):
+    """ellipticPartialAxHex3D argument order (S, MM dropped)."""
+    check(L.load().libp_ax_hex3d(Nq, Nelements, _ptr(elementList), _ptr(GlobalToLocal), _ptr(wJ), _ptr(ggeo),
+                                 _ptr(D), float(lam), _ptr(q), _ptr(AqL), _stream()))
+
+
+def ax_hex3d_gather(Nq, Nelements, elementList, GlobalToLocal, wJ, ggeo, D, lam, q, Aq):
+    check(L.load().libp_ax_hex3d_gather(Nq, Nelements, _ptr(elementList), _ptr(GlobalToLocal), _ptr(wJ), _ptr(ggeo),
+                                        _ptr(D), float(lam), _ptr(q), _ptr(Aq), _stream()))
+
+
+class Elliptic:
+    """The C0 branch of elliptic_t::Operator as an operator_t."""
+
+    def __init__(self, Nq, localList, globalList, GlobalToLocal, wJ, ggeo, D, lam, ogsMasked, mode=1):
+        self.keep = (localList, globalList, GlobalToLocal, wJ, ggeo, D, ogsMasked)
+        d = L.EllipticDesc()
+        d.Nq = Nq
+        d.NlocalGatherElements = 0 if localList is None else localList.numel()
+        d.NglobalGatherElements = 0 if globalList is None else globalList.numel()
+        d.Nelements = d.NlocalGatherElements + d.NglobalGatherElements
+        d.localGatherElementList = _ptr(localList) if d.NlocalGatherElements else None
+        d.globalGatherElementList = _ptr(globalList) if d.NglobalGatherElements else None
+        d.GlobalToLocal, d.wJ, d.ggeo, d.D = _ptr(GlobalToLocal), _ptr(wJ), _ptr(ggeo), _ptr(D)
+        d.lambda_ = float(lam)
+        d.ogsMasked = ogsMasked.handle
+        d.mode = mode
+        self._h = C.c_void_p()
+        check(L.load().libp_elliptic_create(C.byref(d), C.byref(self._h)))
+        self.Ndofs = ogsMasked.Ngather
+        self.Nhalo = ogsMasked.Nhalo
+
+    @property
+    def handle(self):
+        return self._h
+
+    def Operator(self, o_q, o_Aq):
+        check(L.load().libp_elliptic_operator(self._h, _ptr(o_q), _ptr(o_Aq), _stream()))
+
+    def Free(self):
+        if self._h:
+            L.load().libp_elliptic_free(self._h)
+            self._h = C.c_void_p()
+
+
+# --------------------------------------------------------------------------- linAlg_t
+class LinAlg:
+    """linAlg_t (include/linAlg.hpp:52-120) on torch float64 tensors."""
+
+    def __init__(self, comm=None):
+        self.comm = comm
+
+    def _c(self):
+        return self.comm.handle if self.comm is not None else None
+
+    def set(self, N, alpha, a): check(L.load().libp_linalg_set(N, alpha, _ptr(a), _stream()))
+    def add(self, N, alpha, a): check(L.load().libp_linalg_add(N, alpha, _ptr(a), _stream()))
+    def scale(self, N, alpha, a): check(L.load().libp_linalg_scale(N, alpha, _ptr(a), _stream()))
+    def axpy(self, N, alpha, x, beta, y): check(L.load().libp_linalg_axpy(N, alpha, _ptr(x), beta, _ptr(y), _stream()))
+    def zaxpy(self, N, alpha, x, beta, y, z): check(L.load().libp_linalg_zaxpy(N, alpha, _ptr(x), beta, _ptr(y), _ptr(z), _stream()))
+    def amx(self, N, alpha, a, x): check(L.load().libp_linalg_amx(N, alpha, _ptr(a), _ptr(x), _stream()))
+    def amxpy(self, N, alpha, a, x, beta, y): check(L.load().libp_linalg_amxpy(N, alpha, _ptr(a), _ptr(x), beta, _ptr(y), _stream()))
+    def zamxpy(self, N, alpha, a, x, beta, y, z): check(L.load().libp_linalg_zamxpy(N, alpha, _ptr(a), _ptr(x), beta, _ptr(y), _ptr(z), _stream()))
+    def adx(self, N, alpha, a, x): check(L.load().libp_linalg_adx(N, alpha, _ptr(a), _ptr(x), _stream()))
+    def adxpy(self, N, alpha, a, x, beta, y): check(L.load().libp_linalg_adxpy(N, alpha, _ptr(a), _ptr(x), beta, _ptr(y), _stream()))
+    def zadxpy(self, N, alpha, a, x, beta, y, z): check(L.load().libp_linalg_zadxpy(N, alpha, _ptr(a), _ptr(x), beta, _ptr(y), _ptr(z), _stream()))
+
+    def _red(self, fn, N, *ptrs):
+        out = C.c_double()
+        check(fn(N, *[_ptr(p) for p in ptrs], self._c(), _stream(), C.byref(out)))
+        return out.value
+
+    def min(self, N, a): return self._red(L.load().libp_linalg_min, N, a)
+    def max(self, N, a): return self._red(L.load().libp_linalg_max, N, a)
+    def sum(self, N, a): return self._red(L.load().libp_linalg_sum, N, a)
+    def norm2(self, N, a): return self._red(L.load().libp_linalg_norm2, N, a)
+    def innerProd(self, N, x, y): return self._red(L.load().libp_linalg_inner_prod, N, x, y)
+    def weightedNorm2(self, N, w, a): return self._red(L.load().libp_linalg_weighted_norm2, N, w, a)
+    def weightedInnerProd(self, N, w, x, y): return self._red(L.load().libp_linalg_weighted_inner_prod, N, w, x, y)
+
+
+# --------------------------------------------------------------------------- precon_t / pcg
+class Precon:
+    def __init__(self, handle, keep=None):
+        self._h, self.keep = handle, keep
+
+    @classmethod
+    def Identity(cls, N):
+        h = C.c_void_p()
+        check(L.load().libp_precon_identity_create(int(N), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def Jacobi(cls, Ndofs, invDiagA, allNeumann=False, NglobalDofs=0, comm=None):
+        h = C.c_void_p()
+        check(L.load().libp_precon_jacobi_create(int(Ndofs), _ptr(invDiagA), int(allNeumann), int(NglobalDofs),
+                                                 comm.handle if comm is not None else None, C.byref(h)))
+        return cls(h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def Operator(self, o_r, o_Mr):
+        check(L.load().libp_precon_apply(self._h, _ptr(o_r), _ptr(o_Mr), _stream()))
+
+    def Free(self):
+        if self._h:
+            L.load().libp_precon_free(self._h)
+            self._h = C.c_void_p()
+
+
+class Pcg:
+    """LinearSolver::pcg.  Solve() takes native handles; SolveCallbacks() takes python callables
+    (in, out) -> None working on raw device pointers wrapped as tensors by the caller."""
+
+    def __init__(self, N, Nhalo, comm=None, flexible=False, stopping="ABS/REL-INITRESID"):
+        self._h = C.c_void_p()
+        self.N, self.Nhalo = N, Nhalo
+        st = 0 if stopping == "ABS/REL-INITRESID" else 1
+        check(L.load().libp_pcg_create(int(N), int(Nhalo), int(flexible), st, comm.handle if comm is not None else None,
+                                       C.byref(self._h)))
+
+    def Solve(self, A: Elliptic, M: Precon, o_x, o_r, tol=1e-8, maxit=5000, verbose=0):
+        it = C.c_int()
+        check(L.load().libp_pcg_solve(self._h, A.handle, M.handle, _ptr(o_x), _ptr(o_r), float(tol), int(maxit),
+                                      int(verbose), _stream(), C.byref(it)))
+        return it.value
+
+    def SolveCallbacks(self, A_fn, M_fn, o_x, o_r, tol=1e-8, maxit=5000, verbose=0):
+        def wrap(fn):
+            def cb(ctx, pin, pout, stream):
+                try:
+                    fn(pin, pout)
+                    return 0
+                except Exception as e:  # pragma: no cover
+                    print("operator callback failed:", e)
+                    return -1
+            return L.OPERATOR_FN(cb)
+        a, m = wrap(A_fn), wrap(M_fn)
+        it = C.c_int()
+        check(L.load().libp_pcg_solve_cb(self._h, a, None, m, None, _ptr(o_x), _ptr(o_r), float(tol), int(maxit),
+                                         int(verbose), _stream(), C.byref(it)))
+        return it.value
+
+    def residual_history(self):
+        p, n = C.c_void_p(), C.c_int()
+        check(L.load().libp_pcg_residual_history(self._h, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), (n.value,)).copy()
+
+    def Free(self):
+        if self._h:
+            L.load().libp_pcg_free(self._h)
+            self._h = C.c_void_p()

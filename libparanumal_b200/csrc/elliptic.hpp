@@ -1,0 +1,39 @@
+// Internal handles of the elliptic operator / preconditioners / PCG.
+#pragma once
+#include "common.hpp"
+#include "ogs.hpp"
+
+namespace libp_b200 {
+int ax_hex3d_launch(int Nq, bool fused, bool trusted_D, dlong Nelements, const dlong* elementList, const dlong* G2L,
+                    const dfloat* wJ, const dfloat* ggeo, const dfloat* D, dfloat lambda, const dfloat* q,
+                    dfloat* Aq, dfloat* dotPartials, const int* doneFlag, cudaStream_t s);
+int ax_hex3d_blocks(int Nq, dlong Nelements);
+void ogs_gather_start_f64(libp_ogs_s& o, double* gv, const double* v, int op, int trans, cudaStream_t s);
+void ogs_gather_finish_f64(libp_ogs_s& o, double* gv, const double* v, int op, int trans, cudaStream_t s);
+void halo_start_f64(libp_ogs_s& o, double* v, cudaStream_t s);
+void halo_finish_f64(libp_ogs_s& o, double* v, cudaStream_t s);
+void halo_combine_start_f64(libp_ogs_s& o, cudaStream_t s);
+void halo_combine_finish_f64(libp_ogs_s& o, cudaStream_t s);
+}  // namespace libp_b200
+
+struct libp_elliptic_s {
+  libp_elliptic_desc_t d{};
+  int Np = 0;
+  dlong Ndofs = 0, Nhalo = 0;
+  libp_b200::dev_buf<dfloat> AqL;          // mode 0 scratch, Nelements*Np
+  libp_b200::dev_buf<dfloat> dotPartials;  // one per Ax block (p.Ap partial sums)
+  int nDotPartials = 0;
+  // apply; when dot/doneFlag are given the p.Ap partials are produced and the kernels early-exit
+  void apply(dfloat* q, dfloat* Aq, bool want_dot, const int* doneFlag, cudaStream_t s);
+};
+
+struct libp_precon_s {
+  int kind = 0;  // 0 identity, 1 jacobi, 2 multigrid (later)
+  dlong N = 0;
+  libp_b200::dev_buf<dfloat> invDiag;
+  int allNeumann = 0;
+  libp_hlong NglobalDofs = 0;
+  libp_comm_t comm = nullptr;
+  void* impl = nullptr;  // multigrid hierarchy
+  void apply(const dfloat* r, dfloat* Mr, cudaStream_t s);
+};

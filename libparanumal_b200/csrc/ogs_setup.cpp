@@ -1,0 +1,489 @@
+// Host-side gather-scatter setup: shared-node discovery, unique-owner flagging, local/halo
+// CSR maps and the pairwise exchange lists.
+//
+// Behaviour follows ogsBase_t::Setup (libs/ogs/ogsSetup.cpp:69-190) and the ogsPairwise_t
+// constructor (libs/ogs/ogsPairwise.cpp:194-415) so that every map is bit-identical to the
+// reference's for the same ids in the same call sequence:
+//   * the owner copy of each id group is the (rand() % groupsize)-th record of the group in the
+//     order left by an UNSTABLE std::sort keyed on |id| (ogsSetup.cpp:245-275) -> we call the same
+//     libstdc++ std::sort with an equivalent comparator and the same glibc rand() stream;
+//   * gathered rows are numbered by first appearance in local order, owner rows first
+//     (ogsSetup.cpp:411-433); columns ascend in local id (ogsSetup.cpp:637-663).
+// Collectives go through libp_comm_s (host callbacks; memcpy when size==1).
+#include <algorithm>
+#include <cstdlib>
+#include <numeric>
+
+#include "ogs.hpp"
+
+using namespace libp_b200;
+
+namespace {
+
+struct Node {
+  dlong localId;  // local node id
+  hlong baseId;   // signed global id
+  dlong newId;    // scratch / gathered row id
+  int sign;       // +-1 local group, +-2 group shared between ranks (negative: no owner copy here)
+  int rank;       // origin rank
+  int destRank;   // rendezvous rank = |id| % size
+};
+
+inline hlong habs(hlong v) { return v < 0 ? -v : v; }
+
+// out[key(in[n])] = in[n]
+template <class Key>
+void permute_by(std::vector<Node>& a, Key key) {
+  std::vector<Node> out(a.size());
+  for (const Node& n : a) out[(size_t)key(n)] = n;
+  a.swap(out);
+}
+
+void exchange_nodes(const libp_comm_s& comm, const std::vector<Node>& send, const std::vector<int>& sendCounts,
+                    std::vector<Node>& recv, std::vector<int>& recvCounts) {
+  const int size = comm.size;
+  recvCounts.assign(size, 0);
+  comm.alltoall(sendCounts.data(), recvCounts.data(), sizeof(int));
+  std::vector<int64_t> sc(size), so(size), rc(size), ro(size);
+  int64_t s = 0, r = 0;
+  for (int i = 0; i < size; ++i) {
+    sc[i] = (int64_t)sendCounts[i] * (int64_t)sizeof(Node);
+    so[i] = s;
+    s += sc[i];
+    rc[i] = (int64_t)recvCounts[i] * (int64_t)sizeof(Node);
+    ro[i] = r;
+    r += rc[i];
+  }
+  recv.resize((size_t)(r / (int64_t)sizeof(Node)));
+  comm.alltoallv(send.data(), sc.data(), so.data(), recv.data(), rc.data(), ro.data());
+}
+
+// Flag, for every id group, the owner copy (when unique) and whether the group spans ranks.
+void find_shared_nodes(libp_ogs_s& o, std::vector<Node>& nodes) {
+  const libp_comm_s& comm = *o.comm;
+  const int size = comm.size;
+  std::vector<int> sendCounts(size, 0), sendOffsets(size + 1, 0);
+  for (const Node& n : nodes) sendCounts[n.destRank]++;
+  for (int r = 0; r < size; ++r) sendOffsets[r + 1] = sendOffsets[r] + sendCounts[r];
+  {
+    std::vector<int> fill(size, 0);
+    for (Node& n : nodes) n.newId = sendOffsets[n.destRank] + fill[n.destRank]++;
+  }
+  permute_by(nodes, [](const Node& n) { return n.newId; });  // send order: by destRank, local order inside
+
+  std::vector<Node> recv;
+  std::vector<int> recvCounts;
+  exchange_nodes(comm, nodes, sendCounts, recv, recvCounts);
+  const dlong recvN = (dlong)recv.size();
+  for (dlong n = 0; n < recvN; ++n) recv[n].newId = n;
+
+  // same algorithm + equivalent strict weak order as the reference => same tie order
+  std::sort(recv.begin(), recv.end(), [](const Node& a, const Node& b) { return habs(a.baseId) < habs(b.baseId); });
+
+  int is_unique = 1;
+  dlong start = 0;
+  for (dlong n = 0; n < recvN; ++n) {
+    if (n == recvN - 1 || habs(recv[n].baseId) != habs(recv[n + 1].baseId)) {
+      const dlong end = n + 1;
+      int positiveCount = 0;
+      if (o.unique) {
+        const hlong baseId = habs(recv[start].baseId);
+        const int m = rand() % (end - start);  // glibc stream shared with the embedding program
+        for (dlong i = start; i < end; ++i) recv[i].baseId = -baseId;
+        recv[start + m].baseId = baseId;
+        positiveCount = 1;
+      } else {
+        for (dlong i = start; i < end; ++i)
+          if (recv[i].baseId > 0) positiveCount++;
+        if (positiveCount != 1) is_unique = 0;
+      }
+      LIBP_CHECK(!(o.kind == LIBP_HALO && positiveCount != 1),
+                 "Found " + std::to_string(positiveCount) + " positive Ids for baseId: " +
+                     std::to_string((long long)habs(recv[start].baseId)) + ".");
+      int shared = 1;
+      const int r0 = recv[start].rank;
+      for (dlong i = start + 1; i < end; ++i)
+        if (recv[i].rank != r0) { shared = 2; break; }
+      for (dlong i = start; i < end; ++i) recv[i].sign = shared;
+      start = end;
+    }
+  }
+  int64_t u = is_unique;
+  comm.allreduce_i64(&u, 1, LIBP_MIN);
+  o.gather_defined = (u == 1);
+
+  permute_by(recv, [](const Node& n) { return n.newId; });  // back to arrival order
+  std::vector<Node> back;
+  std::vector<int> backCounts;
+  exchange_nodes(comm, recv, recvCounts, back, backCounts);
+  nodes.swap(back);  // now in send order again, with signs / owner flags filled in
+}
+
+// Number the gathered rows and collect, per shared id, who else holds it.
+void construct_shared_nodes(libp_ogs_s& o, std::vector<Node>& nodes, std::vector<Node>& sharedNodes) {
+  const libp_comm_s& comm = *o.comm;
+  const int size = comm.size;
+  const dlong Nids = (dlong)nodes.size();
+
+  std::sort(nodes.begin(), nodes.end(), [](const Node& a, const Node& b) {
+    if (habs(a.baseId) < habs(b.baseId)) return true;
+    if (habs(a.baseId) > habs(b.baseId)) return false;
+    return a.baseId > b.baseId;  // owner copy leads its group
+  });
+
+  dlong NbaseIds = 0;
+  o.NlocalT = o.NlocalP = o.NhaloT = o.NhaloP = 0;
+  dlong start = 0;
+  for (dlong n = 0; n < Nids; ++n) {
+    if (n == Nids - 1 || habs(nodes[n].baseId) != habs(nodes[n + 1].baseId)) {
+      const dlong end = n + 1;
+      int sign = std::abs(nodes[start].sign);
+      if (nodes[start].baseId < 0) {
+        sign = -sign;
+        for (dlong i = start; i < end; ++i) nodes[i].sign = sign;
+      }
+      if (std::abs(sign) == 1) { o.NlocalT++; if (sign == 1) o.NlocalP++; }
+      else { o.NhaloT++; if (sign == 2) o.NhaloP++; }
+      for (dlong i = start; i < end; ++i) nodes[i].newId = NbaseIds;
+      NbaseIds++;
+      start = end;
+    }
+  }
+  o.Ngather = o.NlocalP + o.NhaloP;
+  int64_t ng = o.Ngather;
+  comm.allreduce_i64(&ng, 1, LIBP_ADD);
+  o.NgatherGlobal = ng;
+
+  std::vector<Node> sendShared;
+  sendShared.reserve((size_t)o.NhaloT);
+  for (dlong n = 0; n < Nids; ++n)
+    if (n == 0 || habs(nodes[n].baseId) != habs(nodes[n - 1].baseId))
+      if (std::abs(nodes[n].sign) == 2) sendShared.push_back(nodes[n]);
+
+  permute_by(nodes, [](const Node& n) { return n.localId; });  // compressed local order
+
+  // renumber groups by first appearance: owner-local, other-local, owner-halo, other-halo
+  std::vector<dlong> indexMap((size_t)NbaseIds, -1);
+  dlong localCntN = 0, localCntT = o.NlocalP, haloCntN = 0, haloCntT = o.NhaloP;
+  for (dlong n = 0; n < Nids; ++n) {
+    const dlong g = nodes[n].newId;
+    if (indexMap[g] == -1) {
+      if (nodes[n].sign == 1) indexMap[g] = localCntN++;
+      else if (nodes[n].sign == -1) indexMap[g] = localCntT++;
+      else if (nodes[n].sign == 2) indexMap[g] = haloCntN++;
+      else indexMap[g] = haloCntT++;
+    }
+    nodes[n].newId = indexMap[g];
+  }
+  for (Node& s : sendShared) s.localId = indexMap[s.newId];
+
+  std::sort(sendShared.begin(), sendShared.end(), [](const Node& a, const Node& b) { return a.destRank < b.destRank; });
+  std::vector<int> sendCounts(size, 0);
+  for (const Node& s : sendShared) sendCounts[s.destRank]++;
+  std::vector<Node> recvShared;
+  std::vector<int> recvCounts;
+  exchange_nodes(comm, sendShared, sendCounts, recvShared, recvCounts);
+
+  std::sort(recvShared.begin(), recvShared.end(),
+            [](const Node& a, const Node& b) { return habs(a.baseId) < habs(b.baseId); });
+
+  const dlong recvN = (dlong)recvShared.size();
+  std::vector<int> shCounts(size, 0), shOffsets(size + 1, 0);
+  start = 0;
+  for (dlong n = 0; n < recvN; ++n)
+    if (n == recvN - 1 || habs(recvShared[n].baseId) != habs(recvShared[n + 1].baseId)) {
+      const dlong end = n + 1;
+      for (dlong i = start; i < end; ++i) shCounts[recvShared[i].rank] += end - start - 1;
+      start = end;
+    }
+  for (int r = 0; r < size; ++r) shOffsets[r + 1] = shOffsets[r] + shCounts[r];
+  std::vector<Node> shSend((size_t)shOffsets[size]);
+  std::vector<int> fill(size, 0);
+  start = 0;
+  for (dlong n = 0; n < recvN; ++n)
+    if (n == recvN - 1 || habs(recvShared[n].baseId) != habs(recvShared[n + 1].baseId)) {
+      const dlong end = n + 1;
+      for (dlong i = start; i < end; ++i) {
+        const int r = recvShared[i].rank;
+        dlong sid = shOffsets[r] + fill[r];
+        for (dlong j = start; j < end; ++j) {
+          if (j == i) continue;
+          shSend[sid] = recvShared[j];       // the other participant (its rank, its gathered row in localId)
+          shSend[sid].newId = recvShared[i].localId;  // receiver's own gathered row for this id
+          shSend[sid].sign = recvShared[i].sign;      // receiver's own ownership flag
+          sid++;
+        }
+        fill[r] += end - start - 1;
+      }
+      start = end;
+    }
+  std::vector<int> shRecvCounts;
+  exchange_nodes(comm, shSend, shCounts, sharedNodes, shRecvCounts);
+}
+
+void build_csr(dlong nrows, const std::vector<dlong>& counts, std::vector<dlong>& rowStarts) {
+  rowStarts.assign((size_t)nrows + 1, 0);
+  for (dlong i = 0; i < nrows; ++i) rowStarts[i + 1] = rowStarts[i] + counts[i];
+}
+
+// gatherLocal / gatherHalo for Signed, Unsigned and Halo kinds
+// (LocalSignedSetup / LocalUnsignedSetup / LocalHaloSetup, ogsSetup.cpp:569-860)
+void local_setup(libp_ogs_s& o, const std::vector<Node>& nodes) {
+  OgsOperator& L = o.gatherLocal;
+  OgsOperator& H = o.gatherHalo;
+  L.Ncols = H.Ncols = o.N;
+  L.NrowsN = o.NlocalP; L.NrowsT = o.NlocalT;
+  H.NrowsN = o.NhaloP;  H.NrowsT = o.NhaloT;
+  const bool isHaloKind = (o.kind == LIBP_HALO);
+  if (isHaloKind) { L.NrowsN = L.NrowsT = 0; }
+  std::vector<dlong> lN((size_t)L.NrowsT, 0), lT((size_t)L.NrowsT, 0), hN((size_t)H.NrowsT, 0), hT((size_t)H.NrowsT, 0);
+  auto inN = [&](const Node& n) {
+    if (o.kind == LIBP_UNSIGNED) return true;
+    if (isHaloKind) return n.sign == 2;
+    return n.baseId > 0;
+  };
+  for (const Node& n : nodes) {
+    if (std::abs(n.sign) == 1) {
+      if (isHaloKind) continue;
+      if (inN(n)) lN[n.newId]++;
+      lT[n.newId]++;
+    } else {
+      if (inN(n)) hN[n.newId]++;
+      hT[n.newId]++;
+    }
+  }
+  build_csr(L.NrowsT, lN, L.rowStartsN); build_csr(L.NrowsT, lT, L.rowStartsT);
+  build_csr(H.NrowsT, hN, H.rowStartsN); build_csr(H.NrowsT, hT, H.rowStartsT);
+  L.colIdsN.assign((size_t)L.nnzN(), 0); L.colIdsT.assign((size_t)L.nnzT(), 0);
+  H.colIdsN.assign((size_t)H.nnzN(), 0); H.colIdsT.assign((size_t)H.nnzT(), 0);
+  std::fill(lN.begin(), lN.end(), 0); std::fill(lT.begin(), lT.end(), 0);
+  std::fill(hN.begin(), hN.end(), 0); std::fill(hT.begin(), hT.end(), 0);
+  for (const Node& n : nodes) {
+    const dlong g = n.newId;
+    if (std::abs(n.sign) == 1) {
+      if (isHaloKind) continue;
+      if (inN(n)) L.colIdsN[L.rowStartsN[g] + lN[g]++] = n.localId;
+      L.colIdsT[L.rowStartsT[g] + lT[g]++] = n.localId;
+    } else {
+      if (inN(n)) H.colIdsN[H.rowStartsN[g] + hN[g]++] = n.localId;
+      H.colIdsT[H.rowStartsT[g] + hT[g]++] = n.localId;
+    }
+  }
+}
+
+// Pairwise exchange lists + post-exchange combine operator (ogsPairwise.cpp:194-415)
+void pairwise_setup(libp_ogs_s& o, std::vector<Node>& sharedNodes) {
+  const libp_comm_s& comm = *o.comm;
+  const int size = comm.size;
+  const dlong Nhalo = o.gatherHalo.NrowsT, NhaloP = o.gatherHalo.NrowsN;
+  std::sort(sharedNodes.begin(), sharedNodes.end(), [](const Node& a, const Node& b) {
+    if (a.rank < b.rank) return true;
+    if (a.rank > b.rank) return false;
+    return a.newId < b.newId;
+  });
+  std::vector<int> sendCountsT(size, 0), sendCountsN(size, 0), recvCountsT(size, 0), recvCountsN(size, 0);
+  for (const Node& s : sharedNodes) {
+    if (s.sign > 0) sendCountsN[s.rank]++;
+    sendCountsT[s.rank]++;
+  }
+  comm.alltoall(sendCountsN.data(), recvCountsN.data(), sizeof(int));
+  for (const Node& s : sharedNodes) {
+    if (s.sign == 2) o.exN.sendIds.push_back(s.newId);
+    o.exT.sendIds.push_back(s.newId);
+  }
+  std::vector<Node> recvNodes;
+  exchange_nodes(comm, sharedNodes, sendCountsT, recvNodes, recvCountsT);
+  const dlong Nrecv = (dlong)recvNodes.size();
+
+  OgsOperator& P = o.postmpi;
+  P.NrowsN = P.NrowsT = Nhalo;
+  P.Ncols = Nhalo + Nrecv;
+  std::vector<dlong> cN((size_t)Nhalo, 0), cT((size_t)Nhalo, 1);
+  for (dlong n = 0; n < NhaloP; ++n) cN[n] = 1;
+  for (const Node& r : recvNodes) {
+    if (r.sign == 2) cN[r.localId]++;
+    cT[r.localId]++;
+  }
+  build_csr(Nhalo, cN, P.rowStartsN); build_csr(Nhalo, cT, P.rowStartsT);
+  P.colIdsN.assign((size_t)P.nnzN(), 0); P.colIdsT.assign((size_t)P.nnzT(), 0);
+  std::fill(cN.begin(), cN.end(), 0); std::fill(cT.begin(), cT.end(), 0);
+  for (dlong n = 0; n < NhaloP; ++n) P.colIdsN[P.rowStartsN[n] + cN[n]++] = n;  // own value first
+  for (dlong n = 0; n < Nhalo; ++n) P.colIdsT[P.rowStartsT[n] + cT[n]++] = n;
+  dlong cnt = Nhalo;
+  for (dlong n = 0; n < Nrecv; ++n) {  // then received copies in arrival (= ascending source rank) order
+    const dlong id = recvNodes[n].localId;
+    if (recvNodes[n].sign == 2) P.colIdsN[P.rowStartsN[id] + cN[id]++] = cnt++;
+    P.colIdsT[P.rowStartsT[id] + cT[id]++] = n + Nhalo;
+  }
+
+  auto compress = [&](const std::vector<int>& sc, const std::vector<int>& rc, ExchangeLists& ex) {
+    int so = 0, ro = 0;
+    for (int r = 0; r < size; ++r) {
+      if (sc[r] > 0) { ex.sendRanks.push_back(r); ex.sendCounts.push_back(sc[r]); ex.sendOffsets.push_back(so); }
+      so += sc[r];
+      if (rc[r] > 0) { ex.recvRanks.push_back(r); ex.recvCounts.push_back(rc[r]); ex.recvOffsets.push_back(ro); }
+      ro += rc[r];
+    }
+    ex.sendOffsets.push_back(so);
+    ex.recvOffsets.push_back(ro);
+  };
+  compress(sendCountsN, recvCountsN, o.exN);
+  compress(sendCountsT, recvCountsT, o.exT);
+}
+
+}  // namespace
+
+void libp_b200::OgsOperator::to_device() {
+  d_rowStartsN.upload(rowStartsN);
+  d_rowStartsT.upload(rowStartsT);
+  d_colIdsN.upload(colIdsN);
+  d_colIdsT.upload(colIdsT);
+}
+
+libp_ogs_s::~libp_ogs_s() {
+  if (ev_ready) cudaEventDestroy(ev_ready);
+  if (ev_done) cudaEventDestroy(ev_done);
+}
+
+void libp_ogs_s::alloc_buffers(size_t bytes_per_node) {
+  const size_t needH = (size_t)std::max<dlong>(postmpi.nnzT(), 1) * bytes_per_node;
+  const size_t needS = (size_t)std::max<dlong>(exT.Nsend(), 1) * bytes_per_node;
+  if (haloBuf.n < needH) haloBuf.alloc(needH);
+  if (sendBuf.n < needS) sendBuf.alloc(needS);
+}
+
+extern "C" int libp_ogs_setup(libp_dlong N, libp_hlong* ids, libp_comm_t comm, int kind, int unique, int verbose,
+                              libp_ogs_t* out) {
+  LIBP_API_BEGIN
+  (void)verbose;
+  LIBP_CHECK(out != nullptr, "null output handle");
+  LIBP_CHECK(comm != nullptr, "null communicator");
+  LIBP_CHECK(N >= 0 && (N == 0 || ids != nullptr), "bad ids");
+  LIBP_CHECK(kind == LIBP_UNSIGNED || kind == LIBP_SIGNED || kind == LIBP_HALO, "bad kind");
+  LIBP_CHECK(!((kind == LIBP_UNSIGNED && unique) || (kind == LIBP_HALO && unique)), "Invalid ogs setup requested");
+  std::unique_ptr<libp_ogs_s> o(new libp_ogs_s());
+  o->comm = comm;
+  o->N = N;
+  o->kind = kind;
+  o->unique = unique != 0;
+  const int rank = comm->rank, size = comm->size;
+
+  std::vector<Node> nodes;
+  nodes.reserve((size_t)N);
+  for (dlong n = 0; n < N; ++n)
+    if (ids[n] != 0) {
+      Node nd;
+      nd.localId = (dlong)nodes.size();
+      nd.baseId = (kind == LIBP_UNSIGNED) ? habs(ids[n]) : ids[n];
+      nd.newId = 0;
+      nd.sign = 0;
+      nd.rank = rank;
+      nd.destRank = (int)(habs(ids[n]) % size);
+      nodes.push_back(nd);
+    }
+  find_shared_nodes(*o, nodes);
+  std::vector<Node> sharedNodes;
+  construct_shared_nodes(*o, nodes, sharedNodes);
+  {
+    size_t c = 0;
+    for (dlong n = 0; n < N; ++n)
+      if (ids[n] != 0) {
+        nodes[c].localId = n;
+        if (o->unique) ids[n] = nodes[c].baseId;
+        c++;
+      }
+  }
+  local_setup(*o, nodes);
+  nodes.clear();
+  nodes.shrink_to_fit();
+  pairwise_setup(*o, sharedNodes);
+
+  // device copies; allowed to fail softly when no GPU is present (CPU-side map tests)
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
+    o->gatherLocal.to_device();
+    o->gatherHalo.to_device();
+    o->postmpi.to_device();
+    o->exN.d_sendIds.upload(o->exN.sendIds);
+    o->exT.d_sendIds.upload(o->exT.sendIds);
+    CUDA_CHECK(cudaEventCreateWithFlags(&o->ev_ready, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&o->ev_done, cudaEventDisableTiming));
+  } else {
+    cudaGetLastError();
+  }
+  *out = o.release();
+  LIBP_API_END
+}
+
+extern "C" int libp_ogs_free(libp_ogs_t ogs) {
+  LIBP_API_BEGIN
+  delete ogs;
+  LIBP_API_END
+}
+
+extern "C" int libp_ogs_info(libp_ogs_t o, libp_ogs_info_t* info) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(o && info, "null argument");
+  info->N = o->N; info->Ngather = o->Ngather;
+  info->NlocalT = o->NlocalT; info->NlocalP = o->NlocalP;
+  info->NhaloT = o->NhaloT; info->NhaloP = o->NhaloP;
+  info->Nhalo = o->NhaloT - o->NhaloP;
+  info->NgatherGlobal = o->NgatherGlobal;
+  info->gather_defined = o->gather_defined ? 1 : 0;
+  info->NranksSendN = (int)o->exN.sendRanks.size(); info->NranksSendT = (int)o->exT.sendRanks.size();
+  info->NranksRecvN = (int)o->exN.recvRanks.size(); info->NranksRecvT = (int)o->exT.recvRanks.size();
+  info->NsendN = o->exN.Nsend(); info->NsendT = o->exT.Nsend();
+  info->NrecvN = o->exN.Nrecv(); info->NrecvT = o->exT.Nrecv();
+  LIBP_API_END
+}
+
+extern "C" int libp_ogs_maps(libp_ogs_t o, int which, libp_dlong* NrowsN, libp_dlong* NrowsT,
+                             const libp_dlong** rowStartsN, const libp_dlong** rowStartsT,
+                             const libp_dlong** colIdsN, const libp_dlong** colIdsT) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(o, "null handle");
+  LIBP_CHECK(which >= 0 && which <= 2, "which must be 0 (local), 1 (halo) or 2 (postmpi)");
+  const OgsOperator& op = which == 0 ? o->gatherLocal : which == 1 ? o->gatherHalo : o->postmpi;
+  if (NrowsN) *NrowsN = op.NrowsN;
+  if (NrowsT) *NrowsT = op.NrowsT;
+  if (rowStartsN) *rowStartsN = op.rowStartsN.data();
+  if (rowStartsT) *rowStartsT = op.rowStartsT.data();
+  if (colIdsN) *colIdsN = op.colIdsN.data();
+  if (colIdsT) *colIdsT = op.colIdsT.data();
+  LIBP_API_END
+}
+
+extern "C" int libp_ogs_exchange_lists(libp_ogs_t o, int trans, libp_dlong* Nsend, const libp_dlong** sendIds,
+                                       int* NranksSend, const int** sendRanks, const int** sendCounts,
+                                       const int** sendOffsets, int* NranksRecv, const int** recvRanks,
+                                       const int** recvCounts, const int** recvOffsets) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(o, "null handle");
+  const ExchangeLists& ex = (trans == LIBP_NOTRANS) ? o->exN : o->exT;
+  if (Nsend) *Nsend = ex.Nsend();
+  if (sendIds) *sendIds = ex.sendIds.data();
+  if (NranksSend) *NranksSend = (int)ex.sendRanks.size();
+  if (sendRanks) *sendRanks = ex.sendRanks.data();
+  if (sendCounts) *sendCounts = ex.sendCounts.data();
+  if (sendOffsets) *sendOffsets = ex.sendOffsets.data();
+  if (NranksRecv) *NranksRecv = (int)ex.recvRanks.size();
+  if (recvRanks) *recvRanks = ex.recvRanks.data();
+  if (recvCounts) *recvCounts = ex.recvCounts.data();
+  if (recvOffsets) *recvOffsets = ex.recvOffsets.data();
+  LIBP_API_END
+}
+
+extern "C" int libp_ogs_global_to_local(libp_ogs_t o, libp_dlong* g2l) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(o && g2l, "null argument");
+  LIBP_CHECK(o->NgatherGlobal != 0, "ogs handle is not set up.");
+  for (dlong n = 0; n < o->N; ++n) g2l[n] = -1;
+  const OgsOperator* ops[2] = {&o->gatherLocal, &o->gatherHalo};
+  const dlong offs[2] = {0, o->NlocalT};
+  for (int w = 0; w < 2; ++w) {
+    const OgsOperator& op = *ops[w];
+    for (dlong r = 0; r < op.NrowsT; ++r)
+      for (dlong g = op.rowStartsT[r]; g < op.rowStartsT[r + 1]; ++g) g2l[op.colIdsT[g]] = r + offs[w];
+  }
+  LIBP_API_END
+}

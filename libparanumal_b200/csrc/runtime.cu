@@ -1,0 +1,180 @@
+// Runtime: error state, device selection, communicator (host callbacks + NCCL via dlopen).
+#include <dlfcn.h>
+#include <mutex>
+
+#include "common.hpp"
+
+namespace libp_b200 {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+}  // namespace libp_b200
+using namespace libp_b200;
+
+extern "C" const char* libp_last_error(void) { return g_err.c_str(); }
+extern "C" const char* libp_b200_version(void) { return "libparanumal_b200 0.1 sm_100a " __DATE__; }
+
+extern "C" int libp_b200_init(int device_id) {
+  LIBP_API_BEGIN
+  int n = 0;
+  CUDA_CHECK(cudaGetDeviceCount(&n));
+  LIBP_CHECK(n > 0, "no CUDA device visible; this library has no CPU fallback");
+  LIBP_CHECK(device_id >= 0 && device_id < n, "device id out of range");
+  CUDA_CHECK(cudaSetDevice(device_id));
+  CUDA_CHECK(cudaFree(0));
+  LIBP_API_END
+}
+
+extern "C" int libp_b200_finish(void* stream) {
+  LIBP_API_BEGIN
+  CUDA_CHECK(cudaStreamSynchronize(as_stream(stream)));
+  LIBP_API_END
+}
+
+// ------------------------------------------------------------------ NCCL (loaded lazily)
+namespace {
+typedef struct { char internal[128]; } ncclUniqueId_;
+typedef void* ncclComm_;
+enum { ncclInt8_ = 0, ncclFloat64_ = 8 };
+enum { ncclSum_ = 0, ncclProd_ = 1, ncclMax_ = 2, ncclMin_ = 3 };
+struct nccl_api {
+  void* h = nullptr;
+  int (*GetUniqueId)(ncclUniqueId_*) = nullptr;
+  int (*CommInitRank)(ncclComm_*, int, ncclUniqueId_, int) = nullptr;
+  int (*CommDestroy)(ncclComm_) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, ncclComm_, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, ncclComm_, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+nccl_api& nccl() {
+  static nccl_api a;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      a.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (a.h) break;
+    }
+    if (!a.h) return;
+#define L(sym) a.sym = reinterpret_cast<decltype(a.sym)>(dlsym(a.h, "nccl" #sym))
+    L(GetUniqueId); L(CommInitRank); L(CommDestroy); L(AllReduce); L(Send); L(Recv);
+    L(GroupStart); L(GroupEnd); L(GetErrorString);
+#undef L
+  });
+  return a;
+}
+void nccl_check(int rc, const char* what) {
+  if (rc != 0) {
+    const char* s = nccl().GetErrorString ? nccl().GetErrorString(rc) : "?";
+    throw error(std::string("NCCL ") + what + " failed: " + s);
+  }
+}
+}  // namespace
+
+extern "C" int libp_comm_create(int rank, int size, const libp_host_collectives_t* host, libp_comm_t* comm) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(comm != nullptr, "null output");
+  LIBP_CHECK(size >= 1 && rank >= 0 && rank < size, "bad rank/size");
+  LIBP_CHECK(size == 1 || host != nullptr, "size>1 needs host collectives for setup");
+  auto* c = new libp_comm_s();
+  c->rank = rank;
+  c->size = size;
+  if (host) { c->host = *host; c->has_host = true; }
+  *comm = c;
+  LIBP_API_END
+}
+
+extern "C" int libp_comm_free(libp_comm_t comm) {
+  LIBP_API_BEGIN
+  if (comm) {
+    if (comm->nccl && nccl().CommDestroy) nccl().CommDestroy(comm->nccl);
+    if (comm->comm_stream) cudaStreamDestroy(comm->comm_stream);
+    delete comm;
+  }
+  LIBP_API_END
+}
+
+extern "C" int libp_comm_rank(libp_comm_t comm, int* rank, int* size) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(comm, "null comm");
+  if (rank) *rank = comm->rank;
+  if (size) *size = comm->size;
+  LIBP_API_END
+}
+
+extern "C" int libp_comm_nccl_unique_id(void* uid128) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(nccl().h && nccl().GetUniqueId, "libnccl.so.2 could not be loaded");
+  ncclUniqueId_ id;
+  nccl_check(nccl().GetUniqueId(&id), "GetUniqueId");
+  memcpy(uid128, &id, 128);
+  LIBP_API_END
+}
+
+extern "C" int libp_comm_nccl_init(libp_comm_t comm, const void* uid128) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(comm, "null comm");
+  LIBP_CHECK(nccl().h && nccl().CommInitRank, "libnccl.so.2 could not be loaded");
+  ncclUniqueId_ id;
+  memcpy(&id, uid128, 128);
+  ncclComm_ c = nullptr;
+  nccl_check(nccl().CommInitRank(&c, comm->size, id, comm->rank), "CommInitRank");
+  comm->nccl = c;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&comm->comm_stream, cudaStreamNonBlocking));
+  LIBP_API_END
+}
+
+// ------------------------------------------------------------------ comm methods
+void libp_comm_s::alltoall(const void* send, void* recv, size_t bytes) const {
+  if (size == 1) { memcpy(recv, send, bytes); return; }
+  LIBP_CHECK(has_host && host.alltoall, "no host alltoall");
+  LIBP_CHECK(host.alltoall(host.ctx, send, recv, bytes) == 0, "host alltoall failed");
+}
+void libp_comm_s::alltoallv(const void* send, const int64_t* sc, const int64_t* so, void* recv, const int64_t* rc,
+                            const int64_t* ro) const {
+  if (size == 1) {
+    if (sc[0]) memcpy(static_cast<char*>(recv) + ro[0], static_cast<const char*>(send) + so[0], (size_t)sc[0]);
+    return;
+  }
+  LIBP_CHECK(has_host && host.alltoallv, "no host alltoallv");
+  LIBP_CHECK(host.alltoallv(host.ctx, send, sc, so, recv, rc, ro) == 0, "host alltoallv failed");
+}
+void libp_comm_s::allreduce_i64(int64_t* inout, int n, int op) const {
+  if (size == 1) return;
+  LIBP_CHECK(has_host && host.allreduce_i64, "no host allreduce");
+  LIBP_CHECK(host.allreduce_i64(host.ctx, inout, n, op) == 0, "host allreduce failed");
+}
+void libp_comm_s::allreduce_f64(double* inout, int n, int op) const {
+  if (size == 1) return;
+  LIBP_CHECK(has_host && host.allreduce_f64, "no host allreduce");
+  LIBP_CHECK(host.allreduce_f64(host.ctx, inout, n, op) == 0, "host allreduce failed");
+}
+void libp_comm_s::allreduce_dev(double* buf, int n, int op, cudaStream_t s) const {
+  if (size == 1) return;
+  LIBP_CHECK(nccl, "communicator has size>1 but NCCL was not initialised (libp_comm_nccl_init)");
+  int nop = op == LIBP_ADD ? ncclSum_ : op == LIBP_MUL ? ncclProd_ : op == LIBP_MAX ? ncclMax_ : ncclMin_;
+  nccl_check(::nccl().AllReduce(buf, buf, (size_t)n, ncclFloat64_, nop, nccl, s), "AllReduce");
+}
+void libp_comm_s::allreduce_sum_dev(double* buf, int n, cudaStream_t s) const { allreduce_dev(buf, n, LIBP_ADD, s); }
+void libp_comm_s::group_start() const { if (size > 1) nccl_check(::nccl().GroupStart(), "GroupStart"); }
+void libp_comm_s::group_end() const { if (size > 1) nccl_check(::nccl().GroupEnd(), "GroupEnd"); }
+void libp_comm_s::send(const void* buf, size_t bytes, int peer, cudaStream_t s) const {
+  LIBP_CHECK(nccl, "NCCL not initialised");
+  nccl_check(::nccl().Send(buf, bytes, ncclInt8_, peer, nccl, s), "Send");
+}
+void libp_comm_s::recv(void* buf, size_t bytes, int peer, cudaStream_t s) const {
+  LIBP_CHECK(nccl, "NCCL not initialised");
+  nccl_check(::nccl().Recv(buf, bytes, ncclInt8_, peer, nccl, s), "Recv");
+}

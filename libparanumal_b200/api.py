@@ -77,8 +77,12 @@ class Comm:
                     rol = [int(ro[i]) for i in range(size)]
                     stot = max((o + c for o, c in zip(sol, scl)), default=0)
                     rtot = max((o + c for o, c in zip(rol, rcl)), default=0)
-                    sarr = np.ctypeslib.as_array(C.cast(send, C.POINTER(C.c_uint8)), (max(stot, 1),))
-                    outs = self._gloo_a2a_lists([torch.from_numpy(sarr[o:o + c].copy()) for o, c in zip(sol, scl)], rcl)
+                    if stot:
+                        sarr = np.ctypeslib.as_array(C.cast(send, C.POINTER(C.c_uint8)), (stot,))
+                        chunks = [torch.from_numpy(sarr[o:o + c].copy()) for o, c in zip(sol, scl)]
+                    else:
+                        chunks = [torch.empty(0, dtype=torch.uint8) for _ in range(size)]
+                    outs = self._gloo_a2a_lists(chunks, rcl)
                     if rtot:
                         rarr = np.ctypeslib.as_array(C.cast(recv, C.POINTER(C.c_uint8)), (rtot,))
                         for o, c, t in zip(rol, rcl, outs):

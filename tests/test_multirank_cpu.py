@@ -1,0 +1,94 @@
+"""world_size>1 checks on CPU (gloo): the C-ABI ogs setup driven by torch.distributed host collectives
+must reproduce the oracle's simulated multi-rank setup (same algorithm as the reference's MPI path)
+map for map: counters, signed ids, local/halo CSR maps, pairwise send lists and post-exchange combine."""
+import ctypes
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle.mesh_box import build_box_hex_mesh, masked_global_ids
+from oracle.ogs_ref import SIGNED, ogs_setup_all
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, size, port, N, n, flag, outq):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        from libparanumal_b200 import _lib as L
+        from libparanumal_b200.api import Comm, Ogs
+        from libparanumal_b200.box_mesh import BoxMesh
+        ctypes.CDLL("libc.so.6").srand(1)  # every MPI rank of the reference is a fresh process
+        mesh = BoxMesh(N, n, n, n, rank, size, flag, geometry=False)
+        _, ids = mesh.masked_global_ids()
+        ids = ids.numpy().copy()
+        comm = Comm(rank, size)
+        ogs = Ogs().Setup(ids.size, ids, comm, kind=L.SIGNED, unique=True)
+        res = dict(rank=rank, ids=ids, counts=[ogs.N, ogs.Ngather, ogs.NlocalT, ogs.NlocalP, ogs.NhaloT, ogs.NhaloP,
+                                                ogs.NgatherGlobal],
+                   local=ogs.maps("local"), halo=ogs.maps("halo"), postmpi=ogs.maps("postmpi"),
+                   exN=ogs.exchange_lists(L.NOTRANS), exT=ogs.exchange_lists(L.TRANS),
+                   g2l=ogs.SetupGlobalToLocalMapping(),
+                   lists=(mesh.localGatherElementList.numpy(), mesh.globalGatherElementList.numpy()))
+        outq.put(res)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("size,N,n,flag", [(2, 3, 4, 1), (4, 2, 4, 1), (8, 2, 4, -1), (3, 2, 5, 1)])
+def test_multirank_ogs_setup_matches_oracle(size, N, n, flag):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, size, port, N, n, flag, q)) for r in range(size)]
+    for p in procs:
+        p.start()
+    results = {}
+    for _ in range(size):
+        r = q.get(timeout=120)
+        results[r["rank"]] = r
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+
+    ids = []
+    for r in range(size):
+        m = build_box_hex_mesh(N, n, n, n, r, size, flag, geometry=False)
+        ids.append(masked_global_ids(m)[1])
+    ref = ogs_setup_all(ids, SIGNED, True)
+    total_halo = 0
+    for r in range(size):
+        got, o = results[r], ref[r]
+        assert got["counts"] == [o.N, o.Ngather, o.NlocalT, o.NlocalP, o.NhaloT, o.NhaloP, o.NgatherGlobal]
+        assert np.array_equal(got["ids"], o.ids)
+        for key, op in (("local", o.gatherLocal), ("halo", o.gatherHalo), ("postmpi", o.exchange.postmpi)):
+            for nm in ("rowStartsN", "rowStartsT", "colIdsN", "colIdsT"):
+                assert np.array_equal(got[key][nm], getattr(op, nm)), (r, key, nm)
+        assert np.array_equal(got["g2l"], o.global_to_local())
+        ex = o.exchange
+        assert np.array_equal(got["exN"]["sendIds"], ex.sendIdsN)
+        assert np.array_equal(got["exT"]["sendIds"], ex.sendIdsT)
+        for key, sc, rc in (("exN", ex.mpiSendCountsN, ex.mpiRecvCountsN), ("exT", ex.mpiSendCountsT, ex.mpiRecvCountsT)):
+            assert np.array_equal(got[key]["sendRanks"], np.nonzero(sc)[0])
+            assert np.array_equal(got[key]["sendCounts"], sc[sc > 0])
+            assert np.array_equal(got[key]["recvRanks"], np.nonzero(rc)[0])
+            assert np.array_equal(got[key]["recvCounts"], rc[rc > 0])
+        total_halo += o.NhaloT
+    assert total_halo > 0  # the partition really shares nodes
+    # global invariants: every unmasked global node owned exactly once
+    nglobal = len(np.unique(np.abs(np.concatenate(ids))[np.concatenate(ids) != 0]))
+    assert ref[0].NgatherGlobal == nglobal

@@ -151,6 +151,13 @@ int libp_ax_hex3d_gather(int Nq, libp_dlong Nelements, const libp_dlong* element
                          const libp_dfloat* wJ, const libp_dfloat* ggeo, const libp_dfloat* D, libp_dfloat lambda,
                          const libp_dfloat* q, libp_dfloat* Aq, void* stream);
 
+/* Tuning knob (not a reference interface): 0 = one-thread-per-column "pencil" kernel that mirrors the
+ * reference's thread layout, 1 = transposed-pencil kernel (default; all contractions in registers). */
+int libp_ax_hex3d_set_variant(int variant);
+/* Development knob, only in builds with -DLIBP_AX_TUNE_GRID (returns LIBP_ERROR otherwise): selects the
+ * prefetch depth / L2 hint / resident-block instantiation of the fused N=7 kernel. */
+int libp_ax_hex3d_tune(int prefetch_slabs, int l2_hints, int min_blocks);
+
 /* ------------------------------------------------------------------ elliptic_t::Operator (C0)
  * solvers/elliptic/src/ellipticOperator.cpp:31-106.  All pointers are device pointers that
  * stay owned by the caller (mesh.o_*, o_GlobalToLocal).                                    */

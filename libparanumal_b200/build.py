@@ -13,6 +13,9 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp",
           "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function"]
+# development builds: LIBP_AX_TUNE_GRID=1 compiles the (prefetch, L2 hint, occupancy) grid of the Ax kernel
+EXTRA = (["-DLIBP_AX_TUNE_GRID"] if os.environ.get("LIBP_AX_TUNE_GRID") == "1" else []) + \
+    os.environ.get("LIBP_NVCC_EXTRA", "").split()
 
 
 def sources():
@@ -35,7 +38,7 @@ def build(force=False, verbose=False, ptxas_info=False):
         o = os.path.join(OBJ, src + ".o")
         objs.append(o)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr):
-            cmd = [NVCC] + ARCH + COMMON + (["-Xptxas", "-v"] if ptxas_info else []) + ["-x", "cu", "-c", s, "-o", o]
+            cmd = [NVCC] + ARCH + COMMON + EXTRA + (["-Xptxas", "-v"] if ptxas_info else []) + ["-x", "cu", "-c", s, "-o", o]
             jobs.append(cmd)
 
     def run(cmd):

@@ -17,14 +17,85 @@
 //   * optional fused epilogue: the ogs gather (Add, Trans) becomes FP64 red.global.add into the
 //     gathered vector, removing the AqL round trip (16 B/node) and the separate gather pass.
 // FP64 tensor cores are deliberately not used (Nq <= 9 contractions).
+#include <algorithm>
+#include <cmath>
+
 #include "common.hpp"
 
 using namespace libp_b200;
 
 namespace {
 
+// defaults of the transposed-pencil kernel (measured on B200, see profiles/ and DESIGN.md)
+#ifndef LIBP_AX_MINB
+#define LIBP_AX_MINB 6
+#endif
+#ifndef LIBP_AX_PF
+#define LIBP_AX_PF 2
+#endif
+#ifndef LIBP_AX_HINT
+#define LIBP_AX_HINT true
+#endif
 constexpr int kMaxNq = 9;
 __constant__ double c_D[kMaxNq * kMaxNq];  // D[i*Nq+m] = phi'_m(r_i), loaded per launch (D2D async)
+// Even-odd factors of a centro-antisymmetric D (GLL: D[N-i][N-m] = -D[i][m]), H = Nq/2:
+//   c_De[i*H+m] = (D[i][m] + D[i][N-m])/2,  c_Do[i*H+m] = (D[i][m] - D[i][N-m])/2      (i,m < H)
+//   c_Dc[i] = D[i][c], c_Dr[m] = D[c][m] for the centre node c = H of odd Nq.
+// They halve the constants a thread keeps in (uniform) registers and cut a pencil contraction from
+// Nq^2 DFMAs to Nq^2/2 DFMAs + 2*Nq DADDs.  The same factors serve D^T ((D^T)e = Do^T, (D^T)o = De^T).
+constexpr int kMaxH = kMaxNq / 2;
+__constant__ double c_De[kMaxH * kMaxH], c_Do[kMaxH * kMaxH], c_Dc[kMaxH], c_Dr[kMaxH];
+
+__global__ void even_odd_factors_kernel(int Nq, const double* __restrict__ D, double* __restrict__ out) {
+  const int H = Nq / 2, N = Nq - 1, t = threadIdx.x;
+  double* De = out; double* Do = out + kMaxH * kMaxH; double* Dc = Do + kMaxH * kMaxH; double* Dr = Dc + kMaxH;
+  if (t < H * H) {
+    const int i = t / H, m = t - i * H;
+    De[t] = 0.5 * (D[i * Nq + m] + D[i * Nq + N - m]);
+    Do[t] = 0.5 * (D[i * Nq + m] - D[i * Nq + N - m]);
+  }
+  if (t < H) {
+    Dc[t] = (Nq & 1) ? D[t * Nq + H] : 0.0;
+    Dr[t] = (Nq & 1) ? D[H * Nq + t] : 0.0;
+  }
+}
+
+// o = D v (kT = false) or o = D^T v (kT = true) on a register pencil.
+template <int Nq, bool kSym, bool kT>
+__device__ __forceinline__ void pencil_apply(const dfloat (&v)[Nq], dfloat (&o)[Nq]) {
+  if (!kSym) {
+#pragma unroll
+    for (int i = 0; i < Nq; ++i) {
+      dfloat s = 0.0;
+#pragma unroll
+      for (int m = 0; m < Nq; ++m) s += (kT ? c_D[m * Nq + i] : c_D[i * Nq + m]) * v[m];
+      o[i] = s;
+    }
+  } else {
+    constexpr int H = Nq / 2, N = Nq - 1;
+    dfloat ve[H > 0 ? H : 1], vo[H > 0 ? H : 1];
+#pragma unroll
+    for (int m = 0; m < H; ++m) { ve[m] = v[m] + v[N - m]; vo[m] = v[m] - v[N - m]; }
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      dfloat E = 0.0, O = 0.0;
+      if (Nq & 1) E = (kT ? c_Dr[i] : c_Dc[i]) * v[H];
+#pragma unroll
+      for (int m = 0; m < H; ++m) {
+        E += (kT ? c_Do[m * H + i] : c_De[i * H + m]) * ve[m];
+        O += (kT ? c_De[m * H + i] : c_Do[i * H + m]) * vo[m];
+      }
+      o[i] = E + O;
+      o[N - i] = O - E;
+    }
+    if (Nq & 1) {
+      dfloat s = 0.0;
+#pragma unroll
+      for (int m = 0; m < H; ++m) s += (kT ? c_Dc[m] : c_Dr[m]) * vo[m];
+      o[H] = s;
+    }
+  }
+}
 
 template <int Nq>
 struct AxCfg {
@@ -182,13 +253,288 @@ ax_hex3d_kernel(const dlong Nelements, const dlong* __restrict__ elementList, co
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Variant 1 ("transposed pencils").  The pencil kernel above reads ~50 doubles of shared memory
+// per node (every 1-D contraction output re-reads a row/column of the slab), which on B200 costs
+// more SM cycles than the node's 64 B of HBM traffic (128 B/clk/SM of shared-memory bandwidth
+// against ~23 B/clk/SM of HBM).  Here every 1-D contraction runs on a pencil held in registers
+// against D taken from the constant bank with compile-time indices (DFMA with a c[][] operand),
+// and shared memory is used only to re-distribute the element between the three pencil
+// orientations: ~15 doubles of shared-memory traffic per node instead of ~50.
+//   layout C: thread (i,j) owns the k-pencil   (global loads/stores, geometric factors, t-derivative)
+//   layout A: thread (j,k) owns the i-pencil   (r-derivative, 128-bit row accesses)
+//   layout B: thread (i,k) owns the j-pencil   (s-derivative, column accesses)
+// Row stride LD and slab stride SS are padded so that all three access patterns are
+// bank-conflict free for Nq = 8 (LD/2 odd for the 128-bit rows, SS = 8 mod 16 for the columns,
+// and layout C pairs rows j and j+4 inside a half-warp: 4*LD = 8 mod 16).
+// L2 residency hints: the geometric factors are a pure stream (each byte used once per apply) and
+// must not push the re-used q / Aq lines out of the 126 MB L2, so they are loaded evict-first and
+// bypass L1; q gathers and the Aq reductions are marked evict-last.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ dfloat ld_stream(const dfloat* p, uint64_t pol) {
+  dfloat v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ dlong ld_stream_i(const dlong* p, uint64_t pol) {
+  dlong v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ dfloat ld_keep(const dfloat* p, uint64_t pol) {
+  dfloat v;
+  asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void red_keep(dfloat* p, dfloat v, uint64_t pol) {
+  asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+
+// 128-bit row accesses of a padded shared-memory row (rows are 16-byte aligned; odd Nq spills one
+// element into the row padding)
 template <int Nq>
-int launch(bool gather, bool fused, dlong Nelements, const dlong* elementList, const dlong* G2L, const dfloat* wJ,
-           const dfloat* ggeo, dfloat lambda, const dfloat* q, dfloat* Aq, dfloat* dotPartials, const int* doneFlag,
-           cudaStream_t s) {
+__device__ __forceinline__ void load_row(const dfloat* __restrict__ row, dfloat (&v)[Nq]) {
+#pragma unroll
+  for (int c = 0; c < Nq / 2; ++c) {
+    const double2 w = *reinterpret_cast<const double2*>(row + 2 * c);
+    v[2 * c] = w.x; v[2 * c + 1] = w.y;
+  }
+  if (Nq & 1) v[Nq - 1] = row[Nq - 1];
+}
+template <int Nq>
+__device__ __forceinline__ void store_row(dfloat* __restrict__ row, const dfloat (&o)[Nq]) {
+#pragma unroll
+  for (int c = 0; c < Nq / 2; ++c) *reinterpret_cast<double2*>(row + 2 * c) = make_double2(o[2 * c], o[2 * c + 1]);
+  if (Nq & 1) row[Nq - 1] = o[Nq - 1];
+}
+
+template <int Nq>
+struct AxT {
+  static constexpr int Nq2 = Nq * Nq;
+  static constexpr int Np = Nq * Nq * Nq;
+  static constexpr int EPB = (Nq2 >= 64) ? 1 : (64 / Nq2);
+  static constexpr int Work = EPB * Nq2;
+  static constexpr int Threads = ((Work + 31) / 32) * 32;
+  static constexpr int LD = (Nq % 2 == 0) ? Nq + 2 : Nq + 1;  // even: rows are 16-byte aligned
+  static constexpr int SS0 = Nq * LD;
+  static constexpr int SS = SS0 + ((8 - (SS0 % 16)) + 16) % 16;  // SS = 8 mod 16, even
+  static constexpr int NPAIR = (Nq + 1) / 2;                      // double2 per row
+};
+
+// PF = geometric-factor slabs in flight per thread, kHint = L2 residency hints on/off
+template <int Nq, bool kGather, bool kFused, bool kDot, int PF, bool kHint, int kMinB, bool kSym>
+__global__ void __launch_bounds__(AxT<Nq>::Threads, (AxT<Nq>::Threads <= 64) ? kMinB : 3)
+ax_hex3d_t_kernel(const dlong Nelements, const dlong* __restrict__ elementList, const dlong* __restrict__ G2L,
+                  const dfloat* __restrict__ wJ, const dfloat* __restrict__ ggeo, const dfloat lambda,
+                  const dfloat* __restrict__ q, dfloat* __restrict__ Aq, dfloat* __restrict__ dotPartials,
+                  const int* __restrict__ doneFlag) {
+  if (doneFlag != nullptr && *doneFlag) return;
+  using C = AxT<Nq>;
+  constexpr int Nq2 = C::Nq2, Np = C::Np, LD = C::LD, SS = C::SS;
+  static_assert(PF >= 1 && PF <= Nq, "prefetch depth");
+  __shared__ __align__(16) dfloat s_u[C::EPB * Nq * SS];
+  __shared__ __align__(16) dfloat s_r[C::EPB * Nq * SS];
+  __shared__ __align__(16) dfloat s_s[C::EPB * Nq * SS];
+
+  const int t = threadIdx.x;
+  const bool valid = t < C::Work;
+  const int es = valid ? t / Nq2 : 0;
+  const int ij = valid ? t - es * Nq2 : 0;
+  const int b = ij / Nq, a = ij - b * Nq;
+  // layout C: i = a, j = jc.  For Nq = 8 a half-warp holds rows jc and jc+4 (conflict-free with LD = 10).
+  const int jc = (Nq == 8) ? (4 * (b & 1) + (b >> 1)) : b;
+  const int nC = jc * Nq + a;                 // node offset inside a k-slab (global arrays)
+  const int sC = es * Nq * SS + jc * LD + a;  // shared offset of (k=0, jc, a); slab k adds k*SS
+  const int sA = es * Nq * SS + b * SS + a * LD;  // layout A: row (k=b, j=a, i=0..)
+  const int sB = es * Nq * SS + b * SS + a;       // layout B: column (k=b, j=0.., i=a); j adds LD
+
+  const dlong ei = (dlong)blockIdx.x * C::EPB + es;
+  const bool active = valid && ei < Nelements;
+  const dlong e = active ? (elementList ? elementList[ei] : ei) : 0;
+  const size_t ebase = (size_t)e * Np + nC;
+
+  // ---- issue the connectivity loads first, then the first geometric-factor slabs, then the q gathers
+  const uint64_t polS = kHint ? policy_evict_first() : 0, polK = kHint ? policy_evict_last() : 0;
+  dlong r_id[Nq];
+  if (kGather) {
+#pragma unroll
+    for (int k = 0; k < Nq; ++k)
+      r_id[k] = active ? (kHint ? ld_stream_i(G2L + ebase + k * Nq2, polS) : __ldg(G2L + ebase + k * Nq2)) : -1;
+  }
+  auto ldgeo = [&](const dfloat* p) -> dfloat { return kHint ? ld_stream(p, polS) : __ldg(p); };
+  const dfloat* __restrict__ gptr = ggeo + (size_t)e * 6 * Np + nC;
+  const dfloat* __restrict__ wptr = wJ + ebase;
+  const bool screened = (lambda != 0.0);
+  dfloat g[PF][7];
+#pragma unroll
+  for (int p = 0; p < PF; ++p) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) g[p][c] = active ? ldgeo(gptr + p * Nq2 + c * Np) : 0.0;
+    g[p][6] = (active && screened) ? ldgeo(wptr + p * Nq2) : 0.0;
+  }
+  dfloat r_q[Nq];
+#pragma unroll
+  for (int k = 0; k < Nq; ++k) {
+    if (kGather) r_q[k] = (r_id[k] >= 0) ? (kHint ? ld_keep(q + r_id[k], polK) : q[r_id[k]]) : 0.0;
+    else r_q[k] = active ? q[ebase + k * Nq2] : 0.0;
+  }
+
+  // ---- phase 0 (layout C): publish u, t-derivative in registers
+  if (valid) {
+#pragma unroll
+    for (int k = 0; k < Nq; ++k) s_u[sC + k * SS] = r_q[k];
+  }
+  dfloat r_t[Nq];  // qt, later Gqt
+  pencil_apply<Nq, kSym, false>(r_q, r_t);
+  __syncthreads();
+
+  // ---- phase 1: r-derivative on i-pencils (layout A), s-derivative on j-pencils (layout B)
+  if (valid) {
+    dfloat v[Nq], o[Nq];
+    load_row<Nq>(&s_u[sA], v);
+    pencil_apply<Nq, kSym, false>(v, o);
+    store_row<Nq>(&s_r[sA], o);
+#pragma unroll
+    for (int m = 0; m < Nq; ++m) v[m] = s_u[sB + m * LD];
+    pencil_apply<Nq, kSym, false>(v, o);
+#pragma unroll
+    for (int j = 0; j < Nq; ++j) s_s[sB + j * LD] = o[j];
+  }
+  __syncthreads();
+
+  // ---- phase 2 (layout C): geometric factors, slab by slab, loads PF slabs ahead
+  dfloat r_Aq[Nq];
+#pragma unroll
+  for (int k = 0; k < Nq; ++k) {
+    const dfloat qr = s_r[sC + k * SS], qs = s_s[sC + k * SS], qt = r_t[k];
+    const dfloat G00 = g[k % PF][0], G01 = g[k % PF][1], G02 = g[k % PF][2];
+    const dfloat G11 = g[k % PF][3], G12 = g[k % PF][4], G22 = g[k % PF][5], GwJ = g[k % PF][6];
+    if (k + PF < Nq) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) g[k % PF][c] = active ? ldgeo(gptr + (k + PF) * Nq2 + c * Np) : 0.0;
+      g[k % PF][6] = (active && screened) ? ldgeo(wptr + (k + PF) * Nq2) : 0.0;
+    }
+    if (valid) {
+      s_r[sC + k * SS] = G00 * qr + G01 * qs + G02 * qt;
+      s_s[sC + k * SS] = G01 * qr + G11 * qs + G12 * qt;
+    }
+    r_t[k] = G02 * qr + G12 * qs + G22 * qt;
+    r_Aq[k] = screened ? GwJ * lambda * s_u[sC + k * SS] : 0.0;  // u is re-read: not kept in registers
+  }
+  {
+    dfloat o[Nq];
+    pencil_apply<Nq, kSym, true>(r_t, o);
+#pragma unroll
+    for (int k = 0; k < Nq; ++k) r_Aq[k] += o[k];
+  }
+  __syncthreads();
+
+  // ---- phase 3: transposed derivatives, in place (each thread rewrites exactly what it read)
+  if (valid) {
+    dfloat v[Nq], o[Nq];
+    load_row<Nq>(&s_r[sA], v);
+    pencil_apply<Nq, kSym, true>(v, o);
+    store_row<Nq>(&s_r[sA], o);
+#pragma unroll
+    for (int m = 0; m < Nq; ++m) v[m] = s_s[sB + m * LD];
+    pencil_apply<Nq, kSym, true>(v, o);
+#pragma unroll
+    for (int j = 0; j < Nq; ++j) s_s[sB + j * LD] = o[j];
+  }
+  __syncthreads();
+
+  // ---- phase 4 (layout C): collect, optional p.Ap partial, store / scatter-add
+#pragma unroll
+  for (int k = 0; k < Nq; ++k) r_Aq[k] += s_r[sC + k * SS] + s_s[sC + k * SS];
+
+  if (kDot) {
+    dfloat d = 0.0;
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < Nq; ++k) d += s_u[sC + k * SS] * r_Aq[k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_down_sync(0xffffffffu, d, o);
+    __shared__ dfloat s_dot[C::Threads / 32];
+    if ((t & 31) == 0) s_dot[t >> 5] = d;
+    __syncthreads();
+    if (t == 0) {
+      dfloat tot = 0.0;
+#pragma unroll
+      for (int w = 0; w < C::Threads / 32; ++w) tot += s_dot[w];
+      dotPartials[blockIdx.x] = tot;
+    }
+  }
+  if (!active) return;
+  if (kFused) {
+#pragma unroll
+    for (int k = 0; k < Nq; ++k)
+      if (r_id[k] >= 0) {
+        if (kHint) red_keep(&Aq[r_id[k]], r_Aq[k], polK);
+        else atomicAdd(&Aq[r_id[k]], r_Aq[k]);
+      }
+  } else {
+#pragma unroll
+    for (int k = 0; k < Nq; ++k) Aq[ebase + k * Nq2] = r_Aq[k];
+  }
+}
+
+int g_variant = 1;                     // 0 = pencil kernel, 1 = transposed-pencil kernel
+int g_pf = 2, g_hint = 1, g_minb = 6;  // tuning state of variant 1 (libp_ax_hex3d_tune)
+
+// Default instantiation for every order; for the fused N=7 kernels (the headline path) a small grid of
+// (prefetch depth, L2 hints, resident blocks) is compiled so the choice can be measured on the device.
+template <int Nq, bool G, bool F, bool DOT, bool SYM>
+void launch_t(int grid, dlong Nelements, const dlong* elementList, const dlong* G2L, const dfloat* wJ,
+              const dfloat* ggeo, dfloat lambda, const dfloat* q, dfloat* Aq, dfloat* dotPartials,
+              const int* doneFlag, cudaStream_t s) {
+#define GOT(PF, H, MB)                                                                                        \
+  ax_hex3d_t_kernel<Nq, G, F, DOT, PF, H, MB, SYM><<<grid, AxT<Nq>::Threads, 0, s>>>(                         \
+      Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag)
+#ifdef LIBP_AX_TUNE_GRID
+  if constexpr (Nq == 8 && G && F && SYM && !DOT) {
+#define ROW(PF, H)                                        \
+    if (g_pf == PF && g_hint == H) {                      \
+      if (g_minb == 4) { GOT(PF, H, 4); return; }         \
+      if (g_minb == 6) { GOT(PF, H, 6); return; }         \
+      if (g_minb == 8) { GOT(PF, H, 8); return; }         \
+      if (g_minb == 10) { GOT(PF, H, 10); return; }       \
+    }
+    ROW(1, true) ROW(2, true) ROW(3, true) ROW(4, true) ROW(2, false)
+#undef ROW
+  }
+#endif
+  GOT(LIBP_AX_PF, LIBP_AX_HINT, LIBP_AX_MINB);
+#undef GOT
+}
+
+template <int Nq>
+int launch(bool gather, bool fused, bool sym, dlong Nelements, const dlong* elementList, const dlong* G2L,
+           const dfloat* wJ, const dfloat* ggeo, dfloat lambda, const dfloat* q, dfloat* Aq, dfloat* dotPartials,
+           const int* doneFlag, cudaStream_t s) {
   using C = AxCfg<Nq>;
   const int grid = (int)((Nelements + C::EPB - 1) / C::EPB);
-#define GO(G, F, DOT) ax_hex3d_kernel<Nq, G, F, DOT><<<grid, C::Threads, 0, s>>>(Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag)
+#define ARGS grid, Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag, s
+#define GO(G, F, DOT)                                                                                         \
+  do {                                                                                                        \
+    if (g_variant == 1) {                                                                                     \
+      if (sym) launch_t<Nq, G, F, DOT, true>(ARGS);                                                           \
+      else launch_t<Nq, G, F, DOT, false>(ARGS);                                                              \
+    } else {                                                                                                  \
+      ax_hex3d_kernel<Nq, G, F, DOT><<<grid, C::Threads, 0, s>>>(Nelements, elementList, G2L, wJ, ggeo, lambda, \
+                                                                 q, Aq, dotPartials, doneFlag);               \
+    }                                                                                                         \
+  } while (0)
   if (dotPartials) {
     if (fused) GO(true, true, true);
     else if (gather) GO(true, false, true);
@@ -199,38 +545,64 @@ int launch(bool gather, bool fused, dlong Nelements, const dlong* elementList, c
     else GO(false, false, false);
   }
 #undef GO
+#undef ARGS
   CUDA_CHECK(cudaGetLastError());
   return grid;
 }
 
-const dfloat* g_cD_owner = nullptr;  // device pointer whose contents currently sit in c_D
+const dfloat* g_cD_owner = nullptr;  // device pointer whose contents currently sit in c_D (+ even-odd factors)
 int g_cD_nq = 0;
+bool g_cD_sym = false;
+dfloat* g_eo_scratch = nullptr;  // device staging of the even-odd factors
 
 }  // namespace
 
 namespace libp_b200 {
 
-// trusted==true: the caller guarantees D is immutable (operator handles) so the constant bank is
-// only reloaded when a different D pointer / order is used.
+// trusted_D: the caller guarantees D is immutable (operator handles), so the constant bank is only
+// reloaded when a different D pointer / order is used.  sym: D was verified centro-antisymmetric
+// (libp_elliptic_create does that once), which enables the even-odd contractions.
 // Returns the number of blocks launched (= number of dotPartials written when dotPartials != nullptr).
-int ax_hex3d_launch(int Nq, bool fused, bool trusted_D, dlong Nelements, const dlong* elementList, const dlong* G2L,
-                    const dfloat* wJ, const dfloat* ggeo, const dfloat* D, dfloat lambda, const dfloat* q,
-                    dfloat* Aq, dfloat* dotPartials, const int* doneFlag, cudaStream_t s) {
+int ax_hex3d_launch(int Nq, bool fused, bool trusted_D, bool sym, dlong Nelements, const dlong* elementList,
+                    const dlong* G2L, const dfloat* wJ, const dfloat* ggeo, const dfloat* D, dfloat lambda,
+                    const dfloat* q, dfloat* Aq, dfloat* dotPartials, const int* doneFlag, cudaStream_t s) {
   LIBP_CHECK(Nq >= 2 && Nq <= kMaxNq, "Nq must be in [2, 9]");
   LIBP_CHECK(!fused || G2L != nullptr, "fused gather needs GlobalToLocal");
   if (Nelements <= 0) return 0;
-  if (!(trusted_D && g_cD_owner == D && g_cD_nq == Nq)) {
+  if (!(trusted_D && g_cD_owner == D && g_cD_nq == Nq && (g_cD_sym || !sym))) {
     CUDA_CHECK(cudaMemcpyToSymbolAsync(c_D, D, sizeof(dfloat) * Nq * Nq, 0, cudaMemcpyDeviceToDevice, s));
+    if (sym) {
+      constexpr int HH = kMaxH * kMaxH;
+      if (!g_eo_scratch) CUDA_CHECK(cudaMalloc(&g_eo_scratch, sizeof(dfloat) * (2 * HH + 2 * kMaxH)));
+      even_odd_factors_kernel<<<1, 32, 0, s>>>(Nq, D, g_eo_scratch);
+      CUDA_CHECK(cudaGetLastError());
+      CUDA_CHECK(cudaMemcpyToSymbolAsync(c_De, g_eo_scratch, sizeof(dfloat) * HH, 0, cudaMemcpyDeviceToDevice, s));
+      CUDA_CHECK(cudaMemcpyToSymbolAsync(c_Do, g_eo_scratch + HH, sizeof(dfloat) * HH, 0, cudaMemcpyDeviceToDevice, s));
+      CUDA_CHECK(cudaMemcpyToSymbolAsync(c_Dc, g_eo_scratch + 2 * HH, sizeof(dfloat) * kMaxH, 0, cudaMemcpyDeviceToDevice, s));
+      CUDA_CHECK(cudaMemcpyToSymbolAsync(c_Dr, g_eo_scratch + 2 * HH + kMaxH, sizeof(dfloat) * kMaxH, 0, cudaMemcpyDeviceToDevice, s));
+    }
     g_cD_owner = trusted_D ? D : nullptr;
     g_cD_nq = Nq;
+    g_cD_sym = sym;
   }
   const bool gather = G2L != nullptr;
   switch (Nq) {
-#define CASE(n) case n: return launch<n>(gather, fused, Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag, s);
+#define CASE(n) case n: return launch<n>(gather, fused, sym, Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag, s);
     CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9)
 #undef CASE
   }
   return 0;
+}
+// Is D centro-antisymmetric (D[N-i][N-m] == -D[i][m]) to rounding?  True for any GLL derivative matrix.
+bool ax_hex3d_D_is_centro_antisymmetric(int Nq, const dfloat* D_host) {
+  double mx = 0.0, dev = 0.0;
+  for (int i = 0; i < Nq; ++i)
+    for (int m = 0; m < Nq; ++m) {
+      const double a = D_host[i * Nq + m], b = D_host[(Nq - 1 - i) * Nq + (Nq - 1 - m)];
+      mx = std::max(mx, std::abs(a));
+      dev = std::max(dev, std::abs(a + b));
+    }
+  return dev <= 1e-13 * mx;
 }
 int ax_hex3d_blocks(int Nq, dlong Nelements) {
   const int nq2 = Nq * Nq;
@@ -240,13 +612,31 @@ int ax_hex3d_blocks(int Nq, dlong Nelements) {
 
 }  // namespace libp_b200
 
+extern "C" int libp_ax_hex3d_set_variant(int variant) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(variant == 0 || variant == 1, "variant must be 0 (pencil) or 1 (transposed pencils)");
+  g_variant = variant;
+  LIBP_API_END
+}
+
+extern "C" int libp_ax_hex3d_tune(int prefetch_slabs, int l2_hints, int min_blocks) {
+  LIBP_API_BEGIN
+#ifndef LIBP_AX_TUNE_GRID
+  throw error("library was built without LIBP_AX_TUNE_GRID");
+#endif
+  LIBP_CHECK(prefetch_slabs >= 1 && prefetch_slabs <= 4, "prefetch_slabs in [1,4]");
+  LIBP_CHECK(min_blocks == 4 || min_blocks == 6 || min_blocks == 8 || min_blocks == 10, "min_blocks in {4,6,8,10}");
+  g_pf = prefetch_slabs; g_hint = l2_hints ? 1 : 0; g_minb = min_blocks;
+  LIBP_API_END
+}
+
 extern "C" int libp_ax_hex3d(int Nq, libp_dlong Nelements, const libp_dlong* elementList,
                              const libp_dlong* GlobalToLocal, const libp_dfloat* wJ, const libp_dfloat* ggeo,
                              const libp_dfloat* D, libp_dfloat lambda, const libp_dfloat* q, libp_dfloat* AqL,
                              void* stream) {
   LIBP_API_BEGIN
   LIBP_CHECK(Nelements == 0 || (wJ && ggeo && D && q && AqL), "null device pointer");
-  ax_hex3d_launch(Nq, false, false, Nelements, elementList, GlobalToLocal, wJ, ggeo, D, lambda, q, AqL,
+  ax_hex3d_launch(Nq, false, false, false, Nelements, elementList, GlobalToLocal, wJ, ggeo, D, lambda, q, AqL,
                   nullptr, nullptr, as_stream(stream));
   LIBP_API_END
 }
@@ -257,7 +647,7 @@ extern "C" int libp_ax_hex3d_gather(int Nq, libp_dlong Nelements, const libp_dlo
                                     void* stream) {
   LIBP_API_BEGIN
   LIBP_CHECK(Nelements == 0 || (GlobalToLocal && wJ && ggeo && D && q && Aq), "null device pointer");
-  ax_hex3d_launch(Nq, true, false, Nelements, elementList, GlobalToLocal, wJ, ggeo, D, lambda, q, Aq,
+  ax_hex3d_launch(Nq, true, false, false, Nelements, elementList, GlobalToLocal, wJ, ggeo, D, lambda, q, Aq,
                   nullptr, nullptr, as_stream(stream));
   LIBP_API_END
 }

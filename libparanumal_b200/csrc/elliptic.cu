@@ -19,7 +19,7 @@ void libp_elliptic_s::apply(dfloat* q, dfloat* Aq, bool want_dot, const int* don
   int doff = 0;
   auto ax = [&](dlong n, const dlong* list) {
     if (n <= 0) return;
-    int nb = ax_hex3d_launch(d.Nq, fused, true, n, list, d.GlobalToLocal, d.wJ, d.ggeo, d.D, d.lambda, q, out,
+    int nb = ax_hex3d_launch(d.Nq, fused, true, symD, n, list, d.GlobalToLocal, d.wJ, d.ggeo, d.D, d.lambda, q, out,
                              dp ? dp + doff : nullptr, doneFlag, s);
     doff += nb;
   };
@@ -65,6 +65,11 @@ extern "C" int libp_elliptic_create(const libp_elliptic_desc_t* desc, libp_ellip
   std::unique_ptr<libp_elliptic_s> e(new libp_elliptic_s());
   e->d = *desc;
   e->Np = desc->Nq * desc->Nq * desc->Nq;
+  {
+    double hD[81];
+    CUDA_CHECK(cudaMemcpy(hD, desc->D, sizeof(double) * desc->Nq * desc->Nq, cudaMemcpyDeviceToHost));
+    e->symD = ax_hex3d_D_is_centro_antisymmetric(desc->Nq, hD);
+  }
   e->Ndofs = desc->ogsMasked->Ngather;
   e->Nhalo = desc->ogsMasked->NhaloT - desc->ogsMasked->NhaloP;
   if (desc->mode == 0) e->AqL.alloc((size_t)desc->Nelements * e->Np);

@@ -4,9 +4,10 @@
 #include "ogs.hpp"
 
 namespace libp_b200 {
-int ax_hex3d_launch(int Nq, bool fused, bool trusted_D, dlong Nelements, const dlong* elementList, const dlong* G2L,
-                    const dfloat* wJ, const dfloat* ggeo, const dfloat* D, dfloat lambda, const dfloat* q,
-                    dfloat* Aq, dfloat* dotPartials, const int* doneFlag, cudaStream_t s);
+int ax_hex3d_launch(int Nq, bool fused, bool trusted_D, bool sym, dlong Nelements, const dlong* elementList,
+                    const dlong* G2L, const dfloat* wJ, const dfloat* ggeo, const dfloat* D, dfloat lambda,
+                    const dfloat* q, dfloat* Aq, dfloat* dotPartials, const int* doneFlag, cudaStream_t s);
+bool ax_hex3d_D_is_centro_antisymmetric(int Nq, const dfloat* D_host);
 int ax_hex3d_blocks(int Nq, dlong Nelements);
 void ogs_gather_start_f64(libp_ogs_s& o, double* gv, const double* v, int op, int trans, cudaStream_t s);
 void ogs_gather_finish_f64(libp_ogs_s& o, double* gv, const double* v, int op, int trans, cudaStream_t s);
@@ -19,6 +20,7 @@ void halo_combine_finish_f64(libp_ogs_s& o, cudaStream_t s);
 struct libp_elliptic_s {
   libp_elliptic_desc_t d{};
   int Np = 0;
+  bool symD = false;  // D verified centro-antisymmetric at create time -> even-odd contractions
   dlong Ndofs = 0, Nhalo = 0;
   libp_b200::dev_buf<dfloat> AqL;          // mode 0 scratch, Nelements*Np
   libp_b200::dev_buf<dfloat> dotPartials;  // one per Ax block (p.Ap partial sums)

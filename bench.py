@@ -34,12 +34,13 @@ METRIC = "GDOF/s (FP64) hex N=7 Ax & PCG solve at 1/2/4/8 B200; % HBM roofline"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--degree", type=int, default=7)
     ap.add_argument("--elements", type=int, default=64, help="global box is elements^3")
-    ap.add_argument("--cpu-elements", type=int, default=16, help="box edge of the bounded CPU sample")
+    ap.add_argument("--cpu-elements", type=int, default=24, help="box edge of the bounded CPU sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
     ap.add_argument("--pcg-iters", type=int, default=40)
     ap.add_argument("--mode", type=int, default=1, help="1 fused gather epilogue, 0 reference data flow")
     ap.add_argument("--no-pcg", action="store_true")
@@ -99,8 +100,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_ax_sample(N, n, steps, warmup):
-    """Oracle C port (OpenMP, all host threads) of the same operator apply on an n^3 box."""
+def cpu_ax_sample(N, n, steps, warmup, seconds=None):
+    """Oracle C port (OpenMP, all host threads) of the same operator apply on an n^3 box.
+    With `seconds` the number of applies is chosen so the timed loop lasts about that long."""
     from oracle import elliptic_ref as er
     from oracle.mesh_box import build_box_hex_mesh, masked_global_ids
     from oracle.ogs_ref import SIGNED, ogs_setup_all
@@ -112,11 +114,16 @@ def cpu_ax_sample(N, n, steps, warmup):
     rs, ci = o.gatherLocal.rowStartsT, o.gatherLocal.colIdsT
     for _ in range(warmup):
         er.operator(N + 1, G2L, m.wJ, m.ggeo, m.D, 0.0, rs, ci, q)
+    if seconds is not None:
+        t0 = time.perf_counter()
+        er.operator(N + 1, G2L, m.wJ, m.ggeo, m.D, 0.0, rs, ci, q)
+        one = max(time.perf_counter() - t0, 1e-6)
+        steps = int(min(max(seconds / one, 3), 5000))
     t0 = time.perf_counter()
     for _ in range(steps):
         er.operator(N + 1, G2L, m.wJ, m.ggeo, m.D, 0.0, rs, ci, q)
     dt = (time.perf_counter() - t0) / steps
-    return o.Ngather / dt / 1e9, dt, er.num_threads(), o.Ngather
+    return o.Ngather / dt / 1e9, dt, er.num_threads(), o.Ngather, steps
 
 
 def run_reference(args):
@@ -125,8 +132,12 @@ def run_reference(args):
         return
     N, n = args.degree, args.cpu_elements
     # keep the whole run within a few minutes: ~0.3 s per apply at 16^3 on a few cores
-    gd, dt, threads, ng = cpu_ax_sample(N, n, max(args.steps, 1), max(args.warmup, 1))
-    sample = f"oracle C port (OpenMP) of elliptic_t::Operator, Hex N={N}, {n}^3 box, lambda=0, {ng} DOFs per apply"
+    # bounded: at most ~60 s of applies however large --steps is (each "step" = one apply of the sample box)
+    one = cpu_ax_sample(N, n, 1, 1)[1]
+    steps = int(max(1, min(args.steps, 60.0 / max(one, 1e-6))))
+    gd, dt, threads, ng, steps = cpu_ax_sample(N, n, steps, min(max(args.warmup, 1), 3))
+    sample = (f"oracle C port (OpenMP, {threads} threads) of elliptic_t::Operator, Hex N={N}, {n}^3 box, lambda=0, "
+              f"{ng} DOFs per apply, {steps} timed applies of {dt:.4f} s")
     line = {"impl": "reference", "metric": METRIC, "value": gd, "unit": "GDOF/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -188,7 +199,7 @@ def main():
 
     # ------------------------------------------------------------------ BP5 operator (lambda = 0)
     t_setup = time.perf_counter()
-    p = EllipticProblem(N, n, lam=0.0, boundary_flag=1, comm=comm, mode=args.mode)
+    p = EllipticProblem(N, n, lam=0.0, boundary_flag=1, comm=comm, mode=args.mode, coords=not args.no_pcg)
     t_setup = time.perf_counter() - t_setup
     Ng = p.NglobalDofs
     q = p.vec()
@@ -222,19 +233,22 @@ def main():
     E, Np = m.Nelements, m.Np
     peak, peak_src = measured_peaks()
     Aq2 = p.vec()
+    api.register_D(p.Nq, m.D)  # mesh.o_D is immutable: same even-odd kernel the operator handle launches
     def kern():
         api.ax_hex3d_gather(p.Nq, E, None, p.GlobalToLocal, m.wJ, m.ggeo, m.D, 0.0, q, Aq2)
     for _ in range(3):
         Aq2.zero_(); kern()
     # the kernel accumulates into Aq2; zeroing is outside the kernel timing (events bracket kernels only)
     kms = 0.0
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    ksteps = min(steps, 50)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ksteps)]
     torch.cuda.synchronize()
     for a, b in ev:
         Aq2.zero_()
         a.record(); kern(); b.record()
     torch.cuda.synchronize()
-    kms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    kms = sum(a.elapsed_time(b) for a, b in ev) / ksteps
+    api.unregister_D(m.D)
     alg_bytes = 8.0 * 6 * E * Np + 16.0 * p.Ndofs  # geofactors + read q + write Aq (lambda = 0)
     achieved = alg_bytes / (kms * 1e-3) / 1e9
     traffic = None
@@ -245,50 +259,86 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "ax_hex3d_kernel<8,gather,fused>", "kernel_ms": kms,
+                "traffic": traffic, "kernel": "ax_hex3d_t_kernel<Nq=8,gather,fused,even-odd>", "kernel_ms": kms,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "elements_per_launch": E}
     del Aq2
 
     # ------------------------------------------------------------------ e2e: host buffers through the C ABI
+    # Each step copies that step's q from pinned host memory, applies the operator through the C ABI and
+    # copies Aq back to pinned host memory.  Two buffer sets alternate so that the D2H of step i overlaps
+    # the H2D of step i+1 (PCIe is full duplex); every step still moves its own input and output.
     e2e = None
     if not args.no_e2e:
-        hq = torch.empty(p.Nall, dtype=torch.float64).pin_memory()
-        hA = torch.empty(p.Nall, dtype=torch.float64).pin_memory()
-        hq.copy_(q.cpu())
-        dq, dA = p.vec(), p.vec()
+        hq = [torch.empty(p.Nall, dtype=torch.float64).pin_memory() for _ in range(2)]
+        hA = [torch.empty(p.Nall, dtype=torch.float64).pin_memory() for _ in range(2)]
+        for h in hq:
+            h.copy_(q.cpu())
+        dq, dA = [p.vec(), p.vec()], [p.vec(), p.vec()]
+        main_s = torch.cuda.current_stream()
+        h2d_s, d2h_s = torch.cuda.Stream(), torch.cuda.Stream()
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+        ev_cmp = [torch.cuda.Event() for _ in range(2)]
+        state = {"i": 0}
         def e2e_step():
-            dq.copy_(hq, non_blocking=True)
-            p.op.Operator(dq, dA)
-            hA.copy_(dA, non_blocking=True)
-        nst = max(3, min(steps, 10))
+            b = state["i"] & 1
+            state["i"] += 1
+            h2d_s.wait_event(ev_cmp[b])          # dq[b] free again (compute of step i-2 done)
+            with torch.cuda.stream(h2d_s):
+                dq[b].copy_(hq[b], non_blocking=True)
+                ev_in[b].record(h2d_s)
+            main_s.wait_event(ev_in[b])
+            main_s.wait_event(ev_out[b])         # dA[b] drained by the D2H of step i-2
+            p.op.Operator(dq[b], dA[b])
+            ev_cmp[b].record(main_s)
+            d2h_s.wait_event(ev_cmp[b])
+            with torch.cuda.stream(d2h_s):
+                hA[b].copy_(dA[b], non_blocking=True)
+                ev_out[b].record(d2h_s)
+        def e2e_drain():
+            main_s.wait_stream(d2h_s); main_s.wait_stream(h2d_s)
+        nst = max(4, min(steps, 10))
         for _ in range(2):
             e2e_step()
-        ems = timed(e2e_step, nst)
+        e2e_drain()
+        ems = timed(lambda: None, 0)  # barrier + sync
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(nst):
+            e2e_step()
+        e2e_drain()
+        e1.record()
+        barrier()
+        ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        ems = float(ems.item())
+        ok = bool(torch.allclose(hA[0][: p.Ndofs], Aq[: p.Ndofs].cpu(), rtol=1e-9, atol=1e-12))
         e2e = {"value": Ng * nst / (ems * 1e-3) / 1e9, "unit": "GDOF/s",
                "h2d_bytes_per_step": int(8 * p.Nall), "d2h_bytes_per_step": int(8 * p.Nall),
-               "ms_per_step": ems / nst, "path": "pinned host q -> H2D -> libp_elliptic_operator -> D2H Aq"}
+               "ms_per_step": ems / nst, "result_matches_device_run": ok,
+               "path": "pinned host q -> H2D -> libp_elliptic_operator -> D2H Aq (double-buffered over steps)"}
         del hq, hA, dq, dA
 
-    launches_per_step = 2 if world == 1 else 3 + 3  # Ax launches (+ extract/combine kernels when sharded)
-    p.op.Free()
+    # launches inside the timed region per step: single rank = 2 Ax kernels (the two halves of the local
+    # element list; the zero-fill is a memset node); sharded = 3 Ax + halo extract + 2 combine/extract kernels
+    launches_per_step = 2 if world == 1 else 6
 
     # ------------------------------------------------------------------ Jacobi-PCG on the screened problem
     pcg = None
     if not args.no_pcg:
-        del p
-        torch.cuda.empty_cache()
-        ps = EllipticProblem(N, n, lam=1.0, boundary_flag=1, comm=comm, mode=args.mode, coords=True)
-        M = ps.jacobi()
-        r0 = ps.rhs_sine3d()
-        ps.mesh.x = ps.mesh.y = ps.mesh.z = None
-        solver = ps.pcg()
+        p.set_lambda(1.0)           # same mesh / ogs / maps, new operator handle (BASELINE configs[2])
+        M = p.jacobi()
+        r0 = p.rhs_sine3d()
+        solver = p.pcg()
         iters = args.pcg_iters
-        x, r = ps.vec(), r0.clone()
-        solver.Solve(ps.op, M, x, r, tol=1e-30, maxit=3)  # warm-up
+        x, r = p.vec(), r0.clone()
+        solver.Solve(p.op, M, x, r, tol=1e-30, maxit=3)  # warm-up
         def solve():
             x.zero_(); r.copy_(r0)
-            return solver.Solve(ps.op, M, x, r, tol=1e-30, maxit=iters)
+            return solver.Solve(p.op, M, x, r, tol=1e-30, maxit=iters)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
@@ -300,9 +350,9 @@ def main():
             dist.all_reduce(pms, op=dist.ReduceOp.MAX)
         pms = float(pms.item())
         hist = solver.residual_history()
-        it_bytes = (8.0 * 7 * ps.mesh.Nelements * ps.mesh.Np + 16.0 * ps.Ndofs) + 88.0 * ps.Ndofs
+        it_bytes = (8.0 * 7 * p.mesh.Nelements * p.mesh.Np + 16.0 * p.Ndofs) + 88.0 * p.Ndofs
         pcg = {"config": f"screened Poisson (lambda=1) Jacobi-PCG, Hex N={N}, {n}^3 box", "iterations": it,
-               "ms_per_iteration": pms / max(it, 1), "value": ps.NglobalDofs * it / (pms * 1e-3) / 1e9,
+               "ms_per_iteration": pms / max(it, 1), "value": p.NglobalDofs * it / (pms * 1e-3) / 1e9,
                "unit": "GDOF/s", "residual_first_last": [float(hist[0]), float(hist[-1])],
                "roofline_frac": (it_bytes / (pms / max(it, 1) * 1e-3) / 1e9) / peak,
                "algorithmic_bytes_per_iteration": it_bytes}
@@ -311,10 +361,11 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            gd, dt, threads, ngc = cpu_ax_sample(N, args.cpu_elements, 3, 1)
+            gd, dt, threads, ngc, nap = cpu_ax_sample(N, args.cpu_elements, 3, 1, seconds=args.cpu_seconds)
             cpu = {"value": gd, "unit": "GDOF/s", "cores": threads, "kind": "port",
-                   "sample": f"oracle C port (OpenMP) of the same operator apply on a {args.cpu_elements}^3 box "
-                             f"({ngc} DOFs), 3 applies, {dt:.3f} s each"}
+                   "sample": f"oracle C port (OpenMP, {threads} threads) of the same operator apply on a "
+                             f"{args.cpu_elements}^3 box ({ngc} DOFs): {nap} applies of {dt:.4f} s "
+                             f"(~{nap * dt:.0f} s of CPU work)"}
         except Exception as e:  # pragma: no cover
             cpu = {"value": None, "unit": "GDOF/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
 

@@ -151,6 +151,13 @@ int libp_ax_hex3d_gather(int Nq, libp_dlong Nelements, const libp_dlong* element
                          const libp_dfloat* wJ, const libp_dfloat* ggeo, const libp_dfloat* D, libp_dfloat lambda,
                          const libp_dfloat* q, libp_dfloat* Aq, void* stream);
 
+/* Optional promise that the Nq x Nq device array D stays immutable until unregistered (mesh.o_D does):
+ * the library then classifies it once (a GLL derivative matrix is centro-antisymmetric, which enables the
+ * even-odd form of the 1-D contractions) and stops reloading it into constant memory on every call.
+ * libp_elliptic_create does the same internally.  Unregistered pointers always take the general path. */
+int libp_ax_hex3d_register_D(int Nq, const libp_dfloat* D);
+int libp_ax_hex3d_unregister_D(const libp_dfloat* D);
+
 /* Tuning knob (not a reference interface): 0 = one-thread-per-column "pencil" kernel that mirrors the
  * reference's thread layout, 1 = transposed-pencil kernel (default; all contractions in registers). */
 int libp_ax_hex3d_set_variant(int variant);

@@ -81,6 +81,8 @@ SIGNATURES = {
     "libp_ax_hex3d": (i32, [i32, i32, vp, vp, vp, vp, vp, f64, vp, vp, vp]),
     "libp_ax_hex3d_gather": (i32, [i32, i32, vp, vp, vp, vp, vp, f64, vp, vp, vp]),
     "libp_ax_hex3d_set_variant": (i32, [i32]),
+    "libp_ax_hex3d_register_D": (i32, [i32, vp]),
+    "libp_ax_hex3d_unregister_D": (i32, [vp]),
     "libp_ax_hex3d_tune": (i32, [i32, i32, i32]),
     "libp_elliptic_create": (i32, [P(EllipticDesc), P(vp)]),
     "libp_elliptic_free": (i32, [vp]),

@@ -281,6 +281,15 @@ def ax_hex3d(Nq, Nelements, elementList, GlobalToLocal, wJ, ggeo, D, lam, q, AqL
                                  _ptr(D), float(lam), _ptr(q), _ptr(AqL), _stream()))
 
 
+def register_D(Nq, D):
+    """Promise that the device array D is immutable: enables the even-odd kernels for GLL matrices."""
+    check(L.load().libp_ax_hex3d_register_D(int(Nq), _ptr(D)))
+
+
+def unregister_D(D):
+    check(L.load().libp_ax_hex3d_unregister_D(_ptr(D)))
+
+
 def ax_hex3d_gather(Nq, Nelements, elementList, GlobalToLocal, wJ, ggeo, D, lam, q, Aq):
     check(L.load().libp_ax_hex3d_gather(Nq, Nelements, _ptr(elementList), _ptr(GlobalToLocal), _ptr(wJ), _ptr(ggeo),
                                         _ptr(D), float(lam), _ptr(q), _ptr(Aq), _stream()))

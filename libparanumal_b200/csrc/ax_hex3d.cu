@@ -28,10 +28,10 @@ namespace {
 
 // defaults of the transposed-pencil kernel (measured on B200, see profiles/ and DESIGN.md)
 #ifndef LIBP_AX_MINB
-#define LIBP_AX_MINB 6
+#define LIBP_AX_MINB 8
 #endif
 #ifndef LIBP_AX_PF
-#define LIBP_AX_PF 2
+#define LIBP_AX_PF 1
 #endif
 #ifndef LIBP_AX_HINT
 #define LIBP_AX_HINT true
@@ -514,7 +514,8 @@ void launch_t(int grid, dlong Nelements, const dlong* elementList, const dlong* 
 #undef ROW
   }
 #endif
-  GOT(LIBP_AX_PF, LIBP_AX_HINT, LIBP_AX_MINB);
+  // a general (non-GLL) D needs all Nq^2 constants: give the N=7 kernel the registers instead of spilling
+  GOT(LIBP_AX_PF, LIBP_AX_HINT, (SYM || Nq < 8) ? LIBP_AX_MINB : 4);
 #undef GOT
 }
 
@@ -612,6 +613,39 @@ int ax_hex3d_blocks(int Nq, dlong Nelements) {
 
 }  // namespace libp_b200
 
+// Registry of derivative matrices the caller promised to keep immutable (libp_ax_hex3d_register_D):
+// device pointer -> (Nq, centro-antisymmetric?).  Registered matrices skip the per-call constant-bank
+// reload and, when they are GLL matrices, run the even-odd kernels.
+namespace {
+struct RegisteredD { const dfloat* ptr; int Nq; bool sym; };
+std::vector<RegisteredD> g_registry;
+const RegisteredD* find_registered(const dfloat* D, int Nq) {
+  for (const auto& r : g_registry)
+    if (r.ptr == D && r.Nq == Nq) return &r;
+  return nullptr;
+}
+}  // namespace
+
+extern "C" int libp_ax_hex3d_register_D(int Nq, const libp_dfloat* D) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(Nq >= 2 && Nq <= kMaxNq && D, "bad argument");
+  double hD[kMaxNq * kMaxNq];
+  CUDA_CHECK(cudaMemcpy(hD, D, sizeof(double) * Nq * Nq, cudaMemcpyDeviceToHost));
+  const bool sym = ax_hex3d_D_is_centro_antisymmetric(Nq, hD);
+  for (auto& r : g_registry)
+    if (r.ptr == D) { r.Nq = Nq; r.sym = sym; if (g_cD_owner == D) g_cD_owner = nullptr; return LIBP_SUCCESS; }
+  g_registry.push_back({D, Nq, sym});
+  LIBP_API_END
+}
+
+extern "C" int libp_ax_hex3d_unregister_D(const libp_dfloat* D) {
+  LIBP_API_BEGIN
+  for (size_t i = 0; i < g_registry.size(); ++i)
+    if (g_registry[i].ptr == D) { g_registry.erase(g_registry.begin() + i); break; }
+  if (g_cD_owner == D) g_cD_owner = nullptr;
+  LIBP_API_END
+}
+
 extern "C" int libp_ax_hex3d_set_variant(int variant) {
   LIBP_API_BEGIN
   LIBP_CHECK(variant == 0 || variant == 1, "variant must be 0 (pencil) or 1 (transposed pencils)");
@@ -636,8 +670,9 @@ extern "C" int libp_ax_hex3d(int Nq, libp_dlong Nelements, const libp_dlong* ele
                              void* stream) {
   LIBP_API_BEGIN
   LIBP_CHECK(Nelements == 0 || (wJ && ggeo && D && q && AqL), "null device pointer");
-  ax_hex3d_launch(Nq, false, false, false, Nelements, elementList, GlobalToLocal, wJ, ggeo, D, lambda, q, AqL,
-                  nullptr, nullptr, as_stream(stream));
+  const RegisteredD* r = find_registered(D, Nq);
+  ax_hex3d_launch(Nq, false, r != nullptr, r && r->sym, Nelements, elementList, GlobalToLocal, wJ, ggeo, D, lambda, q,
+                  AqL, nullptr, nullptr, as_stream(stream));
   LIBP_API_END
 }
 
@@ -647,7 +682,8 @@ extern "C" int libp_ax_hex3d_gather(int Nq, libp_dlong Nelements, const libp_dlo
                                     void* stream) {
   LIBP_API_BEGIN
   LIBP_CHECK(Nelements == 0 || (GlobalToLocal && wJ && ggeo && D && q && Aq), "null device pointer");
-  ax_hex3d_launch(Nq, true, false, false, Nelements, elementList, GlobalToLocal, wJ, ggeo, D, lambda, q, Aq,
-                  nullptr, nullptr, as_stream(stream));
+  const RegisteredD* r = find_registered(D, Nq);
+  ax_hex3d_launch(Nq, true, r != nullptr, r && r->sym, Nelements, elementList, GlobalToLocal, wJ, ggeo, D, lambda, q,
+                  Aq, nullptr, nullptr, as_stream(stream));
   LIBP_API_END
 }

@@ -24,7 +24,7 @@ class EllipticProblem:
         NZ = NX if NZ is None else NZ
         self.comm = comm if comm is not None else Comm()
         self.device = torch.device(device)
-        self.N, self.Nq, self.lam = N, N + 1, float(lam)
+        self.N, self.Nq, self.lam, self.mode = N, N + 1, float(lam), mode
         self.mesh = mesh if mesh is not None else BoxMesh(N, NX, NY, NZ, self.comm.rank, self.comm.size,
                                                           boundary_flag, device=device, coords=coords)
         m = self.mesh
@@ -41,6 +41,15 @@ class EllipticProblem:
         self.allNeumann = (self.lam == 0.0) and (boundary_flag == -1)
         self.op = Elliptic(self.Nq, m.localGatherElementList, m.globalGatherElementList, self.GlobalToLocal,
                            m.wJ, m.ggeo, m.D, self.lam, self.ogs, mode=mode)
+
+    def set_lambda(self, lam):
+        """Same mesh, maps and ogs with a different screening parameter: only the operator handle changes."""
+        self.op.Free()
+        self.lam = float(lam)
+        m = self.mesh
+        self.allNeumann = (self.lam == 0.0) and (m.boundary_flag == -1)
+        self.op = Elliptic(self.Nq, m.localGatherElementList, m.globalGatherElementList, self.GlobalToLocal,
+                           m.wJ, m.ggeo, m.D, self.lam, self.ogs, mode=self.mode)
 
     def vec(self, fill=0.0):
         return torch.full((self.Nall,), fill, dtype=torch.float64, device=self.device)

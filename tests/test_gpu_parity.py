@@ -39,8 +39,19 @@ def dev(a, dtype=None):
 # ----------------------------------------------------------------------------- Ax kernel
 @pytest.mark.parametrize("N", [1, 2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("lam", [0.0, 1.3])
-def test_ax_hex3d_element_local_and_indexed(N, lam):
+@pytest.mark.parametrize("path", ["general", "gll-registered", "pencil"])
+def test_ax_hex3d_element_local_and_indexed(N, lam, path, request):
+    """general: un-registered D (full Nq^2 contractions); gll-registered: D promised immutable, classified
+    centro-antisymmetric -> even-odd kernels; pencil: the one-thread-per-column variant."""
     Nq, n = N + 1, 3
+    lib = L.load()
+    L.check(lib.libp_ax_hex3d_set_variant(0 if path == "pencil" else 1))
+    request.addfinalizer(lambda: lib.libp_ax_hex3d_set_variant(1))
+    _dev = dev
+    if path == "gll-registered":
+        Dreg = torch.from_numpy(BoxMesh(N, 1, 1, 1, device="cpu", geometry=False).D_host.reshape(-1).copy()).cuda()
+        api.register_D(Nq, Dreg)
+        request.addfinalizer(lambda: api.unregister_D(Dreg))
     mesh = BoxMesh(N, n, n + 1, n, device="cuda")
     E, Np = mesh.Nelements, mesh.Np
     rng = np.random.default_rng(N)
@@ -52,7 +63,8 @@ def test_ax_hex3d_element_local_and_indexed(N, lam):
     q = rng.uniform(-1, 1, E * Np)
     ref = er.ax_hex3d(Nq, wJ, ggeo, D, lam, q)
     out = torch.zeros(E * Np, dtype=torch.float64, device="cuda")
-    api.ax_hex3d(Nq, E, None, None, dev(wJ), dev(ggeo), dev(D), lam, dev(q), out)
+    dD = Dreg if path == "gll-registered" else dev(D)
+    api.ax_hex3d(Nq, E, None, None, dev(wJ), dev(ggeo), dD, lam, dev(q), out)
     assert relerr(out.cpu().numpy(), ref) < AX_TOL
     # indexed (GlobalToLocal with -1 entries) on an element sub-list
     Ng = E * Np // 2
@@ -62,8 +74,37 @@ def test_ax_hex3d_element_local_and_indexed(N, lam):
     ref = np.full(E * Np, 7.0)
     er.ax_hex3d(Nq, wJ, ggeo, D, lam, qg, G2L=G2L, element_list=elist, out=ref)
     out = torch.full((E * Np,), 7.0, dtype=torch.float64, device="cuda")
-    api.ax_hex3d(Nq, len(elist), dev(elist), dev(G2L), dev(wJ), dev(ggeo), dev(D), lam, dev(qg), out)
+    api.ax_hex3d(Nq, len(elist), dev(elist), dev(G2L), dev(wJ), dev(ggeo), dD, lam, dev(qg), out)
     assert relerr(out.cpu().numpy(), ref) < AX_TOL  # untouched elements keep the sentinel
+    # fused scatter-add epilogue: Aq[G2L] += A_e q over the sub-list
+    refg = np.zeros(Ng)
+    loc = ref.reshape(E, Np)
+    g2 = G2L.reshape(E, Np)
+    for e in elist:
+        m = g2[e] >= 0
+        np.add.at(refg, g2[e][m], loc[e][m])
+    outg = torch.zeros(Ng, dtype=torch.float64, device="cuda")
+    api.ax_hex3d_gather(Nq, len(elist), dev(elist), dev(G2L), dev(wJ), dev(ggeo), dD, lam, dev(qg), outg)
+    assert relerr(outg.cpu().numpy(), refg) < AX_TOL
+
+
+def test_ax_hex3d_non_gll_D_registered_takes_general_path():
+    """A registered D that is NOT centro-antisymmetric must still give the right answer."""
+    N, Nq, n = 3, 4, 2
+    mesh = BoxMesh(N, n, n, n, device="cuda")
+    E, Np = mesh.Nelements, mesh.Np
+    rng = np.random.default_rng(5)
+    D = rng.standard_normal((Nq, Nq))
+    q = rng.uniform(-1, 1, E * Np)
+    ref = er.ax_hex3d(Nq, mesh.wJ.cpu().numpy(), mesh.ggeo.cpu().numpy(), D, 0.7, q)
+    dD = dev(D.reshape(-1))
+    api.register_D(Nq, dD)
+    try:
+        out = torch.zeros(E * Np, dtype=torch.float64, device="cuda")
+        api.ax_hex3d(Nq, E, None, None, mesh.wJ, mesh.ggeo, dD, 0.7, dev(q), out)
+        assert relerr(out.cpu().numpy(), ref) < AX_TOL
+    finally:
+        api.unregister_D(dD)
 
 
 @pytest.mark.parametrize("name", FULL)

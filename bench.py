@@ -174,6 +174,7 @@ def main():
         gloo = dist.new_group(backend="gloo")
     comm = Comm(rank, world, gloo)
     comm.init_nccl()
+    p2p = comm.init_p2p() if (world > 1 and os.environ.get("LIBP_P2P", "1") != "0") else False
     N, n = args.degree, args.elements
     steps, warmup = args.steps, max(args.warmup, 3)
 
@@ -374,7 +375,7 @@ def main():
                 "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"bp5_operator_hex_n{N}_e{n}", "N": N, "elements": [n, n, n], "lambda": 0.0,
-                           "global_dofs": int(Ng), "mode": "fused-gather" if args.mode == 1 else "reference-flow",
+                           "global_dofs": int(Ng), "exchange": ("nvlink-peer-window" if p2p else "nccl") if world > 1 else "none", "mode": "fused-gather" if args.mode == 1 else "reference-flow",
                            "l2": "inputs (6.4 GB of geometric factors per apply) are far larger than the 126 MB L2; no flush needed",
                            "setup_seconds": round(t_setup, 1)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * steps,

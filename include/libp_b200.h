@@ -85,6 +85,16 @@ int libp_comm_rank(libp_comm_t comm, int* rank, int* size);
 int libp_comm_nccl_unique_id(void* uid128);
 int libp_comm_nccl_init(libp_comm_t comm, const void* uid128);
 
+/* NVLink peer window (replaces the reference's GPU-aware-MPI exchange, libs/ogs/ogsPairwise.cpp:116-183, and
+ * the 8-byte MPI_Allreduce of linAlg.cpp:149-187 on the PCG path): every rank allocates `window_bytes`
+ * (0 = LIBP_P2P_WINDOW_MB or 256 MB) of device memory and maps every peer's window through CUDA IPC, using the
+ * host all-to-all callback to trade handles.  Afterwards halo packing kernels store straight into the
+ * neighbours' receive buffers over NVLink and reduction kernels all-reduce their scalars through mailboxes,
+ * with release/acquire flags instead of NCCL launches.  Collective; all ranks of one node.  If it is not
+ * called (or fails on any rank: LIBP_ERROR on every rank) the NCCL path is used.                          */
+int libp_comm_p2p_init(libp_comm_t comm, size_t window_bytes);
+int libp_comm_p2p_enabled(libp_comm_t comm, int* enabled);
+
 /* ------------------------------------------------------------------ ogs
  * ogs::ogs_t::Setup (include/ogs.hpp:216-226; libs/ogs/ogsSetup.cpp:43-190).
  * `ids` (host, length N): 0 = ignored, sign = flag.  When `unique` the array is rewritten

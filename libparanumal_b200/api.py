@@ -168,6 +168,26 @@ class Comm:
         uid = t.numpy().copy()
         check(L.load().libp_comm_nccl_init(self._h, _ptr(uid)))
 
+    def init_p2p(self, window_bytes=0, required=False):
+        """NVLink peer window (CUDA IPC): halo exchange and PCG scalar all-reduces run inside our own kernels.
+        Returns True when every rank mapped every peer; otherwise the NCCL path stays in use."""
+        if self.size == 1:
+            return False
+        rc = L.load().libp_comm_p2p_init(self._h, int(window_bytes))
+        if rc != 0:
+            if required:
+                check(rc)
+            if self.rank == 0:
+                print("peer window unavailable, using NCCL:", L.load().libp_last_error().decode())
+            return False
+        return True
+
+    @property
+    def p2p(self):
+        e = C.c_int(0)
+        check(L.load().libp_comm_p2p_enabled(self._h, C.byref(e)))
+        return bool(e.value)
+
     @property
     def handle(self):
         return self._h

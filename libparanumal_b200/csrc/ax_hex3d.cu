@@ -328,7 +328,6 @@ struct AxT {
   static constexpr int LD = (Nq % 2 == 0) ? Nq + 2 : Nq + 1;  // even: rows are 16-byte aligned
   static constexpr int SS0 = Nq * LD;
   static constexpr int SS = SS0 + ((8 - (SS0 % 16)) + 16) % 16;  // SS = 8 mod 16, even
-  static constexpr int NPAIR = (Nq + 1) / 2;                      // double2 per row
 };
 
 // PF = geometric-factor slabs in flight per thread, kHint = L2 residency hints on/off

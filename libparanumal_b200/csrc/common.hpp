@@ -80,6 +80,21 @@ struct dev_buf {
 
 int sm_count();
 
+// Fixed header at the start of every peer window: mailboxes of the scalar all-reduce.
+constexpr int kWinMaxRanks = 64;
+constexpr int kWinMaxVals = 8;
+struct WinHeader {
+  double mbox[2][kWinMaxRanks][kWinMaxVals];   // [parity][source rank][value]
+  unsigned long long mflag[2][kWinMaxRanks];   // sequence number of the last all-reduce rank r contributed to
+};
+
+// What a kernel needs to all-reduce a few doubles across ranks through the peer windows.
+struct WinAR {
+  int rank = 0, size = 1;
+  char* const* peer_win = nullptr;   // device table
+  unsigned long long* seq = nullptr; // device counter (shared by every user of the communicator)
+};
+
 }  // namespace libp_b200
 
 // ------------------------------------------------------------------ communicator
@@ -88,7 +103,17 @@ struct libp_comm_s {
   libp_host_collectives_t host{};
   bool has_host = false;
   void* nccl = nullptr;           // ncclComm_t
-  cudaStream_t comm_stream = nullptr;  // side stream for exchanges (the reference's dataStream)
+  cudaStream_t comm_stream = nullptr;  // high-priority side stream for exchanges (the reference's dataStream)
+  // ---- NVLink peer window (libp_comm_p2p_init): one device allocation per rank, mapped by every peer through
+  // CUDA IPC.  Kernels exchange halo values and reduction scalars with plain stores into the peers' windows and
+  // release/acquire flags - no NCCL launch, no host involvement.  Layout: [WinHeader | bump-allocated regions].
+  bool p2p = false;
+  char* win = nullptr;
+  size_t win_bytes = 0, win_used = 0;
+  std::vector<char*> peer_win;                  // peer_win[r] = rank r's window in my address space (self included)
+  libp_b200::dev_buf<char*> d_peer_win;         // the same table on the device
+  unsigned long long* d_ar_seq = nullptr;       // device counter of window all-reduces
+  size_t win_alloc(size_t bytes);               // offset of a new 256-byte aligned region of my window
   // host collectives with size==1 shortcuts
   void alltoall(const void* send, void* recv, size_t bytes_per_rank) const;
   void alltoallv(const void* send, const int64_t* sc, const int64_t* so, void* recv, const int64_t* rc,

@@ -9,7 +9,7 @@
 
 using namespace libp_b200;
 
-void libp_elliptic_s::apply(dfloat* q, dfloat* Aq, bool want_dot, const int* doneFlag, cudaStream_t s) {
+void libp_elliptic_s::apply(dfloat* q, dfloat* Aq, bool want_dot, const int* doneFlag, cudaStream_t s, bool zeroed) {
   libp_ogs_s& ogs = *d.ogsMasked;
   const dlong nL = d.NlocalGatherElements, nG = d.NglobalGatherElements;
   const dlong nL0 = nL / 2, nL1 = (nL + 1) / 2;
@@ -23,26 +23,16 @@ void libp_elliptic_s::apply(dfloat* q, dfloat* Aq, bool want_dot, const int* don
                              dp ? dp + doff : nullptr, doneFlag, s);
     doff += nb;
   };
-  if (fused)
+  if (fused && !zeroed)
     CUDA_CHECK(cudaMemsetAsync(Aq, 0, sizeof(dfloat) * (size_t)(ogs.NlocalT + ogs.NhaloT), s));
   halo_start_f64(ogs, q, s);
   ax(nL0, d.localGatherElementList);
   halo_finish_f64(ogs, q, s);
   ax(nG, d.globalGatherElementList);
   if (fused) {
-    if (ogs.comm->size > 1) {
-      ogs.alloc_buffers(sizeof(dfloat));
-      CUDA_CHECK(cudaMemcpyAsync(ogs.haloBuf.p, Aq + ogs.NlocalT, sizeof(dfloat) * (size_t)ogs.NhaloT,
-                                 cudaMemcpyDeviceToDevice, s));
-      halo_combine_start_f64(ogs, s);
-    }
+    halo_combine_start_f64(ogs, Aq, s);
     ax(nL1, d.localGatherElementList ? d.localGatherElementList + nL0 : nullptr);
-    if (ogs.comm->size > 1) {
-      halo_combine_finish_f64(ogs, s);
-      if (ogs.NhaloP)
-        CUDA_CHECK(cudaMemcpyAsync(Aq + ogs.NlocalT, ogs.haloBuf.p, sizeof(dfloat) * (size_t)ogs.NhaloP,
-                                   cudaMemcpyDeviceToDevice, s));
-    }
+    halo_combine_finish_f64(ogs, Aq, s);
   } else {
     ogs_gather_start_f64(ogs, Aq, AqL.p, LIBP_ADD, LIBP_TRANS, s);
     ax(nL1, d.localGatherElementList ? d.localGatherElementList + nL0 : nullptr);

@@ -13,8 +13,8 @@ void ogs_gather_start_f64(libp_ogs_s& o, double* gv, const double* v, int op, in
 void ogs_gather_finish_f64(libp_ogs_s& o, double* gv, const double* v, int op, int trans, cudaStream_t s);
 void halo_start_f64(libp_ogs_s& o, double* v, cudaStream_t s);
 void halo_finish_f64(libp_ogs_s& o, double* v, cudaStream_t s);
-void halo_combine_start_f64(libp_ogs_s& o, cudaStream_t s);
-void halo_combine_finish_f64(libp_ogs_s& o, cudaStream_t s);
+void halo_combine_start_f64(libp_ogs_s& o, double* gv, cudaStream_t s);
+void halo_combine_finish_f64(libp_ogs_s& o, double* gv, cudaStream_t s);
 }  // namespace libp_b200
 
 struct libp_elliptic_s {
@@ -26,7 +26,8 @@ struct libp_elliptic_s {
   libp_b200::dev_buf<dfloat> dotPartials;  // one per Ax block (p.Ap partial sums)
   int nDotPartials = 0;
   // apply; when dot/doneFlag are given the p.Ap partials are produced and the kernels early-exit
-  void apply(dfloat* q, dfloat* Aq, bool want_dot, const int* doneFlag, cudaStream_t s);
+  // zeroed: the caller already zero-filled Aq[0 : NlocalT+NhaloT] (PCG folds it into its p-update pass)
+  void apply(dfloat* q, dfloat* Aq, bool want_dot, const int* doneFlag, cudaStream_t s, bool zeroed = false);
 };
 
 struct libp_precon_s {

@@ -10,9 +10,11 @@
 // pair and walks its few columns; row starts and column ids stream coalesced, values are
 // sector-sized random reads that mostly hit L2.  The exchange posts one ncclGroup of
 // send/recv pairs straight from/into device buffers on a side stream (no host staging).
+#include <algorithm>
 #include <limits>
 
 #include "ogs.hpp"
+#include "p2p.cuh"
 
 using namespace libp_b200;
 
@@ -274,6 +276,148 @@ void halo_finish(libp_ogs_s& o, T* v, int K, cudaStream_t s) {
                                (size_t)K * Nhalo * sizeof(T), cudaMemcpyDeviceToDevice, s));
 }
 
+// ---- NVLink peer-window exchange (double, k = 1) ---------------------------------------------------------
+// pack + send in one kernel: every packed value is stored straight into the neighbour's receive buffer.
+struct P2PPackArgs {
+  const double* src;            // halo rows of the local vector (v + NlocalT)
+  const dlong* sendIds;
+  double* const* dst[2];        // remote addresses per value, per parity
+  dlong Nsend;
+  int nSendRanks;
+  const int* sendRanks;
+  unsigned long long* const* peerFlags;
+  const unsigned long long* acks;  // my window
+  unsigned long long* d_seq;
+  unsigned int* d_done;
+  int rank, size;
+};
+__global__ void __launch_bounds__(kBlock) p2p_pack_send_kernel(P2PPackArgs a) {
+  const unsigned long long seq = *a.d_seq + 1;
+  const int par = (int)(seq & 1);
+  // the buffer of this parity was last used by exchange seq-2: wait until every destination consumed it
+  if (seq > 2 && threadIdx.x < a.nSendRanks)
+    while (ld_acquire_sys(&a.acks[par * a.size + a.sendRanks[threadIdx.x]]) < seq - 2) { }
+  __syncthreads();
+  double* const* dst = a.dst[par];
+  for (dlong n = blockIdx.x * kBlock + threadIdx.x; n < a.Nsend; n += gridDim.x * kBlock)
+    st_peer(dst[n], a.src[a.sendIds[n]]);
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = (atomicAdd(a.d_done, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last) {
+    __threadfence_system();
+    if (threadIdx.x < a.nSendRanks) st_release_sys(a.peerFlags[threadIdx.x] + par * a.size + a.rank, seq);
+    if (threadIdx.x == 0) { *a.d_done = 0; *a.d_seq = seq; }
+  }
+}
+
+// wait for the senders' flags, then combine.  kTrans = false: halo rows [rowBegin,rowEnd) take the owner's value
+// (halo_t::Exchange); kTrans = true: owned rows add the received partial sums in ascending source rank
+// (the post-exchange gather of ogsPairwise.cpp:283-336).  The last block acknowledges to every sharer.
+struct P2PUnpackArgs {
+  double* out;                  // v + NlocalT
+  const double* recv;           // my window, parity 0
+  size_t cap;
+  const unsigned long long* flags;
+  int nRecvRanks;
+  const int* recvRanks;
+  const dlong* rowStarts;
+  const dlong* colIds;
+  dlong rowBegin, rowEnd, Nhalo;
+  unsigned long long* const* peerAcks;
+  int nAckRanks;
+  const unsigned long long* d_seq;
+  unsigned int* d_done;
+  int rank, size;
+};
+template <bool kTrans>
+__global__ void __launch_bounds__(kBlock) p2p_wait_unpack_kernel(P2PUnpackArgs a) {
+  const unsigned long long seq = *a.d_seq;  // already advanced by this exchange's pack kernel
+  const int par = (int)(seq & 1);
+  if (threadIdx.x < a.nRecvRanks)
+    while (ld_acquire_sys(&a.flags[par * a.size + a.recvRanks[threadIdx.x]]) < seq) { }
+  __syncthreads();
+  const double* recv = a.recv + (size_t)par * a.cap;
+  for (dlong row = a.rowBegin + blockIdx.x * kBlock + threadIdx.x; row < a.rowEnd; row += gridDim.x * kBlock) {
+    const dlong s = a.rowStarts[row], e = a.rowStarts[row + 1];
+    if (kTrans) {
+      double acc = a.out[row];  // own partial first (colIds[s] == row)
+      for (dlong g = s + 1; g < e; ++g) acc += ld_peer_written(recv + (a.colIds[g] - a.Nhalo));
+      a.out[row] = acc;
+    } else {
+      if (e > s) a.out[row] = ld_peer_written(recv + (a.colIds[s] - a.Nhalo));
+    }
+  }
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = (atomicAdd(a.d_done, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last) {
+    if (threadIdx.x < a.nAckRanks) st_release_sys(a.peerAcks[threadIdx.x] + par * a.size + a.rank, seq);
+    if (threadIdx.x == 0) *a.d_done = 0;
+  }
+}
+
+// flavour 0: owners -> sharers (halo of q); flavour 1: all sharers (combine of the partial sums in place)
+void p2p_start(libp_ogs_s& o, double* v, int flavour, cudaStream_t s) {
+  const libp_comm_s& c = *o.comm;
+  P2PExchange& x = o.p2p;
+  const ExchangeLists& ex = flavour == 0 ? o.exN : o.exT;
+  LIBP_CHECK((int)ex.sendRanks.size() <= kBlock && (int)o.exT.recvRanks.size() <= kBlock, "too many neighbours");
+  cudaStream_t cs = c.comm_stream;
+  CUDA_CHECK(cudaEventRecord(o.ev_ready, s));
+  CUDA_CHECK(cudaStreamWaitEvent(cs, o.ev_ready, 0));
+  P2PPackArgs a;
+  a.src = v + o.NlocalT;
+  a.sendIds = ex.d_sendIds.p;
+  a.dst[0] = x.sendDst[flavour][0].p;
+  a.dst[1] = x.sendDst[flavour][1].p;
+  a.Nsend = ex.Nsend();
+  a.nSendRanks = (int)ex.sendRanks.size();
+  a.sendRanks = x.sendRanks[flavour].p;
+  a.peerFlags = x.peerFlags[flavour].p;
+  a.acks = x.acks;
+  a.d_seq = x.d_seq;
+  a.d_done = x.d_done;
+  a.rank = c.rank;
+  a.size = c.size;
+  int g = (int)std::min<size_t>(((size_t)std::max<dlong>(a.Nsend, 1) + kBlock - 1) / kBlock, 64);
+  p2p_pack_send_kernel<<<g, kBlock, 0, cs>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaEventRecord(o.ev_done, cs));
+}
+void p2p_finish(libp_ogs_s& o, double* v, int flavour, cudaStream_t s) {
+  const libp_comm_s& c = *o.comm;
+  P2PExchange& x = o.p2p;
+  const ExchangeLists& ex = flavour == 0 ? o.exN : o.exT;
+  CUDA_CHECK(cudaStreamWaitEvent(s, o.ev_done, 0));  // pack kernel done => sequence counter advanced
+  P2PUnpackArgs a;
+  a.out = v + o.NlocalT;
+  a.recv = x.recv;
+  a.cap = x.cap;
+  a.flags = x.flags;
+  a.nRecvRanks = (int)ex.recvRanks.size();
+  a.recvRanks = x.recvRanks[flavour].p;
+  a.rowStarts = flavour == 0 ? o.postmpi.d_rowStartsN.p : o.postmpi.d_rowStartsT.p;
+  a.colIds = flavour == 0 ? o.postmpi.d_colIdsN.p : o.postmpi.d_colIdsT.p;
+  a.rowBegin = flavour == 0 ? o.NhaloP : 0;
+  a.rowEnd = flavour == 0 ? o.NhaloT : o.NhaloP;
+  a.Nhalo = o.NhaloT;
+  a.peerAcks = x.peerAcks.p;
+  a.nAckRanks = x.nAckRanks;
+  a.d_seq = x.d_seq;
+  a.d_done = x.d_done + 1;
+  a.rank = c.rank;
+  a.size = c.size;
+  const dlong nrows = std::max<dlong>(a.rowEnd - a.rowBegin, 1);
+  int g = (int)std::min<size_t>(((size_t)nrows + kBlock - 1) / kBlock, 64);
+  if (flavour == 0) p2p_wait_unpack_kernel<false><<<g, kBlock, 0, s>>>(a);
+  else p2p_wait_unpack_kernel<true><<<g, kBlock, 0, s>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+}
+
 #define DISPATCH_TYPE(type, CALL)                                             \
   switch (type) {                                                             \
     case LIBP_FLOAT: { typedef float T; CALL; } break;                        \
@@ -299,14 +443,31 @@ void ogs_gather_start_f64(libp_ogs_s& o, double* gv, const double* v, int op, in
 void ogs_gather_finish_f64(libp_ogs_s& o, double* gv, const double* v, int op, int trans, cudaStream_t s) {
   ogs_gather_finish<double>(o, gv, v, 1, op, trans, s);
 }
-void halo_start_f64(libp_ogs_s& o, double* v, cudaStream_t s) { halo_start<double>(o, v, 1, s); }
-void halo_finish_f64(libp_ogs_s& o, double* v, cudaStream_t s) { halo_finish<double>(o, v, 1, s); }
-// combine the NhaloT partial sums in haloBuf across ranks; owned totals end up in haloBuf[0:NhaloP]
-void halo_combine_start_f64(libp_ogs_s& o, cudaStream_t s) {
+void halo_start_f64(libp_ogs_s& o, double* v, cudaStream_t s) {
+  if (o.comm->size == 1) return;
+  if (o.p2p.enabled) p2p_start(o, v, 0, s);
+  else halo_start<double>(o, v, 1, s);
+}
+void halo_finish_f64(libp_ogs_s& o, double* v, cudaStream_t s) {
+  if (o.comm->size == 1) return;
+  if (o.p2p.enabled) p2p_finish(o, v, 0, s);
+  else halo_finish<double>(o, v, 1, s);
+}
+// Combine the partial sums of the shared rows, held in place in gv[NlocalT : NlocalT+NhaloT] (fused Ax epilogue),
+// across ranks; the owned totals end up in gv[NlocalT : NlocalT+NhaloP].
+void halo_combine_start_f64(libp_ogs_s& o, double* gv, cudaStream_t s) {
+  if (o.comm->size == 1) return;
+  if (o.p2p.enabled) { p2p_start(o, gv, 1, s); return; }
+  o.alloc_buffers(sizeof(double));
+  CUDA_CHECK(cudaMemcpyAsync(o.haloBuf.p, gv + o.NlocalT, sizeof(double) * (size_t)o.NhaloT, cudaMemcpyDeviceToDevice, s));
   exchange_start<double>(o, reinterpret_cast<double*>(o.haloBuf.p), 1, LIBP_TRANS, s);
 }
-void halo_combine_finish_f64(libp_ogs_s& o, cudaStream_t s) {
+void halo_combine_finish_f64(libp_ogs_s& o, double* gv, cudaStream_t s) {
+  if (o.comm->size == 1) return;
+  if (o.p2p.enabled) { p2p_finish(o, gv, 1, s); return; }
   exchange_finish<double>(o, reinterpret_cast<double*>(o.haloBuf.p), 1, LIBP_ADD, LIBP_TRANS, s);
+  if (o.NhaloP)
+    CUDA_CHECK(cudaMemcpyAsync(gv + o.NlocalT, o.haloBuf.p, sizeof(double) * (size_t)o.NhaloP, cudaMemcpyDeviceToDevice, s));
 }
 }  // namespace libp_b200
 
@@ -364,13 +525,15 @@ int libp_halo_exchange_start(libp_ogs_t o, void* v, int k, int type, void* strea
   LIBP_API_BEGIN
   check(o, k);
   LIBP_CHECK(o->gather_defined, "Gather operation not well-defined.");
-  DISPATCH_TYPE(type, halo_start<T>(*o, (T*)v, k, as_stream(stream)));
+  if (type == LIBP_DOUBLE && k == 1 && o->p2p.enabled) halo_start_f64(*o, (double*)v, as_stream(stream));
+  else DISPATCH_TYPE(type, halo_start<T>(*o, (T*)v, k, as_stream(stream)));
   LIBP_API_END
 }
 int libp_halo_exchange_finish(libp_ogs_t o, void* v, int k, int type, void* stream) {
   LIBP_API_BEGIN
   check(o, k);
-  DISPATCH_TYPE(type, halo_finish<T>(*o, (T*)v, k, as_stream(stream)));
+  if (type == LIBP_DOUBLE && k == 1 && o->p2p.enabled) halo_finish_f64(*o, (double*)v, as_stream(stream));
+  else DISPATCH_TYPE(type, halo_finish<T>(*o, (T*)v, k, as_stream(stream)));
   LIBP_API_END
 }
 int libp_halo_exchange(libp_ogs_t o, void* v, int k, int type, void* stream) {

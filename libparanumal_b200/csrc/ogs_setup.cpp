@@ -331,6 +331,62 @@ void pairwise_setup(libp_ogs_s& o, std::vector<Node>& sharedNodes) {
   compress(sendCountsT, recvCountsT, o.exT);
 }
 
+// Peer-window exchange setup: carve my receive buffers / flags out of my window, tell every neighbour where its
+// values land, and precompute the remote address of every value I send (both parities, both flavours).
+void p2p_setup(libp_ogs_s& o) {
+  libp_comm_s& c = *o.comm;
+  P2PExchange& x = o.p2p;
+  const int size = c.size, rank = c.rank;
+  x.cap = (size_t)std::max<dlong>(o.exT.Nrecv(), 1);
+  const size_t recv_off = c.win_alloc(2 * x.cap * sizeof(double));
+  const size_t flags_off = c.win_alloc(2 * (size_t)size * sizeof(unsigned long long));
+  const size_t acks_off = c.win_alloc(2 * (size_t)size * sizeof(unsigned long long));
+  x.recv = reinterpret_cast<double*>(c.win + recv_off);
+  x.flags = reinterpret_cast<unsigned long long*>(c.win + flags_off);
+  x.acks = reinterpret_cast<unsigned long long*>(c.win + acks_off);
+  CUDA_CHECK(cudaMalloc(&x.d_seq, sizeof(unsigned long long)));
+  CUDA_CHECK(cudaMemset(x.d_seq, 0, sizeof(unsigned long long)));
+  CUDA_CHECK(cudaMalloc(&x.d_done, 2 * sizeof(unsigned int)));
+  CUDA_CHECK(cudaMemset(x.d_done, 0, 2 * sizeof(unsigned int)));
+  // what each peer needs to know about my window: {recv_off, cap, flags_off, acks_off, slotN, slotT}
+  std::vector<int64_t> mine((size_t)size * 6, -1), theirs((size_t)size * 6, -1);
+  for (int r = 0; r < size; ++r) {
+    int64_t* m = &mine[(size_t)r * 6];
+    m[0] = (int64_t)recv_off; m[1] = (int64_t)x.cap; m[2] = (int64_t)flags_off; m[3] = (int64_t)acks_off;
+  }
+  for (size_t i = 0; i < o.exN.recvRanks.size(); ++i) mine[(size_t)o.exN.recvRanks[i] * 6 + 4] = o.exN.recvOffsets[i];
+  for (size_t i = 0; i < o.exT.recvRanks.size(); ++i) mine[(size_t)o.exT.recvRanks[i] * 6 + 5] = o.exT.recvOffsets[i];
+  c.alltoall(mine.data(), theirs.data(), 6 * sizeof(int64_t));  // also orders every rank's window zero-fill before use
+  for (int f = 0; f < 2; ++f) {
+    const ExchangeLists& ex = f == 0 ? o.exN : o.exT;
+    std::vector<double*> d0((size_t)ex.Nsend()), d1((size_t)ex.Nsend());
+    std::vector<unsigned long long*> pf(ex.sendRanks.size());
+    for (size_t i = 0; i < ex.sendRanks.size(); ++i) {
+      const int r = ex.sendRanks[i];
+      const int64_t* t = &theirs[(size_t)r * 6];
+      LIBP_CHECK(t[4 + f] >= 0, "peer-window setup: neighbour lists are not symmetric");
+      double* base = reinterpret_cast<double*>(c.peer_win[r] + t[0]) + t[4 + f];
+      for (int n = ex.sendOffsets[i]; n < ex.sendOffsets[i + 1]; ++n) {
+        d0[n] = base + (n - ex.sendOffsets[i]);
+        d1[n] = d0[n] + t[1];
+      }
+      pf[i] = reinterpret_cast<unsigned long long*>(c.peer_win[r] + t[2]);
+    }
+    x.sendDst[f][0].upload(d0);
+    x.sendDst[f][1].upload(d1);
+    x.peerFlags[f].upload(pf);
+    x.sendRanks[f].upload(ex.sendRanks);
+    x.recvRanks[f].upload(ex.recvRanks);
+  }
+  std::vector<unsigned long long*> pa(o.exT.recvRanks.size());
+  for (size_t i = 0; i < o.exT.recvRanks.size(); ++i)
+    pa[i] = reinterpret_cast<unsigned long long*>(c.peer_win[o.exT.recvRanks[i]] + theirs[(size_t)o.exT.recvRanks[i] * 6 + 3]);
+  x.peerAcks.upload(pa);
+  x.nAckRanks = (int)pa.size();
+  (void)rank;
+  x.enabled = true;
+}
+
 }  // namespace
 
 void libp_b200::OgsOperator::to_device() {
@@ -343,6 +399,8 @@ void libp_b200::OgsOperator::to_device() {
 libp_ogs_s::~libp_ogs_s() {
   if (ev_ready) cudaEventDestroy(ev_ready);
   if (ev_done) cudaEventDestroy(ev_done);
+  if (p2p.d_seq) cudaFree(p2p.d_seq);
+  if (p2p.d_done) cudaFree(p2p.d_done);
 }
 
 void libp_ogs_s::alloc_buffers(size_t bytes_per_node) {
@@ -408,6 +466,7 @@ extern "C" int libp_ogs_setup(libp_dlong N, libp_hlong* ids, libp_comm_t comm, i
     o->exT.d_sendIds.upload(o->exT.sendIds);
     CUDA_CHECK(cudaEventCreateWithFlags(&o->ev_ready, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&o->ev_done, cudaEventDisableTiming));
+    if (comm->p2p && size > 1) p2p_setup(*o);
   } else {
     cudaGetLastError();
   }

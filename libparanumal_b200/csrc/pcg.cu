@@ -17,6 +17,7 @@
 
 #include "elliptic.hpp"
 #include "linalg.hpp"
+#include "p2p.cuh"
 
 using namespace libp_b200;
 
@@ -26,7 +27,7 @@ constexpr int kBlock = 256;
 
 struct PcgScalars {
   double rdotz1, rdotz2, alpha, beta, pAp, rdotr, TOL, zdotAp;
-  double red[4];  // landing slots for reductions: [0]=rdotr [1]=rdotz [2]=pAp [3]=zdotAp
+  double red[4];  // landing slots for reductions (NCCL path): [0]=r.r [1]=r.z [2]=z.Ap [3]=p.Ap
   int iter;       // completed iterations
   int done;       // convergence flag: later kernels become no-ops
   int maxit, flexible;
@@ -55,8 +56,10 @@ __device__ inline double block_sum(double v, double* s_w) {
   return v;
 }
 
-// x += alpha p ; r -= alpha Ap ; partial r.r ; (jacobi) z = invD r ; partial r.z
-template <bool kJacobi>
+// x += alpha p ; r -= alpha Ap ; partial r.r ; z = M r and partial r.z when the preconditioner is diagonal
+// (kPrecon 1: Jacobi z = invD r, 2: identity z = r, 0: z is produced by a separate precon apply) ;
+// partial z.Ap for the flexible variant.  partials = [r.r | r.z | z.Ap], nparts entries each.
+template <int kPrecon, bool kFlex>
 __global__ void __launch_bounds__(kBlock) update_kernel(dlong N, const PcgScalars* __restrict__ sc,
                                                         const double* __restrict__ p, const double* __restrict__ Ap,
                                                         const double* __restrict__ invD, double* __restrict__ x,
@@ -65,29 +68,36 @@ __global__ void __launch_bounds__(kBlock) update_kernel(dlong N, const PcgScalar
   if (sc->done) return;
   __shared__ double s_w[32];
   const double alpha = sc->alpha;
-  double rr = 0.0, rz = 0.0;
+  double rr = 0.0, rz = 0.0, zAp = 0.0;
   for (dlong n = blockIdx.x * kBlock + threadIdx.x; n < N; n += gridDim.x * kBlock) {
     double rn = r[n];
+    const double Apn = Ap[n];
     x[n] += alpha * p[n];
-    rn -= alpha * Ap[n];
+    rn -= alpha * Apn;
     rr += rn * rn;
     r[n] = rn;
-    if (kJacobi) {
-      const double zn = invD[n] * rn;
+    if (kPrecon != 0) {
+      const double zn = (kPrecon == 1) ? invD[n] * rn : rn;
       z[n] = zn;
       rz += rn * zn;
+      if (kFlex) zAp += zn * Apn;
     }
   }
   rr = block_sum(rr, s_w);
   if (threadIdx.x == 0) partials[blockIdx.x] = rr;
-  if (kJacobi) {
+  if (kPrecon != 0) {
     rz = block_sum(rz, s_w);
     if (threadIdx.x == 0) partials[nparts + blockIdx.x] = rz;
+    if (kFlex) {
+      zAp = block_sum(zAp, s_w);
+      if (threadIdx.x == 0) partials[2 * nparts + blockIdx.x] = zAp;
+    }
   }
 }
 
-// z = invD r ; partial r.z   (first iteration, Jacobi)   or just partial x.y
-__global__ void __launch_bounds__(kBlock) jacobi_dot_kernel(dlong N, const PcgScalars* __restrict__ sc,
+// z = M r (diagonal preconditioners) ; partial r.z   (before the first iteration)
+template <int kPrecon>
+__global__ void __launch_bounds__(kBlock) precon_dot_kernel(dlong N, const PcgScalars* __restrict__ sc,
                                                             const double* __restrict__ invD,
                                                             const double* __restrict__ r, double* __restrict__ z,
                                                             double* __restrict__ partials) {
@@ -95,13 +105,14 @@ __global__ void __launch_bounds__(kBlock) jacobi_dot_kernel(dlong N, const PcgSc
   __shared__ double s_w[32];
   double rz = 0.0;
   for (dlong n = blockIdx.x * kBlock + threadIdx.x; n < N; n += gridDim.x * kBlock) {
-    const double rn = r[n], zn = invD[n] * rn;
+    const double rn = r[n], zn = (kPrecon == 1) ? invD[n] * rn : rn;
     z[n] = zn;
     rz += rn * zn;
   }
   rz = block_sum(rz, s_w);
   if (threadIdx.x == 0) partials[blockIdx.x] = rz;
 }
+// partial a.b (general preconditioners: r.z and z.Ap after the precon apply)
 __global__ void __launch_bounds__(kBlock) dot_kernel(dlong N, const PcgScalars* __restrict__ sc,
                                                      const double* __restrict__ a, const double* __restrict__ b,
                                                      double* __restrict__ partials) {
@@ -113,54 +124,99 @@ __global__ void __launch_bounds__(kBlock) dot_kernel(dlong N, const PcgScalars* 
   if (threadIdx.x == 0) partials[blockIdx.x] = v;
 }
 
-// p = z + beta p
-__global__ void __launch_bounds__(kBlock) pupdate_kernel(dlong N, const PcgScalars* __restrict__ sc,
-                                                         const double* __restrict__ z, double* __restrict__ p) {
+// p = z + beta p ; optionally zero-fill Ap (the accumulator of the fused Ax epilogue) in the same pass
+__global__ void __launch_bounds__(kBlock) pupdate_kernel(dlong N, dlong Nzero, const PcgScalars* __restrict__ sc,
+                                                         const double* __restrict__ z, double* __restrict__ p,
+                                                         double* __restrict__ Ap) {
   if (sc->done) return;
   const double beta = sc->beta;
-  for (dlong n = blockIdx.x * kBlock + threadIdx.x; n < N; n += gridDim.x * kBlock) p[n] = z[n] + beta * p[n];
+  const dlong M = N > Nzero ? N : Nzero;
+  for (dlong n = blockIdx.x * kBlock + threadIdx.x; n < M; n += gridDim.x * kBlock) {
+    if (n < N) p[n] = z[n] + beta * p[n];
+    if (n < Nzero) Ap[n] = 0.0;
+  }
 }
 
-// sum `n` partials (several segments) into sc->red[slot...]; one block, fixed order
-__global__ void __launch_bounds__(1024) finish_partials_kernel(PcgScalars* sc, const double* __restrict__ partials,
-                                                               int n0, int slot0, int n1, int slot1) {
+// deterministic single-block sum of n partials: 4 independent accumulators per thread, fixed tree
+__device__ inline double block_sum_array(const double* __restrict__ a, int n, double* s_w) {
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+  const int T = blockDim.x;
+  int i = threadIdx.x;
+  for (; i + 3 * T < n; i += 4 * T) { v0 += a[i]; v1 += a[i + T]; v2 += a[i + 2 * T]; v3 += a[i + 3 * T]; }
+  for (; i < n; i += T) v0 += a[i];
+  return block_sum((v0 + v1) + (v2 + v3), s_w);
+}
+
+// One block per rank: finish the reductions of a stage, all-reduce them across ranks through the NVLink peer
+// window (no NCCL launch, bit-identical result on every rank) and run the scalar recurrences of
+// linearSolverPCG.cpp:104-150 on the device.
+//   kStage 0: partials = [r.z | z.Ap]      -> rdotz1/rdotz2, beta                         (after a precon apply)
+//   kStage 1: partials = [p.Ap]            -> alpha                                       (after the Ax)
+//   kStage 2: partials = [r.r | r.z | z.Ap]-> rdotr, iteration count, convergence flag, history (+ beta when
+//             the update kernel already produced z = M r)
+// phase 0 = everything; phase 1 = local sums only (an NCCL all-reduce of sc->red follows); phase 2 = scalars only.
+template <int kStage>
+__global__ void __launch_bounds__(1024) pcg_stage_kernel(PcgScalars* sc, const double* __restrict__ partials, int n0,
+                                                         int n1, int n2, WinAR w, int phase, int with_beta,
+                                                         double* __restrict__ hist, int maxhist) {
   if (sc->done) return;
   __shared__ double s_w[32];
-  double v = 0.0;
-  for (int i = threadIdx.x; i < n0; i += blockDim.x) v += partials[i];
-  v = block_sum(v, s_w);
-  if (threadIdx.x == 0) sc->red[slot0] = v;
-  if (n1 > 0) {
-    double u = 0.0;
-    for (int i = threadIdx.x; i < n1; i += blockDim.x) u += partials[n0 + i];
-    u = block_sum(u, s_w);
-    if (threadIdx.x == 0) sc->red[slot1] = u;
+  __shared__ double s_v[kWinMaxVals];
+  const int nseg = (n2 > 0) ? 3 : (n1 > 0) ? 2 : 1;
+  if (phase != 2) {
+    const double a0 = block_sum_array(partials, n0, s_w);
+    if (threadIdx.x == 0) s_v[0] = a0;
+    if (n1 > 0) {
+      const double a1 = block_sum_array(partials + n0, n1, s_w);
+      if (threadIdx.x == 0) s_v[1] = a1;
+    }
+    if (n2 > 0) {
+      const double a2 = block_sum_array(partials + n0 + n1, n2, s_w);
+      if (threadIdx.x == 0) s_v[2] = a2;
+    }
+    if (phase == 0) win_allreduce_sum(w, s_v, nseg);
+    else __syncthreads();
+    if (phase == 1) {
+      if (threadIdx.x == 0) {
+        if (kStage == 0) { sc->red[1] = s_v[0]; sc->red[2] = (n1 > 0) ? s_v[1] : 0.0; }
+        if (kStage == 1) sc->red[3] = s_v[0];
+        if (kStage == 2) { sc->red[0] = s_v[0]; sc->red[1] = (n1 > 0) ? s_v[1] : 0.0; sc->red[2] = (n2 > 0) ? s_v[2] : 0.0; }
+      }
+      return;
+    }
   }
-}
-
-// scalar recurrences (one thread).  stage 0: after r.z (+z.Ap) -> beta ; stage 1: after p.Ap -> alpha ;
-// stage 2: after r.r -> convergence test + iteration count
-__global__ void scalars_kernel(PcgScalars* sc, int stage) {
-  if (sc->done) return;
-  if (stage == 0) {
-    sc->rdotz2 = sc->rdotz1;
-    sc->rdotz1 = sc->red[1];
-    if (sc->flexible) sc->beta = (sc->iter == 0) ? 0.0 : -sc->alpha * sc->red[3] / sc->rdotz2;
-    else sc->beta = (sc->iter == 0) ? 0.0 : sc->rdotz1 / sc->rdotz2;
-  } else if (stage == 1) {
-    sc->pAp = sc->red[2];
-    sc->alpha = sc->rdotz1 / sc->pAp;
+  if (threadIdx.x != 0) return;
+  double v0, v1 = 0.0, v2 = 0.0;
+  if (phase == 2) {
+    if (kStage == 0) { v0 = sc->red[1]; v1 = sc->red[2]; }
+    else if (kStage == 1) v0 = sc->red[3];
+    else { v0 = sc->red[0]; v1 = sc->red[1]; v2 = sc->red[2]; }
   } else {
-    sc->rdotr = sc->red[0];
-    sc->iter += 1;
-    if (sc->rdotr <= sc->TOL || sc->iter >= sc->maxit) sc->done = 1;
+    v0 = s_v[0];
+    if (n1 > 0) v1 = s_v[1];
+    if (n2 > 0) v2 = s_v[2];
   }
-}
-
-__global__ void hist_kernel(const PcgScalars* sc, double* hist, int maxhist) {
-  // records sqrt(rdotr) after the iteration that just completed (no-op once converged earlier)
-  const int it = sc->iter;
-  if (it >= 0 && it < maxhist) hist[it] = sqrt(sc->rdotr);
+  if (kStage == 1) {
+    sc->pAp = v0;
+    sc->alpha = sc->rdotz1 / v0;
+    return;
+  }
+  double rz = v0, zAp = v1;
+  if (kStage == 2) {
+    sc->rdotr = v0;
+    const int it = sc->iter + 1;
+    sc->iter = it;
+    if (it < maxhist) hist[it] = sqrt(v0);
+    if (v0 <= sc->TOL || it >= sc->maxit) sc->done = 1;
+    if (!with_beta) return;
+    rz = v1;
+    zAp = v2;
+  }
+  // beta for the coming iteration (flexible: -alpha (z.Ap) / rdotz_old)
+  sc->rdotz2 = sc->rdotz1;
+  sc->rdotz1 = rz;
+  if (sc->iter == 0) sc->beta = 0.0;
+  else sc->beta = sc->flexible ? -sc->alpha * zAp / sc->rdotz2 : rz / sc->rdotz2;
 }
 
 }  // namespace
@@ -247,7 +303,7 @@ extern "C" int libp_pcg_create(libp_dlong N, libp_dlong Nhalo, int flexible, int
   s->p.alloc(Ntotal); s->z.alloc(Ntotal); s->Ax.alloc(Ntotal); s->Ap.alloc(Ntotal);
   for (dev_buf<dfloat>* b : {&s->p, &s->z, &s->Ax, &s->Ap})
     if (Ntotal) CUDA_CHECK(cudaMemset(b->p, 0, sizeof(dfloat) * Ntotal));
-  s->partials.alloc((size_t)2 * kRedMaxBlocks);
+  s->partials.alloc((size_t)4 * kRedMaxBlocks);
   s->sc.alloc(1);
   CUDA_CHECK(cudaMallocHost(&s->h_sc, sizeof(PcgScalars)));
   const char* ce = getenv("LIBP_PCG_CHECK_EVERY");
@@ -316,11 +372,12 @@ extern "C" int libp_pcg_solve_cb(libp_pcg_t pcg, libp_operator_fn A, void* Actx,
       cudaStream_t s = as_stream(stream);
       PcgScalars hs{};
       hs.alpha = alpha;
+      hs.maxit = maxit + 1;
       CUDA_CHECK(cudaMemcpyAsync(pcg->sc.p, &hs, sizeof(PcgScalars), cudaMemcpyHostToDevice, s));
       const int nb = std::min(vgrid(N), kRedMaxBlocks);
-      update_kernel<false><<<nb, kBlock, 0, s>>>(N, pcg->sc.p, pcg->p.p, pcg->Ap.p, nullptr, x, r, nullptr,
-                                                 pcg->partials.p, nb);
-      finish_partials_kernel<<<1, 1024, 0, s>>>(pcg->sc.p, pcg->partials.p, nb, 0, 0, 0);
+      update_kernel<0, false><<<nb, kBlock, 0, s>>>(N, pcg->sc.p, pcg->p.p, pcg->Ap.p, nullptr, x, r, nullptr,
+                                                    pcg->partials.p, nb);
+      pcg_stage_kernel<2><<<1, 1024, 0, s>>>(pcg->sc.p, pcg->partials.p, nb, 0, 0, WinAR{}, 1, 0, nullptr, 0);
       CUDA_CHECK(cudaGetLastError());
       if (comm && comm->size > 1) comm->allreduce_sum_dev(pcg->sc.p->red, 1, s);
       CUDA_CHECK(cudaMemcpyAsync(pcg->h_sc, pcg->sc.p, sizeof(PcgScalars), cudaMemcpyDeviceToHost, s));
@@ -385,49 +442,66 @@ extern "C" int libp_pcg_solve(libp_pcg_t pcg, libp_elliptic_t A, libp_precon_t M
   CUDA_CHECK(cudaMemsetAsync(pcg->d_hist.p, 0, sizeof(double) * ((size_t)maxit + 2), s));
   const int* done = &sc->done;
   const int nb = std::min(vgrid(N), kRedMaxBlocks);
-
-  // z = M r ; r.z for the first iteration
-  auto precon_and_rz = [&]() {
-    if (jacobi) {
-      jacobi_dot_kernel<<<nb, kBlock, 0, s>>>(N, sc, M->invDiag.p, r, pcg->z.p, parts);
+  const bool flex = pcg->flexible != 0;
+  const int precon = jacobi ? 1 : (M->kind == 0 ? 2 : 0);  // diagonal preconditioners ride the update kernel
+  // cross-rank reduction of a stage: through the NVLink peer window inside the stage kernel when the
+  // communicator has one, otherwise local sums -> NCCL all-reduce -> scalar kernel
+  const bool win = multi && comm->p2p;
+  WinAR w{};
+  if (win) { w.rank = comm->rank; w.size = comm->size; w.peer_win = comm->d_peer_win.p; w.seq = comm->d_ar_seq; }
+  auto stage = [&](int st, const double* partials, int n0, int n1, int n2, int with_beta) {
+    double* hist = pcg->d_hist.p;
+    const int mh = maxit + 2;
+#define STAGE(ST, PH) pcg_stage_kernel<ST><<<1, 1024, 0, s>>>(sc, partials, n0, n1, n2, w, PH, with_beta, hist, mh)
+    if (!multi || win) {
+      if (st == 0) STAGE(0, 0); else if (st == 1) STAGE(1, 0); else STAGE(2, 0);
     } else {
+      if (st == 0) STAGE(0, 1); else if (st == 1) STAGE(1, 1); else STAGE(2, 1);
+      // red = [r.r, r.z, z.Ap, p.Ap]: every stage all-reduces exactly the slots it wrote
+      if (st == 0) comm->allreduce_sum_dev(sc->red + 1, 2, s);
+      else if (st == 1) comm->allreduce_sum_dev(sc->red + 3, 1, s);
+      else comm->allreduce_sum_dev(sc->red, 3, s);
+      if (st == 0) STAGE(0, 2); else if (st == 1) STAGE(1, 2); else STAGE(2, 2);
+    }
+#undef STAGE
+  };
+  const dlong Nzero = (A->d.mode == 1) ? (dlong)(A->d.ogsMasked->NlocalT + A->d.ogsMasked->NhaloT) : 0;
+
+  // z = M r ; r.z ; beta = 0 for the first iteration
+  auto precon_and_rz = [&]() {
+    if (precon == 1) precon_dot_kernel<1><<<nb, kBlock, 0, s>>>(N, sc, M->invDiag.p, r, pcg->z.p, parts);
+    else if (precon == 2) precon_dot_kernel<2><<<nb, kBlock, 0, s>>>(N, sc, nullptr, r, pcg->z.p, parts);
+    else {
       M->apply(r, pcg->z.p, s);
       dot_kernel<<<nb, kBlock, 0, s>>>(N, sc, r, pcg->z.p, parts);
+      if (flex) dot_kernel<<<nb, kBlock, 0, s>>>(N, sc, pcg->z.p, pcg->Ap.p, parts + nb);
     }
-    finish_partials_kernel<<<1, 1024, 0, s>>>(sc, parts, nb, 1, 0, 0);
-    if (multi) comm->allreduce_sum_dev(sc->red + 1, 1, s);
+    stage(0, parts, nb, (precon == 0 && flex) ? nb : 0, 0, 1);
   };
   precon_and_rz();
   int queued = 0, iter = 0;
   while (true) {
-    // beta (needs r.z, and z.Ap when flexible)
-    if (pcg->flexible) {
-      dot_kernel<<<nb, kBlock, 0, s>>>(N, sc, pcg->z.p, pcg->Ap.p, parts);
-      finish_partials_kernel<<<1, 1024, 0, s>>>(sc, parts, nb, 3, 0, 0);
-      if (multi) comm->allreduce_sum_dev(sc->red + 3, 1, s);
-    }
-    scalars_kernel<<<1, 1, 0, s>>>(sc, 0);
-    pupdate_kernel<<<vgrid(N), kBlock, 0, s>>>(N, sc, pcg->z.p, pcg->p.p);
-    // Ap = A p with p.Ap partials from the Ax kernel
-    A->apply(pcg->p.p, pcg->Ap.p, true, done, s);
-    finish_partials_kernel<<<1, 1024, 0, s>>>(sc, A->dotPartials.p, A->nDotPartials, 2, 0, 0);
-    if (multi) comm->allreduce_sum_dev(sc->red + 2, 1, s);
-    scalars_kernel<<<1, 1, 0, s>>>(sc, 1);
-    // x, r update + r.r (+ z, r.z for Jacobi)
-    if (jacobi) {
-      update_kernel<true><<<nb, kBlock, 0, s>>>(N, sc, pcg->p.p, pcg->Ap.p, M->invDiag.p, x, r, pcg->z.p, parts, nb);
-      finish_partials_kernel<<<1, 1024, 0, s>>>(sc, parts, nb, 0, nb, 1);
-      if (multi) comm->allreduce_sum_dev(sc->red, 2, s);  // r.r and r.z travel together
+    // p = z + beta p (and the zero-fill of Ap for the fused Ax epilogue)
+    pupdate_kernel<<<vgrid(std::max(N, Nzero)), kBlock, 0, s>>>(N, Nzero, sc, pcg->z.p, pcg->p.p, pcg->Ap.p);
+    // Ap = A p with p.Ap partials from the Ax kernel ; alpha
+    A->apply(pcg->p.p, pcg->Ap.p, true, done, s, /*zeroed=*/Nzero > 0);
+    stage(1, A->dotPartials.p, A->nDotPartials, 0, 0, 0);
+    // x, r update + r.r (+ z = M r, r.z, z.Ap for diagonal preconditioners) ; convergence ; beta
+    if (precon == 1) {
+      if (flex) update_kernel<1, true><<<nb, kBlock, 0, s>>>(N, sc, pcg->p.p, pcg->Ap.p, M->invDiag.p, x, r, pcg->z.p, parts, nb);
+      else update_kernel<1, false><<<nb, kBlock, 0, s>>>(N, sc, pcg->p.p, pcg->Ap.p, M->invDiag.p, x, r, pcg->z.p, parts, nb);
+    } else if (precon == 2) {
+      if (flex) update_kernel<2, true><<<nb, kBlock, 0, s>>>(N, sc, pcg->p.p, pcg->Ap.p, nullptr, x, r, pcg->z.p, parts, nb);
+      else update_kernel<2, false><<<nb, kBlock, 0, s>>>(N, sc, pcg->p.p, pcg->Ap.p, nullptr, x, r, pcg->z.p, parts, nb);
     } else {
-      update_kernel<false><<<nb, kBlock, 0, s>>>(N, sc, pcg->p.p, pcg->Ap.p, nullptr, x, r, nullptr, parts, nb);
-      finish_partials_kernel<<<1, 1024, 0, s>>>(sc, parts, nb, 0, 0, 0);
-      if (multi) comm->allreduce_sum_dev(sc->red, 1, s);
+      update_kernel<0, false><<<nb, kBlock, 0, s>>>(N, sc, pcg->p.p, pcg->Ap.p, nullptr, x, r, nullptr, parts, nb);
     }
-    scalars_kernel<<<1, 1, 0, s>>>(sc, 2);
-    hist_kernel<<<1, 1, 0, s>>>(sc, pcg->d_hist.p, maxit + 2);
-    // non-Jacobi: z = M r ; r.z for the next iteration (the dot kernels no-op once converged);
-    // Jacobi: r.z was produced and reduced together with r.r above
-    if (!jacobi) precon_and_rz();
+    if (precon != 0) {
+      stage(2, parts, nb, nb, flex ? nb : 0, 1);
+    } else {
+      stage(2, parts, nb, 0, 0, 0);
+      precon_and_rz();  // general preconditioner: separate apply, then r.z (z.Ap) and beta
+    }
     CUDA_CHECK(cudaGetLastError());
     queued++;
     iter++;

@@ -101,6 +101,13 @@ extern "C" int libp_comm_free(libp_comm_t comm) {
   if (comm) {
     if (comm->nccl && nccl().CommDestroy) nccl().CommDestroy(comm->nccl);
     if (comm->comm_stream) cudaStreamDestroy(comm->comm_stream);
+    if (comm->p2p) {
+      cudaDeviceSynchronize();
+      for (int r = 0; r < comm->size; ++r)
+        if (r != comm->rank && comm->peer_win[r]) cudaIpcCloseMemHandle(comm->peer_win[r]);
+      cudaFree(comm->win);
+      cudaFree(comm->d_ar_seq);
+    }
     delete comm;
   }
   LIBP_API_END
@@ -132,7 +139,81 @@ extern "C" int libp_comm_nccl_init(libp_comm_t comm, const void* uid128) {
   ncclComm_ c = nullptr;
   nccl_check(nccl().CommInitRank(&c, comm->size, id, comm->rank), "CommInitRank");
   comm->nccl = c;
-  CUDA_CHECK(cudaStreamCreateWithFlags(&comm->comm_stream, cudaStreamNonBlocking));
+  if (!comm->comm_stream) {
+    // highest priority: the small pack / exchange kernels must not queue behind a full-GPU Ax launch
+    int least = 0, greatest = 0;
+    CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CUDA_CHECK(cudaStreamCreateWithPriority(&comm->comm_stream, cudaStreamNonBlocking, greatest));
+  }
+  LIBP_API_END
+}
+
+// ------------------------------------------------------------------ NVLink peer window
+size_t libp_comm_s::win_alloc(size_t bytes) {
+  const size_t off = (win_used + 255) & ~size_t(255);
+  LIBP_CHECK(off + bytes <= win_bytes, "peer window exhausted (raise window_bytes / LIBP_P2P_WINDOW_MB)");
+  win_used = off + bytes;
+  return off;
+}
+
+extern "C" int libp_comm_p2p_init(libp_comm_t comm, size_t window_bytes) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(comm, "null comm");
+  if (comm->size == 1 || comm->p2p) return LIBP_SUCCESS;
+  LIBP_CHECK(comm->size <= kWinMaxRanks, "peer window supports at most 64 ranks");
+  if (window_bytes == 0) {
+    const char* e = getenv("LIBP_P2P_WINDOW_MB");
+    window_bytes = (size_t)(e && atoi(e) > 0 ? atoi(e) : 256) << 20;
+  }
+  LIBP_CHECK(window_bytes >= sizeof(WinHeader) + 4096, "window too small");
+  if (!comm->comm_stream) {
+    int least = 0, greatest = 0;
+    CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CUDA_CHECK(cudaStreamCreateWithPriority(&comm->comm_stream, cudaStreamNonBlocking, greatest));
+  }
+  CUDA_CHECK(cudaMalloc(&comm->win, window_bytes));
+  CUDA_CHECK(cudaMemset(comm->win, 0, window_bytes));
+  CUDA_CHECK(cudaDeviceSynchronize());
+  comm->win_bytes = window_bytes;
+  comm->win_used = sizeof(WinHeader);
+  // exchange IPC handles (host all-to-all of 64-byte handles) and map every peer's window
+  cudaIpcMemHandle_t mine;
+  CUDA_CHECK(cudaIpcGetMemHandle(&mine, comm->win));
+  std::vector<cudaIpcMemHandle_t> sendh((size_t)comm->size, mine), recvh((size_t)comm->size);
+  comm->alltoall(sendh.data(), recvh.data(), sizeof(cudaIpcMemHandle_t));
+  comm->peer_win.assign((size_t)comm->size, nullptr);
+  int ok = 1;
+  std::string why;
+  for (int r = 0; r < comm->size; ++r) {
+    if (r == comm->rank) { comm->peer_win[r] = comm->win; continue; }
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, recvh[r], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { ok = 0; why = cudaGetErrorString(e); cudaGetLastError(); break; }
+    comm->peer_win[r] = static_cast<char*>(p);
+  }
+  // every rank must agree, otherwise some would wait on flags nobody writes
+  int64_t agree = ok;
+  comm->allreduce_i64(&agree, 1, LIBP_MIN);
+  if (!agree) {
+    for (int r = 0; r < comm->size; ++r)
+      if (r != comm->rank && comm->peer_win[r]) cudaIpcCloseMemHandle(comm->peer_win[r]);
+    comm->peer_win.clear();
+    cudaFree(comm->win);
+    comm->win = nullptr;
+    throw error("CUDA IPC peer mapping failed on some rank" + (why.empty() ? std::string() : (": " + why)));
+  }
+  comm->d_peer_win.upload(comm->peer_win);
+  CUDA_CHECK(cudaMalloc(&comm->d_ar_seq, sizeof(unsigned long long)));
+  CUDA_CHECK(cudaMemset(comm->d_ar_seq, 0, sizeof(unsigned long long)));
+  CUDA_CHECK(cudaDeviceSynchronize());
+  comm->p2p = true;
+  LIBP_API_END
+}
+
+extern "C" int libp_comm_p2p_enabled(libp_comm_t comm, int* enabled) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(comm && enabled, "null argument");
+  *enabled = comm->p2p ? 1 : 0;
   LIBP_API_END
 }
 

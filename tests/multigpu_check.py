@@ -1,0 +1,121 @@
+"""Multi-GPU parity check, run under torchrun (one rank per GPU; tests/test_gpu_multirank.py launches it):
+the sharded operator / halo exchange / Jacobi-PCG through (a) NCCL and (b) the NVLink peer window must agree
+with each other and with the same problem solved on a single GPU (rank 0 solves it alone as the checker)."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from libparanumal_b200 import _lib as L  # noqa: E402
+from libparanumal_b200 import api  # noqa: E402
+from libparanumal_b200.api import Comm  # noqa: E402
+from libparanumal_b200.problem import EllipticProblem  # noqa: E402
+
+libc = ctypes.CDLL("libc.so.6")
+
+
+def allsum(t):
+    t = t.clone()
+    dist.all_reduce(t)
+    return t
+
+
+def field(p):
+    m = p.mesh
+    return torch.sin(2.3 * m.x + 0.4) * torch.cos(1.7 * m.y - 0.2) + m.z * m.z * m.x + 0.25
+
+
+def gathered(p, fL):
+    """gathered vector holding one copy of a continuous nodal field (scatter^-1 by averaging copies)"""
+    g = p.vec()
+    cnt = p.vec()
+    p.ogs.Gather(g, fL.reshape(-1).contiguous(), 1, L.ADD, L.TRANS)
+    p.ogs.Gather(cnt, torch.ones_like(fL).reshape(-1).contiguous(), 1, L.ADD, L.TRANS)
+    g[: p.Ndofs] /= cnt[: p.Ndofs]
+    g[p.Ndofs:] = 0
+    return g
+
+
+def main():
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    api.init(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    gloo = dist.new_group(backend="gloo")
+    commN = Comm(rank, world, gloo); commN.init_nccl()
+    commP = Comm(rank, world, gloo); commP.init_nccl()
+    assert commP.init_p2p(required=True) and commP.p2p and not commN.p2p
+    for N, n, lam, flag in [(3, 6, 1.0, 1), (7, 4, 0.0, 1), (2, 5, 0.5, -1), (7, 6, 1.0, 1)]:
+        probs = {}
+        for name, comm in (("nccl", commN), ("p2p", commP)):
+            libc.srand(1)
+            probs[name] = EllipticProblem(N, n, lam=lam, boundary_flag=flag, comm=comm, coords=True)
+        pN, pP = probs["nccl"], probs["p2p"]
+        assert np.array_equal(pN.G2L_host, pP.G2L_host)
+        q = gathered(pN, field(pN))
+        # (d) halo exchange through the public API: exact agreement
+        vN, vP = q.clone(), q.clone()
+        vN[pN.Ndofs:] = -7; vP[pP.Ndofs:] = -9
+        pN.ogs.Exchange(vN); pP.ogs.Exchange(vP)
+        assert torch.equal(vN, vP), "halo exchange differs between NCCL and the peer window"
+        # (a) operator: same to rounding (fused atomics have no fixed summation order)
+        AN = pN.operator(q.clone()); AP = pP.operator(q.clone())
+        scale = float(allsum(AN[: pN.Ndofs].abs().max().reshape(1)).item())
+        errAP = float((AN[: pN.Ndofs] - AP[: pN.Ndofs]).abs().max().item()) / scale
+        assert errAP < 1e-13, errAP
+        # (e) protocol stress: many back-to-back applies and exchanges without host synchronisation
+        for i in range(60):
+            pP.op.Operator(q, AP)
+            if i % 7 == 0:
+                pP.ogs.Exchange(vP)
+        errAP2 = float((AN[: pN.Ndofs] - AP[: pN.Ndofs]).abs().max().item()) / scale
+        assert errAP2 < 1e-13, errAP2
+        # (b) against the single-GPU problem (rank 0 alone), through rank-count independent invariants
+        nrm = allsum((AP[: pP.Ndofs] ** 2).sum().reshape(1)).item()
+        qAq = allsum((q[: pP.Ndofs] * AP[: pP.Ndofs]).sum().reshape(1)).item()
+        # (c) Jacobi-PCG
+        res = {}
+        for name, p in probs.items():
+            r = p.rhs_sine3d(); x = p.vec()
+            solver = p.pcg()
+            it = solver.Solve(p.op, p.jacobi(), x, r, tol=1e-8, maxit=500)
+            xn = allsum((x[: p.Ndofs] ** 2).sum().reshape(1)).item()
+            res[name] = (it, solver.residual_history(), xn)
+        assert abs(res["nccl"][0] - res["p2p"][0]) <= 1
+        k = min(len(res["nccl"][1]), len(res["p2p"][1]))
+        # CG amplifies rounding differences (atomics order) late in the solve: tight early, loose late
+        assert np.allclose(res["nccl"][1][:min(k, 20)], res["p2p"][1][:min(k, 20)], rtol=1e-6)
+        assert np.allclose(res["nccl"][1][:k], res["p2p"][1][:k], rtol=5e-2)
+        if rank == 0:
+            libc.srand(1)
+            p1 = EllipticProblem(N, n, lam=lam, boundary_flag=flag, coords=True)
+            q1 = gathered(p1, field(p1))
+            A1 = p1.operator(q1)
+            nrm1 = float((A1[: p1.Ndofs] ** 2).sum().item())
+            qAq1 = float((q1[: p1.Ndofs] * A1[: p1.Ndofs]).sum().item())
+            assert p1.NglobalDofs == pP.NglobalDofs
+            assert abs(nrm - nrm1) <= 1e-11 * abs(nrm1), (nrm, nrm1)
+            assert abs(qAq - qAq1) <= 1e-11 * abs(qAq1), (qAq, qAq1)
+            r1 = p1.rhs_sine3d(); x1 = p1.vec(); s1 = p1.pcg()
+            it1 = s1.Solve(p1.op, p1.jacobi(), x1, r1, tol=1e-8, maxit=500)
+            assert abs(it1 - res["p2p"][0]) <= 1, (it1, res["p2p"][0])
+            h1 = s1.residual_history(); k = min(len(h1), len(res["p2p"][1]))
+            assert np.allclose(h1[:min(k, 20)], res["p2p"][1][:min(k, 20)], rtol=1e-6)
+            assert np.allclose(h1[:k], res["p2p"][1][:k], rtol=5e-2)
+            xn1 = float((x1[: p1.Ndofs] ** 2).sum().item())
+            assert abs(xn1 - res["p2p"][2]) <= 1e-7 * xn1
+            print(f"multigpu ok: world={world} N={N} n={n} lam={lam} flag={flag} it={res['p2p'][0]} (1 GPU {it1}) "
+                  f"|AN-AP|={errAP:.1e}", flush=True)
+        dist.barrier()
+    if rank == 0:
+        print("MULTIGPU CHECK PASSED", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,11 @@ typedef struct libp_ogs_s* libp_ogs_t;
 typedef struct libp_elliptic_s* libp_elliptic_t;
 typedef struct libp_pcg_s* libp_pcg_t;
 typedef struct libp_precon_s* libp_precon_t;
+typedef struct libp_mglevel_s* libp_mglevel_t;
+typedef struct libp_csr_s* libp_csr_t;
+typedef struct libp_amglevel_s* libp_amglevel_t;
+typedef struct libp_coarse_s* libp_coarse_t;
+typedef struct libp_multigrid_s* libp_multigrid_t;
 
 /* ------------------------------------------------------------------ runtime / errors */
 const char* libp_last_error(void);
@@ -242,6 +247,68 @@ int libp_precon_jacobi_create(libp_dlong Ndofs, const libp_dfloat* invDiagA, int
                               libp_hlong NglobalDofs, libp_comm_t comm, libp_precon_t* precon);
 int libp_precon_apply(libp_precon_t precon, const libp_dfloat* r, libp_dfloat* Mr, void* stream);
 int libp_precon_free(libp_precon_t precon);
+
+/* ------------------------------------------------------------------ p-multigrid level (matrix-free)
+ * MGLevel (solvers/elliptic/ellipticPrecon.hpp:66-116; src/ellipticPreconMultiGridLevel.cpp:30-206).  Every
+ * level owns the elliptic_t of its degree (`fine`) and refers to the elliptic_t of the next degree (`coarse`,
+ * MGLevel::ellipticC): coarsen gathers onto coarse.ogsMasked, prolongate reads through coarse.GlobalToLocal.
+ * Setup products (P, invDiagA, Chebyshev bounds from the Arnoldi estimate) cross the boundary as data.   */
+typedef struct {
+  libp_elliptic_t fine, coarse;
+  int NqF, NqC;
+  const libp_dfloat* P;        /* device, [NqF][NqC] 1-D degree-raise matrix (MGLevel::o_P) */
+  const libp_dfloat* invDiagA; /* device, fine Ndofs (already times lambda0 for the Jacobi smoother, :374-380) */
+  const libp_dfloat* weightG;  /* device, fine Ndofs (elliptic_t::o_weightG) */
+  int smoother;                /* 1 = JACOBI, 2 = CHEBYSHEV (MGLevel::SmootherType) */
+  libp_dfloat lambda0, lambda1;
+  int ChebyshevIterations;
+} libp_mglevel_desc_t;
+int libp_mglevel_create(const libp_mglevel_desc_t* desc, libp_mglevel_t* level);
+int libp_mglevel_free(libp_mglevel_t level);
+/* multigridLevel interface (include/parAlmond.hpp:70-91): vectors are gathered vectors of Ndofs+Nhalo entries */
+int libp_mglevel_operator(libp_mglevel_t level, libp_dfloat* x, libp_dfloat* Ax, void* stream);
+int libp_mglevel_smooth(libp_mglevel_t level, const libp_dfloat* rhs, libp_dfloat* x, int x_is_zero, void* stream);
+int libp_mglevel_residual(libp_mglevel_t level, const libp_dfloat* rhs, libp_dfloat* x, libp_dfloat* res, void* stream);
+int libp_mglevel_coarsen(libp_mglevel_t level, libp_dfloat* x, libp_dfloat* Rx, void* stream);
+int libp_mglevel_prolongate(libp_mglevel_t level, libp_dfloat* xC, libp_dfloat* x, void* stream); /* x += P xC */
+
+/* ------------------------------------------------------------------ parAlmond CSR levels (V-cycle apply)
+ * parCSR (include/parAlmond/parAlmondparCSR.hpp:35-100): local CSR block; arrays are HOST arrays produced by
+ * the reference's AMGSetup (out of scope to rebuild) and are copied to the device.  This round supports the
+ * single-rank case (empty off-diagonal block); a non-empty offd block is rejected with LIBP_ERROR.      */
+int libp_csr_create(libp_dlong Nrows, libp_dlong Ncols, libp_dlong nnz, const libp_dlong* rowStarts,
+                    const libp_dlong* cols, const libp_dfloat* vals, libp_dlong offd_nnz, libp_csr_t* csr);
+int libp_csr_free(libp_csr_t csr);
+/* parCSR::SpMV (libs/parAlmond/parAlmondparCSR.cpp:99-141): z = beta*y + alpha*A*x  (z may alias y) */
+int libp_csr_spmv(libp_csr_t A, libp_dfloat alpha, const libp_dfloat* x, libp_dfloat beta, const libp_dfloat* y,
+                  libp_dfloat* z, void* stream);
+/* amgLevel (libs/parAlmond/parAlmondAMGLevel.cpp:48-84): A, P (may be NULL on the last level), R (may be NULL),
+ * diagInv (host, Nrows), smoother 0 = DAMPED_JACOBI (lambda) / 1 = CHEBYSHEV (lambda0, lambda1)         */
+int libp_amglevel_create(libp_csr_t A, libp_csr_t P, libp_csr_t R, const libp_dfloat* diagInv, int smoother,
+                         libp_dfloat lambda, libp_dfloat lambda0, libp_dfloat lambda1, int ChebyshevIterations,
+                         libp_amglevel_t* level);
+int libp_amglevel_free(libp_amglevel_t level);
+int libp_amglevel_smooth(libp_amglevel_t level, const libp_dfloat* rhs, libp_dfloat* x, int x_is_zero, void* stream);
+int libp_amglevel_residual(libp_amglevel_t level, const libp_dfloat* rhs, const libp_dfloat* x, libp_dfloat* res, void* stream);
+int libp_amglevel_coarsen(libp_amglevel_t level, const libp_dfloat* x, libp_dfloat* Rx, void* stream);
+int libp_amglevel_prolongate(libp_amglevel_t level, const libp_dfloat* xC, libp_dfloat* x, void* stream);
+/* exactSolver_t::solve (libs/parAlmond/parAlmondCoarseExact.cpp:35-73): x = invA * rhs with the dense inverse
+ * stored transposed, invAT[n + m*N] (host array, N*N; single rank: offdTotal == 0)                      */
+int libp_coarse_exact_create(int N, const libp_dfloat* diagInvAT, libp_coarse_t* coarse);
+int libp_coarse_free(libp_coarse_t coarse);
+int libp_coarse_solve(libp_coarse_t coarse, const libp_dfloat* rhs, libp_dfloat* x, void* stream);
+
+/* multigrid_t (include/parAlmond.hpp:100-190; vcycle libs/parAlmond/parAlmondVcycle.cpp:34-60): levels are
+ * appended finest first (matrix-free p-MG levels, then CSR levels), the coarse solver closes the hierarchy. */
+int libp_multigrid_create(libp_comm_t comm, libp_multigrid_t* mg);
+int libp_multigrid_add_mglevel(libp_multigrid_t mg, libp_mglevel_t level);
+int libp_multigrid_add_amglevel(libp_multigrid_t mg, libp_amglevel_t level);
+int libp_multigrid_set_coarse(libp_multigrid_t mg, libp_coarse_t coarse);
+int libp_multigrid_vcycle(libp_multigrid_t mg, const libp_dfloat* rhs, libp_dfloat* x, void* stream);
+int libp_multigrid_free(libp_multigrid_t mg);
+/* MultiGridPrecon (solvers/elliptic/src/ellipticPreconMultiGrid.cpp:29-37): one V-cycle (+ZeroMean when allNeumann) */
+int libp_precon_multigrid_create(libp_multigrid_t mg, int allNeumann, libp_hlong NglobalDofs, libp_comm_t comm,
+                                 libp_precon_t* precon);
 
 /* ------------------------------------------------------------------ LinearSolver::pcg
  * linearSolverBase_t ctor (include/linearSolver.hpp:88-95) + pcg (libs/linearSolver/

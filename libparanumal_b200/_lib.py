@@ -47,6 +47,11 @@ class EllipticDesc(C.Structure):
                 ("wJ", vp), ("ggeo", vp), ("D", vp), ("lambda_", f64), ("ogsMasked", vp), ("mode", i32)]
 
 
+class MGLevelDesc(C.Structure):
+    _fields_ = [("fine", vp), ("coarse", vp), ("NqF", i32), ("NqC", i32), ("P", vp), ("invDiagA", vp), ("weightG", vp),
+                ("smoother", i32), ("lambda0", f64), ("lambda1", f64), ("ChebyshevIterations", i32)]
+
+
 OPERATOR_FN = C.CFUNCTYPE(i32, vp, vp, vp, vp)
 
 # name -> (restype, argtypes); every symbol include/libp_b200.h declares
@@ -111,6 +116,32 @@ SIGNATURES = {
     "libp_precon_jacobi_create": (i32, [i32, vp, i32, i64, vp, P(vp)]),
     "libp_precon_apply": (i32, [vp, vp, vp, vp]),
     "libp_precon_free": (i32, [vp]),
+    "libp_mglevel_create": (i32, [P(MGLevelDesc), P(vp)]),
+    "libp_mglevel_free": (i32, [vp]),
+    "libp_mglevel_operator": (i32, [vp, vp, vp, vp]),
+    "libp_mglevel_smooth": (i32, [vp, vp, vp, i32, vp]),
+    "libp_mglevel_residual": (i32, [vp, vp, vp, vp, vp]),
+    "libp_mglevel_coarsen": (i32, [vp, vp, vp, vp]),
+    "libp_mglevel_prolongate": (i32, [vp, vp, vp, vp]),
+    "libp_csr_create": (i32, [i32, i32, i32, vp, vp, vp, i32, P(vp)]),
+    "libp_csr_free": (i32, [vp]),
+    "libp_csr_spmv": (i32, [vp, f64, vp, f64, vp, vp, vp]),
+    "libp_amglevel_create": (i32, [vp, vp, vp, vp, i32, f64, f64, f64, i32, P(vp)]),
+    "libp_amglevel_free": (i32, [vp]),
+    "libp_amglevel_smooth": (i32, [vp, vp, vp, i32, vp]),
+    "libp_amglevel_residual": (i32, [vp, vp, vp, vp, vp]),
+    "libp_amglevel_coarsen": (i32, [vp, vp, vp, vp]),
+    "libp_amglevel_prolongate": (i32, [vp, vp, vp, vp]),
+    "libp_coarse_exact_create": (i32, [i32, vp, P(vp)]),
+    "libp_coarse_free": (i32, [vp]),
+    "libp_coarse_solve": (i32, [vp, vp, vp, vp]),
+    "libp_multigrid_create": (i32, [vp, P(vp)]),
+    "libp_multigrid_add_mglevel": (i32, [vp, vp]),
+    "libp_multigrid_add_amglevel": (i32, [vp, vp]),
+    "libp_multigrid_set_coarse": (i32, [vp, vp]),
+    "libp_multigrid_vcycle": (i32, [vp, vp, vp, vp]),
+    "libp_multigrid_free": (i32, [vp]),
+    "libp_precon_multigrid_create": (i32, [vp, i32, i64, vp, P(vp)]),
     "libp_pcg_create": (i32, [i32, i32, i32, i32, vp, P(vp)]),
     "libp_pcg_free": (i32, [vp]),
     "libp_pcg_solve_cb": (i32, [vp, OPERATOR_FN, vp, OPERATOR_FN, vp, vp, vp, f64, i32, i32, vp, P(i32)]),

@@ -403,6 +403,14 @@ class Precon:
                                                  comm.handle if comm is not None else None, C.byref(h)))
         return cls(h)
 
+    @classmethod
+    def MultiGrid(cls, mg, allNeumann=False, NglobalDofs=0, comm=None):
+        """MultiGridPrecon (solvers/elliptic/src/ellipticPreconMultiGrid.cpp:29-37)"""
+        h = C.c_void_p()
+        check(L.load().libp_precon_multigrid_create(mg.handle, int(allNeumann), int(NglobalDofs),
+                                                    comm.handle if comm is not None else None, C.byref(h)))
+        return cls(h, keep=mg)
+
     @property
     def handle(self):
         return self._h
@@ -414,6 +422,118 @@ class Precon:
         if self._h:
             L.load().libp_precon_free(self._h)
             self._h = C.c_void_p()
+
+
+# --------------------------------------------------------------------------- multigrid (apply path)
+class MGLevel:
+    """MGLevel (solvers/elliptic/ellipticPrecon.hpp:66-116): matrix-free p-multigrid level."""
+    JACOBI, CHEBYSHEV = 1, 2
+
+    def __init__(self, fine: Elliptic, coarse: Elliptic, NqF, NqC, P, invDiagA, weightG, smoother, lambda0, lambda1,
+                 ChebyshevIterations=2):
+        self.keep = (fine, coarse, P, invDiagA, weightG)
+        d = L.MGLevelDesc()
+        d.fine, d.coarse, d.NqF, d.NqC = fine.handle, coarse.handle, NqF, NqC
+        d.P, d.invDiagA, d.weightG = _ptr(P), _ptr(invDiagA), _ptr(weightG)
+        d.smoother, d.lambda0, d.lambda1, d.ChebyshevIterations = smoother, float(lambda0), float(lambda1), ChebyshevIterations
+        self._h = C.c_void_p()
+        check(L.load().libp_mglevel_create(C.byref(d), C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def Operator(self, o_x, o_Ax): check(L.load().libp_mglevel_operator(self._h, _ptr(o_x), _ptr(o_Ax), _stream()))
+    def smooth(self, o_rhs, o_x, x_is_zero): check(L.load().libp_mglevel_smooth(self._h, _ptr(o_rhs), _ptr(o_x), int(x_is_zero), _stream()))
+    def residual(self, o_rhs, o_x, o_res): check(L.load().libp_mglevel_residual(self._h, _ptr(o_rhs), _ptr(o_x), _ptr(o_res), _stream()))
+    def coarsen(self, o_x, o_Rx): check(L.load().libp_mglevel_coarsen(self._h, _ptr(o_x), _ptr(o_Rx), _stream()))
+    def prolongate(self, o_xC, o_x): check(L.load().libp_mglevel_prolongate(self._h, _ptr(o_xC), _ptr(o_x), _stream()))
+
+
+class Csr:
+    """parCSR local block (include/parAlmond/parAlmondparCSR.hpp): host numpy arrays in, device copy inside."""
+
+    def __init__(self, Nrows, Ncols, rowStarts, cols, vals, offd_nnz=0):
+        rowStarts = np.ascontiguousarray(rowStarts, dtype=np.int32)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        self.Nrows, self.Ncols = int(Nrows), int(Ncols)
+        self._h = C.c_void_p()
+        check(L.load().libp_csr_create(int(Nrows), int(Ncols), int(vals.size), _ptr(rowStarts), _ptr(cols), _ptr(vals),
+                                       int(offd_nnz), C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def SpMV(self, alpha, o_x, beta, o_y, o_z=None):
+        check(L.load().libp_csr_spmv(self._h, float(alpha), _ptr(o_x), float(beta), _ptr(o_y),
+                                     _ptr(o_y if o_z is None else o_z), _stream()))
+
+
+class AmgLevel:
+    """parAlmond::amgLevel apply (libs/parAlmond/parAlmondAMGLevel.cpp:48-84)."""
+    DAMPED_JACOBI, CHEBYSHEV = 0, 1
+
+    def __init__(self, A: Csr, P: Csr | None, R: Csr | None, diagInv, smoother, lam, lambda0, lambda1, ChebyshevIterations=2):
+        self.keep = (A, P, R)
+        diagInv = np.ascontiguousarray(diagInv, dtype=np.float64)
+        self._h = C.c_void_p()
+        check(L.load().libp_amglevel_create(A.handle, P.handle if P else None, R.handle if R else None, _ptr(diagInv),
+                                            int(smoother), float(lam), float(lambda0), float(lambda1),
+                                            int(ChebyshevIterations), C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def smooth(self, o_rhs, o_x, x_is_zero): check(L.load().libp_amglevel_smooth(self._h, _ptr(o_rhs), _ptr(o_x), int(x_is_zero), _stream()))
+    def residual(self, o_rhs, o_x, o_res): check(L.load().libp_amglevel_residual(self._h, _ptr(o_rhs), _ptr(o_x), _ptr(o_res), _stream()))
+    def coarsen(self, o_x, o_Rx): check(L.load().libp_amglevel_coarsen(self._h, _ptr(o_x), _ptr(o_Rx), _stream()))
+    def prolongate(self, o_xC, o_x): check(L.load().libp_amglevel_prolongate(self._h, _ptr(o_xC), _ptr(o_x), _stream()))
+
+
+class CoarseExact:
+    """parAlmond::exactSolver_t::solve (libs/parAlmond/parAlmondCoarseExact.cpp:35-73), single rank."""
+
+    def __init__(self, N, diagInvAT):
+        a = np.ascontiguousarray(diagInvAT, dtype=np.float64)
+        assert a.size == N * N
+        self._h = C.c_void_p()
+        check(L.load().libp_coarse_exact_create(int(N), _ptr(a), C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def solve(self, o_rhs, o_x): check(L.load().libp_coarse_solve(self._h, _ptr(o_rhs), _ptr(o_x), _stream()))
+
+
+class Multigrid:
+    """parAlmond::multigrid_t V-cycle (libs/parAlmond/parAlmondVcycle.cpp:34-60)."""
+
+    def __init__(self, comm=None):
+        self._h = C.c_void_p()
+        self.keep = []
+        check(L.load().libp_multigrid_create(comm.handle if comm is not None else None, C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def AddLevel(self, level):
+        self.keep.append(level)
+        if isinstance(level, MGLevel):
+            check(L.load().libp_multigrid_add_mglevel(self._h, level.handle))
+        else:
+            check(L.load().libp_multigrid_add_amglevel(self._h, level.handle))
+
+    def SetCoarse(self, coarse):
+        self.keep.append(coarse)
+        check(L.load().libp_multigrid_set_coarse(self._h, coarse.handle))
+
+    def Operator(self, o_rhs, o_x):
+        check(L.load().libp_multigrid_vcycle(self._h, _ptr(o_rhs), _ptr(o_x), _stream()))
 
 
 class Pcg:

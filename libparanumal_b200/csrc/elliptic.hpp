@@ -15,6 +15,7 @@ void halo_start_f64(libp_ogs_s& o, double* v, cudaStream_t s);
 void halo_finish_f64(libp_ogs_s& o, double* v, cudaStream_t s);
 void halo_combine_start_f64(libp_ogs_s& o, double* gv, cudaStream_t s);
 void halo_combine_finish_f64(libp_ogs_s& o, double* gv, cudaStream_t s);
+void multigrid_apply(void* impl, const dfloat* r, dfloat* Mr, cudaStream_t s);
 }  // namespace libp_b200
 
 struct libp_elliptic_s {
@@ -31,7 +32,7 @@ struct libp_elliptic_s {
 };
 
 struct libp_precon_s {
-  int kind = 0;  // 0 identity, 1 jacobi, 2 multigrid (later)
+  int kind = 0;  // 0 identity, 1 jacobi, 2 multigrid (impl = libp_multigrid_t, not owned)
   dlong N = 0;
   libp_b200::dev_buf<dfloat> invDiag;
   int allNeumann = 0;

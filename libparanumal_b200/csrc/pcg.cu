@@ -233,6 +233,14 @@ void libp_precon_s::apply(const dfloat* r, dfloat* Mr, cudaStream_t s) {
       LIBP_CHECK(libp_linalg_sum(N, Mr, comm, s, &sum) == LIBP_SUCCESS, libp_last_error());
       LIBP_CHECK(libp_linalg_add(N, -sum / (double)NglobalDofs, Mr, s) == LIBP_SUCCESS, libp_last_error());
     }
+  } else if (kind == 2) {
+    // MultiGridPrecon::Operator (solvers/elliptic/src/ellipticPreconMultiGrid.cpp:29-37)
+    multigrid_apply(impl, r, Mr, s);
+    if (allNeumann) {
+      double sum = 0.0;
+      LIBP_CHECK(libp_linalg_sum(N, Mr, comm, s, &sum) == LIBP_SUCCESS, libp_last_error());
+      LIBP_CHECK(libp_linalg_add(N, -sum / (double)NglobalDofs, Mr, s) == LIBP_SUCCESS, libp_last_error());
+    }
   } else {
     throw error("unsupported preconditioner kind");
   }
@@ -406,7 +414,7 @@ extern "C" int libp_pcg_solve(libp_pcg_t pcg, libp_elliptic_t A, libp_precon_t M
   LIBP_API_BEGIN
   LIBP_CHECK(pcg && A && M && x && r && iters, "null argument");
   // all-Neumann Jacobi needs a host-visible mean per apply: use the reference control flow
-  if (M->kind == 1 && M->allNeumann)
+  if (M->allNeumann)
     return libp_pcg_solve_cb(pcg, elliptic_cb, A, precon_cb, M, x, r, tol, maxit, verbose, stream, iters);
   cudaStream_t s = as_stream(stream);
   const dlong N = pcg->N;

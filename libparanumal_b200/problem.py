@@ -109,5 +109,84 @@ class EllipticProblem:
         self.ogs.Gather(r, rL.contiguous(), 1, L.ADD, L.TRANS)
         return r
 
+    def weightG(self):
+        """elliptic_t::weightG (ellipticBoundarySetup.cpp:100-110): inverse multiplicity of every gathered DOF."""
+        ones = torch.ones(self.mesh.Nelements * self.mesh.Np, dtype=torch.float64, device=self.device)
+        w = self.vec()
+        self.ogs.Gather(w, ones, 1, L.ADD, L.TRANS)
+        w[: self.Ndofs] = torch.where(w[: self.Ndofs] > 0, 1.0 / w[: self.Ndofs], w[: self.Ndofs])
+        w[self.Ndofs:] = 0
+        return w
+
     def pcg(self, flexible=False):
         return Pcg(self.Ndofs, self.Nhalo, self.comm, flexible=flexible)
+
+
+def degree_raise_1d(Nc, Nf):
+    """mesh_t::DegreeRaiseMatrix1D (libs/mesh/meshBasis1D.cpp): P[NqF, NqC], degree-Nc GLL Lagrange basis
+    evaluated at the degree-Nf GLL nodes."""
+    from .box_mesh import gll
+    rc, rf = gll(Nc)[0], gll(Nf)[0]
+    P = np.ones((Nf + 1, Nc + 1))
+    for m in range(Nc + 1):
+        for l in range(Nc + 1):
+            if l != m:
+                P[:, m] *= (rf - rc[l]) / (rc[m] - rc[l])
+    return P
+
+
+def halfdofs_ladder(N):
+    """Degree ladder of MULTIGRID COARSENING = HALFDOFS for hexes (ellipticPreconMultiGrid.cpp:69-84)."""
+    lad, Nf = [N], N
+    while Nf > 1:
+        Nc, NpF = Nf, (Nf + 1) ** 3
+        NpC = NpF
+        while NpC > NpF // 2 and Nc > 1:
+            Nc -= 1
+            NpC = (Nc + 1) ** 3
+        lad.append(Nc)
+        Nf = Nc
+    return lad
+
+
+class MultigridHierarchy:
+    """Harness-side assembly of MultiGridPrecon (solvers/elliptic/src/ellipticPreconMultiGrid.cpp:40-154) from
+    setup products: one EllipticProblem per degree of the ladder (built in the reference's order, so every
+    `unique` ogs setup consumes rand() in the same sequence), smoother parameters and the AMG levels / coarse
+    inverse that the reference's setup produced (`levels` = list of dicts, see tests/test_gpu_multigrid.py)."""
+
+    def __init__(self, fine: EllipticProblem, ladder, level_data, amg_data, coarse_invAT, coarse_N):
+        from .api import AmgLevel, CoarseExact, Csr, MGLevel, Multigrid
+        self.fine = fine
+        self.problems = []
+        m = fine.mesh
+        for Nl in list(ladder) + ([1] if ladder[-1] != 1 else []):
+            self.problems.append(EllipticProblem(Nl, m.NX, m.NY, m.NZ, lam=fine.lam, boundary_flag=m.boundary_flag,
+                                                 comm=fine.comm, device=fine.device, mode=1))
+        self.mg = Multigrid(fine.comm)
+        self.keep = []
+        for l, ld in enumerate(level_data):
+            pF, pC = self.problems[l], self.problems[l + 1]
+            P = torch.from_numpy(np.ascontiguousarray(ld["P"], dtype=np.float64)).to(fine.device)
+            inv = ld.get("invDiagA")
+            if inv is None:
+                inv = pF.inv_diagonal()[: pF.Ndofs].clone()
+                if ld["smoother"] == MGLevel.JACOBI:
+                    inv *= ld["lambda0"]
+            else:
+                inv = torch.from_numpy(np.ascontiguousarray(inv)).to(fine.device)
+            wG = pF.weightG()
+            self.keep += [P, inv, wG]
+            self.mg.AddLevel(MGLevel(pF.op, pC.op, pF.Nq, pC.Nq, P, inv, wG, ld["smoother"], ld["lambda0"], ld["lambda1"],
+                                     ld.get("ChebyshevIterations", 2)))
+        for ad in amg_data:
+            A = Csr(*ad["A"])
+            Pm = Csr(*ad["P"]) if ad.get("P") is not None else None
+            R = Csr(*ad["R"]) if ad.get("R") is not None else None
+            self.mg.AddLevel(AmgLevel(A, Pm, R, ad["diagInv"], ad["smoother"], ad["lambda"], ad["lambda0"], ad["lambda1"],
+                                      ad.get("ChebyshevIterations", 2)))
+        self.mg.SetCoarse(CoarseExact(coarse_N, coarse_invAT))
+
+    def precon(self):
+        from .api import Precon
+        return Precon.MultiGrid(self.mg, self.fine.allNeumann, self.fine.NglobalDofs, self.fine.comm)

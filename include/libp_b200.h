@@ -274,13 +274,40 @@ int libp_mglevel_prolongate(libp_mglevel_t level, libp_dfloat* xC, libp_dfloat* 
 
 /* ------------------------------------------------------------------ parAlmond CSR levels (V-cycle apply)
  * parCSR (include/parAlmond/parAlmondparCSR.hpp:35-100): local CSR block; arrays are HOST arrays produced by
- * the reference's AMGSetup (out of scope to rebuild) and are copied to the device.  This round supports the
- * single-rank case (empty off-diagonal block); a non-empty offd block is rejected with LIBP_ERROR.      */
+ * the reference's AMGSetup (out of scope to rebuild) and are copied to the device.  libp_csr_create is the
+ * single-rank form (empty off-diagonal block); libp_parcsr_create below takes the distributed matrix.
+ * Vectors multiplied by a handle need Ncols entries and are not const: the column halo is received in place. */
 int libp_csr_create(libp_dlong Nrows, libp_dlong Ncols, libp_dlong nnz, const libp_dlong* rowStarts,
                     const libp_dlong* cols, const libp_dfloat* vals, libp_dlong offd_nnz, libp_csr_t* csr);
+/* Distributed parCSR (multi-rank AMG levels): local `diag` CSR block + off-rank `offd` block in the reference's
+ * compressed-row MCSR form (parAlmondparCSR.hpp:62-79), whose column indices address the non-local columns
+ * [NlocalCols, NlocalCols+Noffdcols) of the vector.  offd_colIds are the global ids of those columns, ascending
+ * (colMap[NlocalCols:] decoded as -(colMap)-1, parAlmondparCSR.cpp:307-310), globalColStarts the column partition
+ * (size+1 entries).  parCSR::haloSetup's halo_t is replaced by a pack kernel + grouped NCCL send/recv straight
+ * into the tail of the input vector, which therefore needs NlocalCols+Noffdcols entries and is written by every
+ * product (as in the reference, where SpMV takes a non-const o_x).  Collective over `comm`.                  */
+typedef struct {
+  libp_dlong Nrows, NlocalCols;
+  libp_dlong diag_nnz;
+  const libp_dlong* diag_rowStarts; /* Nrows+1 */
+  const libp_dlong* diag_cols;
+  const libp_dfloat* diag_vals;
+  libp_dlong offd_nnz, offd_nzRows;
+  const libp_dlong* offd_rows;       /* offd_nzRows: local row of every compressed row */
+  const libp_dlong* offd_mRowStarts; /* offd_nzRows+1 */
+  const libp_dlong* offd_cols;       /* in [NlocalCols, NlocalCols+Noffdcols) */
+  const libp_dfloat* offd_vals;
+  libp_dlong Noffdcols;
+  const libp_hlong* offd_colIds;     /* Noffdcols global column ids, strictly ascending */
+  const libp_hlong* globalColStarts; /* comm size + 1 */
+} libp_parcsr_desc_t;
+int libp_parcsr_create(libp_comm_t comm, const libp_parcsr_desc_t* desc, libp_csr_t* csr);
+/* Shape and exchange lists of a CSR handle (host; for the setup checks): Ncols = NlocalCols + Noffdcols */
+int libp_csr_info(libp_csr_t csr, libp_dlong* Nrows, libp_dlong* NlocalCols, libp_dlong* Ncols, libp_dlong* Nsend,
+                  const libp_dlong** sendIds, int* NranksSend, int* NranksRecv);
 int libp_csr_free(libp_csr_t csr);
 /* parCSR::SpMV (libs/parAlmond/parAlmondparCSR.cpp:99-141): z = beta*y + alpha*A*x  (z may alias y) */
-int libp_csr_spmv(libp_csr_t A, libp_dfloat alpha, const libp_dfloat* x, libp_dfloat beta, const libp_dfloat* y,
+int libp_csr_spmv(libp_csr_t A, libp_dfloat alpha, libp_dfloat* x, libp_dfloat beta, const libp_dfloat* y,
                   libp_dfloat* z, void* stream);
 /* amgLevel (libs/parAlmond/parAlmondAMGLevel.cpp:48-84): A, P (may be NULL on the last level), R (may be NULL),
  * diagInv (host, Nrows), smoother 0 = DAMPED_JACOBI (lambda) / 1 = CHEBYSHEV (lambda0, lambda1)         */
@@ -289,12 +316,18 @@ int libp_amglevel_create(libp_csr_t A, libp_csr_t P, libp_csr_t R, const libp_df
                          libp_amglevel_t* level);
 int libp_amglevel_free(libp_amglevel_t level);
 int libp_amglevel_smooth(libp_amglevel_t level, const libp_dfloat* rhs, libp_dfloat* x, int x_is_zero, void* stream);
-int libp_amglevel_residual(libp_amglevel_t level, const libp_dfloat* rhs, const libp_dfloat* x, libp_dfloat* res, void* stream);
-int libp_amglevel_coarsen(libp_amglevel_t level, const libp_dfloat* x, libp_dfloat* Rx, void* stream);
-int libp_amglevel_prolongate(libp_amglevel_t level, const libp_dfloat* xC, libp_dfloat* x, void* stream);
+int libp_amglevel_residual(libp_amglevel_t level, const libp_dfloat* rhs, libp_dfloat* x, libp_dfloat* res, void* stream);
+int libp_amglevel_coarsen(libp_amglevel_t level, libp_dfloat* x, libp_dfloat* Rx, void* stream);
+int libp_amglevel_prolongate(libp_amglevel_t level, libp_dfloat* xC, libp_dfloat* x, void* stream);
 /* exactSolver_t::solve (libs/parAlmond/parAlmondCoarseExact.cpp:35-73): x = invA * rhs with the dense inverse
  * stored transposed, invAT[n + m*N] (host array, N*N; single rank: offdTotal == 0)                      */
 int libp_coarse_exact_create(int N, const libp_dfloat* diagInvAT, libp_coarse_t* coarse);
+/* Multi-rank exact solver: rank r owns coarse rows [coarseOffsets[r], coarseOffsets[r+1]) (= A.globalRowStarts,
+ * parAlmondCoarseExact.cpp:88-97).  diagInvAT[n + m*N] as above; offdInvAT[n + m*N] for the offdTotal =
+ * coarseTotal-N right-hand-side entries of the other ranks in ascending rank order (:120-170).  The Alltoallv of
+ * the right-hand side through the host (:60-61) becomes one grouped NCCL exchange on the device.            */
+int libp_coarse_exact_create_par(libp_comm_t comm, int N, const libp_hlong* coarseOffsets, const libp_dfloat* diagInvAT,
+                                 const libp_dfloat* offdInvAT, libp_coarse_t* coarse);
 int libp_coarse_free(libp_coarse_t coarse);
 int libp_coarse_solve(libp_coarse_t coarse, const libp_dfloat* rhs, libp_dfloat* x, void* stream);
 

@@ -124,6 +124,8 @@ SIGNATURES = {
     "libp_mglevel_coarsen": (i32, [vp, vp, vp, vp]),
     "libp_mglevel_prolongate": (i32, [vp, vp, vp, vp]),
     "libp_csr_create": (i32, [i32, i32, i32, vp, vp, vp, i32, P(vp)]),
+    "libp_parcsr_create": (i32, [vp, P(ParCsrDesc), P(vp)]),
+    "libp_csr_info": (i32, [vp, P(i32), P(i32), P(i32), P(i32), P(vp), P(i32), P(i32)]),
     "libp_csr_free": (i32, [vp]),
     "libp_csr_spmv": (i32, [vp, f64, vp, f64, vp, vp, vp]),
     "libp_amglevel_create": (i32, [vp, vp, vp, vp, i32, f64, f64, f64, i32, P(vp)]),
@@ -133,6 +135,7 @@ SIGNATURES = {
     "libp_amglevel_coarsen": (i32, [vp, vp, vp, vp]),
     "libp_amglevel_prolongate": (i32, [vp, vp, vp, vp]),
     "libp_coarse_exact_create": (i32, [i32, vp, P(vp)]),
+    "libp_coarse_exact_create_par": (i32, [vp, i32, vp, vp, vp, P(vp)]),
     "libp_coarse_free": (i32, [vp]),
     "libp_coarse_solve": (i32, [vp, vp, vp, vp]),
     "libp_multigrid_create": (i32, [vp, P(vp)]),

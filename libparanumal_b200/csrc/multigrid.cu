@@ -183,6 +183,38 @@ __global__ void __launch_bounds__(kBlock) csr_kernel(dlong Nrows, const dlong* _
     }
   }
 }
+// Off-rank block in compressed-row (MCSR) form, applied after the halo exchange on top of the diag result:
+// kMode 0: z[m] += alpha * (A_offd x)[m]          (SpMVmcsr1/2 with beta = 1)
+// kMode 1: z[m] -= dInv[m] * (A_offd x)[m]        (SmoothChebyshevMCSR)
+// kMode 2: z[m] -= alpha * dInv[m] * (A_offd x)[m] (SmoothJacobiMCSR)
+template <int kMode>
+__global__ void __launch_bounds__(kBlock) mcsr_kernel(dlong nzRows, const dlong* __restrict__ rows,
+                                                      const dlong* __restrict__ mRowStarts, const dlong* __restrict__ cols,
+                                                      const double* __restrict__ vals, double alpha,
+                                                      const double* __restrict__ dInv, const double* __restrict__ x,
+                                                      double* z) {
+  const int lane = threadIdx.x & 3;
+  for (dlong row = (blockIdx.x * kBlock + threadIdx.x) >> 2; row < ((nzRows + 63) & ~63); row += (gridDim.x * kBlock) >> 2) {
+    double acc = 0.0;
+    if (row < nzRows) {
+      const dlong s = mRowStarts[row], e = mRowStarts[row + 1];
+      for (dlong g = s + lane; g < e; g += 4) acc += vals[g] * x[cols[g]];
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (row < nzRows && lane == 0) {
+      const dlong m = rows[row];
+      if (kMode == 0) z[m] += alpha * acc;
+      else if (kMode == 1) z[m] -= dInv[m] * acc;
+      else z[m] -= alpha * dInv[m] * acc;
+    }
+  }
+}
+// pack the locally owned entries the neighbours asked for (parCSR halo, extract of ogsKernels.okl:167-177)
+__global__ void __launch_bounds__(kBlock) csr_pack_kernel(dlong N, const dlong* __restrict__ ids, const double* __restrict__ x,
+                                                          double* __restrict__ out) {
+  for (dlong n = blockIdx.x * kBlock + threadIdx.x; n < N; n += gridDim.x * kBlock) out[n] = x[ids[n]];
+}
 // SmoothChebyshevStart: r = dInv .* b ; d = lambda*r ; x = d
 __global__ void __launch_bounds__(kBlock) csr_cheb_start_kernel(dlong N, double lambda, const double* __restrict__ dInv,
                                                                 const double* __restrict__ b, double* __restrict__ r,
@@ -205,13 +237,13 @@ __global__ void __launch_bounds__(kBlock) csr_cheb_update_kernel(dlong N, double
     x[n] += dn;
   }
 }
-// dense coarse solve: x[n] = sum_m invAT[n + m*N] * rhs[m]   (one warp per row, fixed shuffle tree)
-__global__ void __launch_bounds__(kBlock) dense_gemv_kernel(int N, const double* __restrict__ AT, const double* __restrict__ rhs,
-                                                            double* __restrict__ x) {
+// dense coarse solve: x[n] = sum_{m<M} invAT[n + m*N] * rhs[m]   (one warp per row, fixed shuffle tree)
+__global__ void __launch_bounds__(kBlock) dense_gemv_kernel(int N, int M, const double* __restrict__ AT,
+                                                            const double* __restrict__ rhs, double* __restrict__ x) {
   const int warp = (blockIdx.x * kBlock + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= N) return;
   double acc = 0.0;
-  for (int m = lane; m < N; m += 32) acc += AT[(size_t)warp + (size_t)m * N] * rhs[m];
+  for (int m = lane; m < M; m += 32) acc += AT[(size_t)warp + (size_t)m * N] * rhs[m];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) x[warp] = acc;
@@ -240,14 +272,60 @@ struct libp_mglevel_s {
 };
 
 struct libp_csr_s {
-  dlong Nrows = 0, Ncols = 0, nnz = 0;
+  dlong Nrows = 0, Ncols = 0, nnz = 0;  // Ncols = NlocalCols + Noffdcols
   dev_buf<dlong> rowStarts, cols;
   dev_buf<double> vals;
+  // ---- off-rank block + its column halo (distributed levels; empty on a single rank)
+  libp_comm_t comm = nullptr;
+  dlong NlocalCols = 0, Noffdcols = 0, offd_nnz = 0, offd_nzRows = 0;
+  dev_buf<dlong> o_rows, o_mRowStarts, o_cols;
+  dev_buf<double> o_vals;
+  std::vector<dlong> sendIds;  // my columns requested by the neighbours, grouped by destination rank
+  dev_buf<dlong> d_sendIds;
+  dev_buf<double> sendBuf;
+  std::vector<int> sendRanks, sendCounts, sendOffsets, recvRanks, recvCounts, recvOffsets;
+  cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+  bool distributed() const { return comm && comm->size > 1; }
+  ~libp_csr_s() {
+    if (ev_ready) cudaEventDestroy(ev_ready);
+    if (ev_done) cudaEventDestroy(ev_done);
+  }
+  // parCSR::halo.ExchangeStart: the owners' values of the non-local columns land in x[NlocalCols : Ncols]
+  void halo_start(double* x, cudaStream_t s) {
+    if (!distributed() || (sendRanks.empty() && recvRanks.empty())) return;
+    cudaStream_t cs = comm->comm_stream;
+    CUDA_CHECK(cudaEventRecord(ev_ready, s));
+    CUDA_CHECK(cudaStreamWaitEvent(cs, ev_ready, 0));
+    if (!sendIds.empty()) {
+      csr_pack_kernel<<<vgrid(sendIds.size()), kBlock, 0, cs>>>((dlong)sendIds.size(), d_sendIds.p, x, sendBuf.p);
+      CUDA_CHECK(cudaGetLastError());
+    }
+    comm->group_start();
+    for (size_t r = 0; r < recvRanks.size(); ++r)
+      comm->recv(x + NlocalCols + recvOffsets[r], (size_t)recvCounts[r] * sizeof(double), recvRanks[r], cs);
+    for (size_t r = 0; r < sendRanks.size(); ++r)
+      comm->send(sendBuf.p + sendOffsets[r], (size_t)sendCounts[r] * sizeof(double), sendRanks[r], cs);
+    comm->group_end();
+    CUDA_CHECK(cudaEventRecord(ev_done, cs));
+  }
+  void halo_finish(cudaStream_t s) {
+    if (!distributed() || (sendRanks.empty() && recvRanks.empty())) return;
+    CUDA_CHECK(cudaStreamWaitEvent(s, ev_done, 0));
+  }
+  // diag product on the caller's stream while the column halo is in flight, then the off-rank block
   template <int kMode>
-  void run(double alpha, double beta, const double* dInv, const double* x, const double* y, double* z, cudaStream_t s) const {
-    if (Nrows == 0) return;
-    csr_kernel<kMode><<<vgrid((size_t)Nrows * 4), kBlock, 0, s>>>(Nrows, rowStarts.p, cols.p, vals.p, alpha, beta, dInv, x, y, z);
-    CUDA_CHECK(cudaGetLastError());
+  void run(double alpha, double beta, const double* dInv, double* x, const double* y, double* z, cudaStream_t s) {
+    halo_start(x, s);
+    if (Nrows) {
+      csr_kernel<kMode><<<vgrid((size_t)Nrows * 4), kBlock, 0, s>>>(Nrows, rowStarts.p, cols.p, vals.p, alpha, beta, dInv, x, y, z);
+      CUDA_CHECK(cudaGetLastError());
+    }
+    halo_finish(s);
+    if (offd_nzRows) {
+      mcsr_kernel<kMode><<<vgrid((size_t)offd_nzRows * 4), kBlock, 0, s>>>(offd_nzRows, o_rows.p, o_mRowStarts.p, o_cols.p,
+                                                                           o_vals.p, alpha, dInv, x, z);
+      CUDA_CHECK(cudaGetLastError());
+    }
   }
 };
 
@@ -261,7 +339,15 @@ struct libp_amglevel_s {
 
 struct libp_coarse_s {
   int N = 0;
-  dev_buf<double> invAT;
+  dev_buf<double> invAT;  // [coarseTotal][N]: invAT[n + m*N], m over ALL coarse rows in global (rank) order
+  // ---- multi-rank: every rank needs the whole coarse right-hand side
+  libp_comm_t comm = nullptr;
+  int coarseTotal = 0;
+  std::vector<int> counts, offsets;  // rows per rank / first row of every rank
+  dev_buf<double> rhsAll;
+  cudaEvent_t ev = nullptr;
+  ~libp_coarse_s() { if (ev) cudaEventDestroy(ev); }
+  void solve(const double* rhs, double* x, cudaStream_t s);
 };
 
 struct libp_multigrid_s {
@@ -443,11 +529,11 @@ extern "C" int libp_csr_create(libp_dlong Nrows, libp_dlong Ncols, libp_dlong nn
                                const libp_dlong* cols, const libp_dfloat* vals, libp_dlong offd_nnz, libp_csr_t* csr) {
   LIBP_API_BEGIN
   LIBP_CHECK(csr && Nrows >= 0 && Ncols >= 0 && nnz >= 0, "bad argument");
-  LIBP_CHECK(offd_nnz == 0, "multi-rank CSR levels (non-empty off-diagonal block) are not supported in this round");
+  LIBP_CHECK(offd_nnz == 0, "a non-empty off-diagonal block needs libp_parcsr_create");
   LIBP_CHECK(Nrows == 0 || (rowStarts && (nnz == 0 || (cols && vals))), "null array");
   LIBP_CHECK(Nrows == 0 || rowStarts[Nrows] == nnz, "rowStarts does not match nnz");
   std::unique_ptr<libp_csr_s> A(new libp_csr_s());
-  A->Nrows = Nrows; A->Ncols = Ncols; A->nnz = nnz;
+  A->Nrows = Nrows; A->Ncols = Ncols; A->NlocalCols = Ncols; A->nnz = nnz;
   if (Nrows) {
     A->rowStarts.upload(rowStarts, (size_t)Nrows + 1);
     A->cols.upload(cols, (size_t)nnz);
@@ -456,12 +542,107 @@ extern "C" int libp_csr_create(libp_dlong Nrows, libp_dlong Ncols, libp_dlong nn
   *csr = A.release();
   LIBP_API_END
 }
+// parCSR with an off-rank block: parCSR::haloSetup (libs/parAlmond/parAlmondparCSR.cpp:252-330) restated as
+// "ask the owner of every non-local column for its value": the sorted global ids split into one contiguous
+// run per owner rank (the column partition is contiguous), so receives land straight in x[NlocalCols:].
+extern "C" int libp_parcsr_create(libp_comm_t comm, const libp_parcsr_desc_t* d, libp_csr_t* csr) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(comm && d && csr, "null argument");
+  LIBP_CHECK(d->Nrows >= 0 && d->NlocalCols >= 0 && d->diag_nnz >= 0 && d->offd_nnz >= 0 && d->offd_nzRows >= 0 &&
+             d->Noffdcols >= 0, "negative size");
+  LIBP_CHECK(d->Nrows == 0 || (d->diag_rowStarts && d->diag_rowStarts[d->Nrows] == d->diag_nnz), "diag rowStarts does not match nnz");
+  LIBP_CHECK(d->diag_nnz == 0 || (d->diag_cols && d->diag_vals), "null diag arrays");
+  LIBP_CHECK(d->offd_nnz == 0 || (d->offd_rows && d->offd_mRowStarts && d->offd_cols && d->offd_vals), "null offd arrays");
+  LIBP_CHECK(d->offd_nzRows == 0 || d->offd_mRowStarts[d->offd_nzRows] == d->offd_nnz, "offd mRowStarts does not match nnz");
+  LIBP_CHECK(d->globalColStarts != nullptr, "null globalColStarts");
+  LIBP_CHECK(d->Noffdcols == 0 || d->offd_colIds, "null offd_colIds");
+  const int size = comm->size, rank = comm->rank;
+  LIBP_CHECK(d->globalColStarts[rank + 1] - d->globalColStarts[rank] == (hlong)d->NlocalCols, "NlocalCols does not match the column partition");
+  for (dlong g = 0; g < d->diag_nnz; ++g) LIBP_CHECK(d->diag_cols[g] >= 0 && d->diag_cols[g] < d->NlocalCols, "diag column out of range");
+  for (dlong g = 0; g < d->offd_nnz; ++g)
+    LIBP_CHECK(d->offd_cols[g] >= d->NlocalCols && d->offd_cols[g] < d->NlocalCols + d->Noffdcols, "offd column out of range");
+  for (dlong r = 0; r < d->offd_nzRows; ++r) LIBP_CHECK(d->offd_rows[r] >= 0 && d->offd_rows[r] < d->Nrows, "offd row out of range");
+  std::unique_ptr<libp_csr_s> A(new libp_csr_s());
+  A->comm = comm;
+  A->Nrows = d->Nrows; A->NlocalCols = d->NlocalCols; A->Noffdcols = d->Noffdcols;
+  A->Ncols = d->NlocalCols + d->Noffdcols;
+  A->nnz = d->diag_nnz; A->offd_nnz = d->offd_nnz; A->offd_nzRows = d->offd_nzRows;
+  // owners of the non-local columns
+  std::vector<int64_t> want((size_t)size, 0), asked((size_t)size, 0);
+  {
+    int owner = 0;
+    for (dlong c = 0; c < d->Noffdcols; ++c) {
+      const hlong gid = d->offd_colIds[c];
+      LIBP_CHECK(c == 0 || gid > d->offd_colIds[c - 1], "offd_colIds must be strictly ascending");
+      LIBP_CHECK(gid >= d->globalColStarts[0] && gid < d->globalColStarts[size], "offd column id outside the partition");
+      while (gid >= d->globalColStarts[owner + 1]) ++owner;
+      LIBP_CHECK(owner != rank, "offd_colIds holds a locally owned column");
+      want[owner]++;
+    }
+  }
+  comm->alltoall(want.data(), asked.data(), sizeof(int64_t));
+  std::vector<int64_t> sc((size_t)size), so((size_t)size), rc((size_t)size), ro((size_t)size);
+  int64_t stot = 0, rtot = 0;
+  for (int r = 0; r < size; ++r) {
+    sc[r] = want[r] * (int64_t)sizeof(hlong); so[r] = stot; stot += sc[r];
+    rc[r] = asked[r] * (int64_t)sizeof(hlong); ro[r] = rtot; rtot += rc[r];
+    if (want[r]) {
+      A->recvRanks.push_back(r); A->recvCounts.push_back((int)want[r]); A->recvOffsets.push_back((int)(so[r] / (int64_t)sizeof(hlong)));
+    }
+    if (asked[r]) {
+      A->sendRanks.push_back(r); A->sendCounts.push_back((int)asked[r]); A->sendOffsets.push_back((int)(ro[r] / (int64_t)sizeof(hlong)));
+    }
+  }
+  std::vector<hlong> askedIds((size_t)(rtot / (int64_t)sizeof(hlong)));
+  comm->alltoallv(d->offd_colIds, sc.data(), so.data(), askedIds.data(), rc.data(), ro.data());
+  A->sendIds.resize(askedIds.size());
+  for (size_t n = 0; n < askedIds.size(); ++n) {
+    const hlong loc = askedIds[n] - d->globalColStarts[rank];
+    LIBP_CHECK(loc >= 0 && loc < (hlong)d->NlocalCols, "a neighbour asked for a column this rank does not own");
+    A->sendIds[n] = (dlong)loc;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
+    if (d->Nrows) {
+      A->rowStarts.upload(d->diag_rowStarts, (size_t)d->Nrows + 1);
+      A->cols.upload(d->diag_cols, (size_t)d->diag_nnz);
+      A->vals.upload(d->diag_vals, (size_t)d->diag_nnz);
+    }
+    if (d->offd_nzRows) {
+      A->o_rows.upload(d->offd_rows, (size_t)d->offd_nzRows);
+      A->o_mRowStarts.upload(d->offd_mRowStarts, (size_t)d->offd_nzRows + 1);
+      A->o_cols.upload(d->offd_cols, (size_t)d->offd_nnz);
+      A->o_vals.upload(d->offd_vals, (size_t)d->offd_nnz);
+    }
+    A->d_sendIds.upload(A->sendIds);
+    A->sendBuf.alloc(std::max<size_t>(A->sendIds.size(), 1));
+    CUDA_CHECK(cudaEventCreateWithFlags(&A->ev_ready, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&A->ev_done, cudaEventDisableTiming));
+  } else {
+    cudaGetLastError();
+  }
+  *csr = A.release();
+  LIBP_API_END
+}
+extern "C" int libp_csr_info(libp_csr_t A, libp_dlong* Nrows, libp_dlong* NlocalCols, libp_dlong* Ncols, libp_dlong* Nsend,
+                             const libp_dlong** sendIds, int* NranksSend, int* NranksRecv) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(A, "null handle");
+  if (Nrows) *Nrows = A->Nrows;
+  if (NlocalCols) *NlocalCols = A->comm ? A->NlocalCols : A->Ncols;
+  if (Ncols) *Ncols = A->Ncols;
+  if (Nsend) *Nsend = (dlong)A->sendIds.size();
+  if (sendIds) *sendIds = A->sendIds.data();
+  if (NranksSend) *NranksSend = (int)A->sendRanks.size();
+  if (NranksRecv) *NranksRecv = (int)A->recvRanks.size();
+  LIBP_API_END
+}
 extern "C" int libp_csr_free(libp_csr_t csr) {
   LIBP_API_BEGIN
   delete csr;
   LIBP_API_END
 }
-extern "C" int libp_csr_spmv(libp_csr_t A, libp_dfloat alpha, const libp_dfloat* x, libp_dfloat beta, const libp_dfloat* y,
+extern "C" int libp_csr_spmv(libp_csr_t A, libp_dfloat alpha, libp_dfloat* x, libp_dfloat beta, const libp_dfloat* y,
                              libp_dfloat* z, void* stream) {
   LIBP_API_BEGIN
   LIBP_CHECK(A && x && z && (beta == 0.0 || y), "null argument");
@@ -534,23 +715,48 @@ extern "C" int libp_amglevel_smooth(libp_amglevel_t L, const libp_dfloat* rhs, l
   L->smooth(rhs, x, x_is_zero != 0, as_stream(stream));
   LIBP_API_END
 }
-extern "C" int libp_amglevel_residual(libp_amglevel_t L, const libp_dfloat* rhs, const libp_dfloat* x, libp_dfloat* res, void* stream) {
+extern "C" int libp_amglevel_residual(libp_amglevel_t L, const libp_dfloat* rhs, libp_dfloat* x, libp_dfloat* res, void* stream) {
   LIBP_API_BEGIN
   LIBP_CHECK(L && rhs && x && res, "null argument");
   L->A->run<0>(-1.0, 1.0, nullptr, x, rhs, res, as_stream(stream));  // A.SpMV(-1, x, 1, rhs, res)
   LIBP_API_END
 }
-extern "C" int libp_amglevel_coarsen(libp_amglevel_t L, const libp_dfloat* x, libp_dfloat* Rx, void* stream) {
+extern "C" int libp_amglevel_coarsen(libp_amglevel_t L, libp_dfloat* x, libp_dfloat* Rx, void* stream) {
   LIBP_API_BEGIN
   LIBP_CHECK(L && L->R && x && Rx, "null argument (level has no R)");
   L->R->run<0>(1.0, 0.0, nullptr, x, nullptr, Rx, as_stream(stream));
   LIBP_API_END
 }
-extern "C" int libp_amglevel_prolongate(libp_amglevel_t L, const libp_dfloat* xC, libp_dfloat* x, void* stream) {
+extern "C" int libp_amglevel_prolongate(libp_amglevel_t L, libp_dfloat* xC, libp_dfloat* x, void* stream) {
   LIBP_API_BEGIN
   LIBP_CHECK(L && L->P && xC && x, "null argument (level has no P)");
   L->P->run<0>(1.0, 1.0, nullptr, xC, x, x, as_stream(stream));  // P.SpMV(1, xC, 1, x)
   LIBP_API_END
+}
+
+// exactSolver_t::solve (libs/parAlmond/parAlmondCoarseExact.cpp:35-73).  Multi-rank: one grouped NCCL exchange
+// replicates the coarse right-hand side (instead of D2H + MPI_Alltoallv + H2D), then one GEMV with this rank's
+// rows of the inverse.
+void libp_coarse_s::solve(const double* rhs, double* x, cudaStream_t s) {
+  const double* b = rhs;
+  int M = N;
+  if (comm && comm->size > 1 && coarseTotal > 0) {
+    const int rank = comm->rank;
+    if (N) CUDA_CHECK(cudaMemcpyAsync(rhsAll.p + offsets[rank], rhs, sizeof(double) * (size_t)N, cudaMemcpyDeviceToDevice, s));
+    comm->group_start();
+    for (int r = 0; r < comm->size; ++r) {
+      if (r == rank) continue;
+      if (counts[r]) comm->recv(rhsAll.p + offsets[r], sizeof(double) * (size_t)counts[r], r, s);
+      if (N) comm->send(rhsAll.p + offsets[rank], sizeof(double) * (size_t)N, r, s);
+    }
+    comm->group_end();
+    b = rhsAll.p;
+    M = coarseTotal;
+  }
+  if (N) {
+    dense_gemv_kernel<<<(N * 32 + kBlock - 1) / kBlock, kBlock, 0, s>>>(N, M, invAT.p, b, x);
+    CUDA_CHECK(cudaGetLastError());
+  }
 }
 
 extern "C" int libp_coarse_exact_create(int N, const libp_dfloat* diagInvAT, libp_coarse_t* coarse) {
@@ -558,7 +764,44 @@ extern "C" int libp_coarse_exact_create(int N, const libp_dfloat* diagInvAT, lib
   LIBP_CHECK(coarse && N >= 0 && (N == 0 || diagInvAT), "bad argument");
   std::unique_ptr<libp_coarse_s> c(new libp_coarse_s());
   c->N = N;
+  c->coarseTotal = N;
   if (N) c->invAT.upload(diagInvAT, (size_t)N * N);
+  *coarse = c.release();
+  LIBP_API_END
+}
+extern "C" int libp_coarse_exact_create_par(libp_comm_t comm, int N, const libp_hlong* coarseOffsets,
+                                            const libp_dfloat* diagInvAT, const libp_dfloat* offdInvAT, libp_coarse_t* coarse) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(comm && coarse && coarseOffsets && N >= 0, "bad argument");
+  const int size = comm->size, rank = comm->rank;
+  LIBP_CHECK(coarseOffsets[rank + 1] - coarseOffsets[rank] == (hlong)N, "N does not match coarseOffsets");
+  const int total = (int)(coarseOffsets[size] - coarseOffsets[0]);
+  const int offdTotal = total - N;
+  LIBP_CHECK(N == 0 || diagInvAT, "null diagInvAT");
+  LIBP_CHECK(N == 0 || offdTotal == 0 || offdInvAT, "null offdInvAT");
+  std::unique_ptr<libp_coarse_s> c(new libp_coarse_s());
+  c->comm = comm;
+  c->N = N;
+  c->coarseTotal = total;
+  for (int r = 0; r < size; ++r) {
+    c->offsets.push_back((int)(coarseOffsets[r] - coarseOffsets[0]));
+    c->counts.push_back((int)(coarseOffsets[r + 1] - coarseOffsets[r]));
+  }
+  // one [total][N] array in global row order: rows of lower ranks, own rows, rows of higher ranks
+  std::vector<double> all((size_t)N * total);
+  const size_t lo = (size_t)c->offsets[rank];
+  for (size_t m = 0; m < (size_t)total; ++m) {
+    const double* src = (m < lo) ? offdInvAT + m * N : (m < lo + N) ? diagInvAT + (m - lo) * N : offdInvAT + (m - N) * N;
+    if (N) memcpy(all.data() + m * N, src, sizeof(double) * (size_t)N);
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
+    if (N) c->invAT.upload(all);
+    c->rhsAll.alloc(std::max<size_t>((size_t)total, 1));
+    CUDA_CHECK(cudaMemset(c->rhsAll.p, 0, sizeof(double) * std::max<size_t>((size_t)total, 1)));
+  } else {
+    cudaGetLastError();
+  }
   *coarse = c.release();
   LIBP_API_END
 }
@@ -570,10 +813,7 @@ extern "C" int libp_coarse_free(libp_coarse_t coarse) {
 extern "C" int libp_coarse_solve(libp_coarse_t c, const libp_dfloat* rhs, libp_dfloat* x, void* stream) {
   LIBP_API_BEGIN
   LIBP_CHECK(c && (c->N == 0 || (rhs && x)), "null argument");
-  if (c->N) {
-    dense_gemv_kernel<<<(c->N * 32 + kBlock - 1) / kBlock, kBlock, 0, as_stream(stream)>>>(c->N, c->invAT.p, rhs, x);
-    CUDA_CHECK(cudaGetLastError());
-  }
+  c->solve(rhs, x, as_stream(stream));
   LIBP_API_END
 }
 
@@ -587,6 +827,7 @@ void libp_multigrid_s::prepare() {
     x.emplace_back(new dev_buf<double>());
     dlong ncols = (k < levels.size()) ? levels[k].Ncols : coarseN;
     if (k > 0 && levels[k - 1].kind == 0) ncols = std::max(ncols, levels[k - 1].mg->NcolsC);  // coarsen target
+    if (k > 0 && levels[k - 1].kind == 1 && levels[k - 1].amg->P) ncols = std::max(ncols, levels[k - 1].amg->P->Ncols);
     ncols = std::max<dlong>(ncols, 1);
     maxCols = std::max(maxCols, ncols);
     if (k > 0) {
@@ -603,10 +844,7 @@ void libp_multigrid_s::prepare() {
 void libp_multigrid_s::vcycle(int k, const double* rhs_k, double* x_k, cudaStream_t s) {
   if (k == (int)levels.size()) {
     LIBP_CHECK(coarse != nullptr, "multigrid has no coarse solver");
-    if (coarse->N) {
-      dense_gemv_kernel<<<(coarse->N * 32 + kBlock - 1) / kBlock, kBlock, 0, s>>>(coarse->N, coarse->invAT.p, rhs_k, x_k);
-      CUDA_CHECK(cudaGetLastError());
-    }
+    coarse->solve(rhs_k, x_k, s);
     return;
   }
   Level& L = levels[k];
@@ -651,7 +889,9 @@ extern "C" int libp_multigrid_add_mglevel(libp_multigrid_t mg, libp_mglevel_t le
 extern "C" int libp_multigrid_add_amglevel(libp_multigrid_t mg, libp_amglevel_t level) {
   LIBP_API_BEGIN
   LIBP_CHECK(mg && level, "null argument");
-  mg->levels.push_back({1, nullptr, level, level->A->Nrows, std::max(level->A->Ncols, level->A->Nrows)});
+  dlong ncols = std::max(level->A->Ncols, level->A->Nrows);
+  if (level->R) ncols = std::max(ncols, level->R->Ncols);  // the residual is R's input vector
+  mg->levels.push_back({1, nullptr, level, level->A->Nrows, ncols});
   mg->rhs.clear();
   LIBP_API_END
 }

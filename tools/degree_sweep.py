@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""BASELINE configs[4]: Hex3D N=3..8 at ~30 M DOF per GPU (SURVEY section 8d, C5 box sizes), single rank or under
+torchrun (weak scaling: every rank owns one such box, the global box is the Factor3 arrangement of them).
+Prints one JSON line per degree: operator and Jacobi-PCG GDOF/s with their fractions of the HBM roofline."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from libparanumal_b200 import api  # noqa: E402
+from libparanumal_b200.api import Comm  # noqa: E402
+from libparanumal_b200.box_mesh import factor3  # noqa: E402
+from libparanumal_b200.problem import EllipticProblem  # noqa: E402
+
+BOX = {1: 310, 2: 155, 3: 104, 4: 78, 5: 62, 6: 52, 7: 44, 8: 39}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--degrees", default="3,4,5,6,7,8")
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--pcg-iters", type=int, default=30)
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the per-GPU box edge (smoke runs)")
+    a = ap.parse_args()
+    import torch.distributed as dist
+    world, rank, lr = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    api.init(lr)
+    gloo = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+        gloo = dist.new_group(backend="gloo")
+    comm = Comm(rank, world, gloo)
+    comm.init_nccl()
+    if world > 1 and os.environ.get("LIBP_P2P", "1") != "0":
+        comm.init_p2p()
+    peak = 6650.0
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peak = float(json.load(open(pk))["hbm_gbs"])
+    sx, sy, sz = factor3(world)
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for N in [int(x) for x in a.degrees.split(",")]:
+        n = max(2, int(round(BOX[N] * a.scale)))
+        for lam in (0.0, 1.0):
+            p = EllipticProblem(N, n * sx, n * sy, n * sz, lam=lam, comm=comm, coords=(lam != 0.0))
+            E, Np = p.mesh.Nelements, p.mesh.Np
+            out = {"N": N, "elements_per_gpu": [n, n, n], "n_gpus": world, "lambda": lam, "global_dofs": int(p.NglobalDofs),
+                   "local_dofs": int(p.Ndofs)}
+            ax_bytes = 8.0 * (6 + (lam != 0.0)) * E * Np + 16.0 * p.Ndofs
+            if lam == 0.0:
+                q, Aq = p.vec(), p.vec()
+                q[: p.Ndofs] = torch.rand(p.Ndofs, dtype=torch.float64, device="cuda") * 2 - 1
+                for _ in range(5):
+                    p.op.Operator(q, Aq)
+                ms = timed(lambda: p.op.Operator(q, Aq), a.steps) / a.steps
+                out.update(kind="operator", ms=ms, gdofs=p.NglobalDofs / ms / 1e6, roofline_frac=ax_bytes / ms / 1e6 / peak)
+                del q, Aq
+            else:
+                M, r0, solver = p.jacobi(), p.rhs_sine3d(), p.pcg()
+                x, r = p.vec(), r0.clone()
+                solver.Solve(p.op, M, x, r, tol=1e-30, maxit=3)
+                x.zero_(); r.copy_(r0)
+                res = {}
+                def solve():
+                    res["it"] = solver.Solve(p.op, M, x, r, tol=1e-30, maxit=a.pcg_iters)
+                ms = timed(solve, 1) / max(res["it"], 1)
+                it_bytes = ax_bytes + 88.0 * p.Ndofs
+                out.update(kind="jacobi_pcg", ms=ms, gdofs=p.NglobalDofs / ms / 1e6, roofline_frac=it_bytes / ms / 1e6 / peak,
+                           iterations=res["it"])
+                del M, r0, solver, x, r
+            if rank == 0:
+                print(json.dumps(out), flush=True)
+            p.op.Free()
+            del p
+            torch.cuda.empty_cache()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

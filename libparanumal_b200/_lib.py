@@ -52,6 +52,12 @@ class MGLevelDesc(C.Structure):
                 ("smoother", i32), ("lambda0", f64), ("lambda1", f64), ("ChebyshevIterations", i32)]
 
 
+class ParCsrDesc(C.Structure):
+    _fields_ = [("Nrows", i32), ("NlocalCols", i32), ("diag_nnz", i32), ("diag_rowStarts", vp), ("diag_cols", vp),
+                ("diag_vals", vp), ("offd_nnz", i32), ("offd_nzRows", i32), ("offd_rows", vp), ("offd_mRowStarts", vp),
+                ("offd_cols", vp), ("offd_vals", vp), ("Noffdcols", i32), ("offd_colIds", vp), ("globalColStarts", vp)]
+
+
 OPERATOR_FN = C.CFUNCTYPE(i32, vp, vp, vp, vp)
 
 # name -> (restype, argtypes); every symbol include/libp_b200.h declares

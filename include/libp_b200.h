@@ -201,6 +201,13 @@ typedef struct {
 } libp_elliptic_desc_t;
 int libp_elliptic_create(const libp_elliptic_desc_t* desc, libp_elliptic_t* op);
 int libp_elliptic_free(libp_elliptic_t op);
+/* Fused mode only (no reference counterpart; tuning of this implementation): the element lists are run in
+ * pieces of `chunkElements` elements and the accumulator o_Aq is zero-filled piece by piece, just ahead of
+ * the reductions that land in it, so the zero lines are still in L2 (saves one DRAM read + one write of the
+ * result vector per apply).  0 = one zero-fill and three launches, the reference split.  The default applies
+ * to handles created afterwards. */
+int libp_elliptic_set_chunk(libp_elliptic_t op, libp_dlong chunkElements);
+int libp_elliptic_set_default_chunk(libp_dlong chunkElements);
 /* o_q and o_Aq are gathered vectors of Ndofs+Nhalo entries; the Nhalo tail of o_q is
  * overwritten by the halo exchange exactly like the reference.         */
 int libp_elliptic_operator(libp_elliptic_t op, libp_dfloat* q, libp_dfloat* Aq, void* stream);

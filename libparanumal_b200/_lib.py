@@ -98,6 +98,8 @@ SIGNATURES = {
     "libp_ax_hex3d_unregister_D": (i32, [vp]),
     "libp_ax_hex3d_tune": (i32, [i32, i32, i32]),
     "libp_elliptic_create": (i32, [P(EllipticDesc), P(vp)]),
+    "libp_elliptic_set_chunk": (i32, [vp, i32]),
+    "libp_elliptic_set_default_chunk": (i32, [i32]),
     "libp_elliptic_free": (i32, [vp]),
     "libp_elliptic_operator": (i32, [vp, vp, vp, vp]),
     "libp_linalg_set": (i32, [i32, f64, vp, vp]),

@@ -150,6 +150,24 @@ class Comm:
         outs = self._gloo_a2a_lists(chunks, rcounts)
         r.copy_(torch.cat(outs))
 
+    def allgather_object(self, obj):
+        """setup-time host collective (comm_t::Allgatherv of setup arrays): list of every rank's object"""
+        if self.size == 1:
+            return [obj]
+        import torch.distributed as dist
+        out = [None] * self.size
+        dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def allreduce_sum(self, x):
+        """setup-time host all-reduce of a python float / numpy array"""
+        if self.size == 1:
+            return x
+        import torch.distributed as dist
+        t = torch.as_tensor(np.asarray(x, dtype=np.float64)).clone().reshape(-1)
+        dist.all_reduce(t, group=self.group)
+        return float(t[0]) if np.ndim(x) == 0 else t.numpy().reshape(np.shape(x))
+
     def init_nccl(self):
         """NCCL bootstrap: rank 0 creates the unique id, torch.distributed broadcasts it."""
         if self.size == 1:
@@ -340,6 +358,10 @@ class Elliptic:
     def handle(self):
         return self._h
 
+    def set_chunk(self, chunk_elements):
+        """elements per zero-fill piece of the fused operator (0 = off); see libp_elliptic_set_chunk"""
+        check(L.load().libp_elliptic_set_chunk(self._h, int(chunk_elements)))
+
     def Operator(self, o_q, o_Aq):
         check(L.load().libp_elliptic_operator(self._h, _ptr(o_q), _ptr(o_Aq), _stream()))
 
@@ -471,6 +493,20 @@ class Csr:
                                      _ptr(o_y if o_z is None else o_z), _stream()))
 
 
+class ParCsr(Csr):
+    """Distributed parCSR row block (libp_parcsr_create): `d` is the dict amg_setup.split_rows returns."""
+
+    def __init__(self, comm, d):
+        self.keep = d
+        self.Nrows, self.Ncols = int(d["Nrows"]), int(d["NlocalCols"]) + int(d["offd_colIds"].size)
+        desc = L.ParCsrDesc(int(d["Nrows"]), int(d["NlocalCols"]), int(d["diag_vals"].size), _ptr(d["diag_rowStarts"]),
+                            _ptr(d["diag_cols"]), _ptr(d["diag_vals"]), int(d["offd_vals"].size), int(d["offd_rows"].size),
+                            _ptr(d["offd_rows"]), _ptr(d["offd_mRowStarts"]), _ptr(d["offd_cols"]), _ptr(d["offd_vals"]),
+                            int(d["offd_colIds"].size), _ptr(d["offd_colIds"]), _ptr(d["globalColStarts"]))
+        self._h = C.c_void_p()
+        check(L.load().libp_parcsr_create(comm.handle, C.byref(desc), C.byref(self._h)))
+
+
 class AmgLevel:
     """parAlmond::amgLevel apply (libs/parAlmond/parAlmondAMGLevel.cpp:48-84)."""
     DAMPED_JACOBI, CHEBYSHEV = 0, 1
@@ -507,6 +543,18 @@ class CoarseExact:
         return self._h
 
     def solve(self, o_rhs, o_x): check(L.load().libp_coarse_solve(self._h, _ptr(o_rhs), _ptr(o_x), _stream()))
+
+
+class CoarseExactPar(CoarseExact):
+    """exactSolver_t on P ranks (parAlmondCoarseExact.cpp:80-196): rank r owns rows [offsets[r], offsets[r+1])."""
+
+    def __init__(self, comm, N, coarseOffsets, diagInvAT, offdInvAT):
+        off = np.ascontiguousarray(coarseOffsets, dtype=np.int64)
+        a = np.ascontiguousarray(diagInvAT, dtype=np.float64)
+        b = np.ascontiguousarray(offdInvAT, dtype=np.float64)
+        assert a.size == N * N and b.size == N * (int(off[-1]) - N)
+        self._h = C.c_void_p()
+        check(L.load().libp_coarse_exact_create_par(comm.handle, int(N), _ptr(off), _ptr(a), _ptr(b), C.byref(self._h)))
 
 
 class Multigrid:

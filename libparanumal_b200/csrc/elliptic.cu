@@ -7,7 +7,64 @@
 // mode 1 fuses the gather into the Ax epilogue (FP64 reductions straight into Aq).
 #include "elliptic.hpp"
 
+#include <vector>
+
+#ifndef LIBP_AX_CHUNK_DEFAULT
+#define LIBP_AX_CHUNK_DEFAULT 0  // elements per zero-fill piece of the fused operator (0 = off); see elliptic.hpp
+#endif
+
 using namespace libp_b200;
+
+namespace {
+dlong g_default_chunk = LIBP_AX_CHUNK_DEFAULT;
+
+// largest local gathered id (< limit) touched by each piece of an element list
+__global__ void __launch_bounds__(256) piece_max_kernel(const dlong* __restrict__ list, const dlong* __restrict__ G2L,
+                                                        int Np, dlong chunk, dlong n, dlong limit, int* __restrict__ mx) {
+  const dlong p0 = (dlong)blockIdx.x * chunk;
+  const dlong cnt = min(chunk, n - p0);
+  int m = -1;
+  for (size_t i = (size_t)blockIdx.y * blockDim.x + threadIdx.x; i < (size_t)cnt * Np; i += (size_t)gridDim.y * blockDim.x) {
+    const dlong e = list[p0 + (dlong)(i / Np)];
+    const dlong id = G2L[(size_t)e * Np + (i % Np)];
+    if (id < limit && id > m) m = id;
+  }
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m >= 0) atomicMax(&mx[blockIdx.x], m);
+}
+}  // namespace
+
+void libp_elliptic_s::build_plan(cudaStream_t s) {
+  plan.clear();
+  plan_built = true;
+  if (!chunked()) return;
+  libp_ogs_s& ogs = *d.ogsMasked;
+  const dlong nL = d.NlocalGatherElements, nG = d.NglobalGatherElements, nL0 = nL / 2;
+  const dlong limit = ogs.NlocalT;  // the shared rows behind NlocalT are zero-filled up front (small)
+  struct Seg { int phase; const dlong* list; dlong off, n; };
+  const Seg segs[3] = {{0, d.localGatherElementList, 0, nL0}, {1, d.globalGatherElementList, 0, nG},
+                       {2, d.localGatherElementList, nL0, nL - nL0}};
+  dlong hi = 0;
+  for (const Seg& sg : segs) {
+    if (sg.n <= 0) continue;
+    const int np = (int)((sg.n + chunk - 1) / chunk);
+    dev_buf<int> mx;
+    mx.alloc((size_t)np);
+    CUDA_CHECK(cudaMemsetAsync(mx.p, 0xff, sizeof(int) * (size_t)np, s));
+    piece_max_kernel<<<dim3(np, 32), 256, 0, s>>>(sg.list + sg.off, d.GlobalToLocal, Np, chunk, sg.n, limit, mx.p);
+    CUDA_CHECK(cudaGetLastError());
+    std::vector<int> h((size_t)np);
+    CUDA_CHECK(cudaMemcpyAsync(h.data(), mx.p, sizeof(int) * (size_t)np, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int k = 0; k < np; ++k) {
+      AxPiece pc{sg.phase, sg.off + (dlong)k * chunk, std::min<dlong>(chunk, sg.n - (dlong)k * chunk), hi, hi};
+      if (h[(size_t)k] + 1 > hi) hi = h[(size_t)k] + 1;
+      pc.z1 = hi;
+      plan.push_back(pc);
+    }
+  }
+  tail0 = hi;  // rows behind the running maximum (the shared rows, ids no element touches) are zero-filled up front
+}
 
 void libp_elliptic_s::apply(dfloat* q, dfloat* Aq, bool want_dot, const int* doneFlag, cudaStream_t s, bool zeroed) {
   libp_ogs_s& ogs = *d.ogsMasked;
@@ -23,6 +80,30 @@ void libp_elliptic_s::apply(dfloat* q, dfloat* Aq, bool want_dot, const int* don
                              dp ? dp + doff : nullptr, doneFlag, s);
     doff += nb;
   };
+  if (chunked()) {
+    // slab-wise zero-fill: see AxPiece.  `zeroed` callers (PCG) skip their own zero-fill when chunked().
+    if (!plan_built) build_plan(s);
+    const dlong total = ogs.NlocalT + ogs.NhaloT;
+    if (!zeroed && total > tail0)
+      CUDA_CHECK(cudaMemsetAsync(Aq + tail0, 0, sizeof(dfloat) * (size_t)(total - tail0), s));
+    auto run = [&](int phase) {
+      for (const AxPiece& pc : plan) {
+        if (pc.phase != phase) continue;
+        if (!zeroed && pc.z1 > pc.z0)
+          CUDA_CHECK(cudaMemsetAsync(Aq + pc.z0, 0, sizeof(dfloat) * (size_t)(pc.z1 - pc.z0), s));
+        ax(pc.count, (phase == 1 ? d.globalGatherElementList : d.localGatherElementList) + pc.start);
+      }
+    };
+    halo_start_f64(ogs, q, s);
+    run(0);
+    halo_finish_f64(ogs, q, s);
+    run(1);
+    halo_combine_start_f64(ogs, Aq, s);
+    run(2);
+    halo_combine_finish_f64(ogs, Aq, s);
+    nDotPartials = doff;
+    return;
+  }
   if (fused && !zeroed)
     CUDA_CHECK(cudaMemsetAsync(Aq, 0, sizeof(dfloat) * (size_t)(ogs.NlocalT + ogs.NhaloT), s));
   halo_start_f64(ogs, q, s);
@@ -63,10 +144,35 @@ extern "C" int libp_elliptic_create(const libp_elliptic_desc_t* desc, libp_ellip
   e->Ndofs = desc->ogsMasked->Ngather;
   e->Nhalo = desc->ogsMasked->NhaloT - desc->ogsMasked->NhaloP;
   if (desc->mode == 0) e->AqL.alloc((size_t)desc->Nelements * e->Np);
-  e->dotPartials.alloc((size_t)ax_hex3d_blocks(desc->Nq, desc->NlocalGatherElements / 2) +
-                       ax_hex3d_blocks(desc->Nq, (desc->NlocalGatherElements + 1) / 2) +
-                       ax_hex3d_blocks(desc->Nq, desc->NglobalGatherElements) + 4);
+  e->chunk = (desc->mode == 1) ? g_default_chunk : 0;
+  e->alloc_dot_partials();
   *op = e.release();
+  LIBP_API_END
+}
+
+void libp_elliptic_s::alloc_dot_partials() {
+  // one partial per Ax block: every piece of the plan rounds its block count up
+  const dlong pieces = chunk > 0 ? d.Nelements / chunk + 4 : 0;
+  dotPartials.alloc((size_t)ax_hex3d_blocks(d.Nq, d.NlocalGatherElements / 2) +
+                    ax_hex3d_blocks(d.Nq, (d.NlocalGatherElements + 1) / 2) +
+                    ax_hex3d_blocks(d.Nq, d.NglobalGatherElements) + 4 + (size_t)pieces);
+}
+
+extern "C" int libp_elliptic_set_chunk(libp_elliptic_t op, libp_dlong chunkElements) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(op && chunkElements >= 0, "bad argument");
+  if (op->d.mode != 1) chunkElements = 0;
+  op->chunk = chunkElements;
+  op->plan_built = false;
+  op->plan.clear();
+  op->alloc_dot_partials();
+  LIBP_API_END
+}
+
+extern "C" int libp_elliptic_set_default_chunk(libp_dlong chunkElements) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(chunkElements >= 0, "bad argument");
+  g_default_chunk = chunkElements;
   LIBP_API_END
 }
 

@@ -1,5 +1,7 @@
 // Internal handles of the elliptic operator / preconditioners / PCG.
 #pragma once
+#include <vector>
+
 #include "common.hpp"
 #include "ogs.hpp"
 
@@ -26,6 +28,18 @@ struct libp_elliptic_s {
   libp_b200::dev_buf<dfloat> AqL;          // mode 0 scratch, Nelements*Np
   libp_b200::dev_buf<dfloat> dotPartials;  // one per Ax block (p.Ap partial sums)
   int nDotPartials = 0;
+  // ---- slab-wise zero-fill of the fused accumulator (mode 1).  The element lists are cut into pieces of
+  // `chunk` elements; before piece k runs, only the part of Aq that piece k is the first to touch is zero-filled
+  // ([z0, z1) = ids below the running maximum of the connectivity), so the zero lines are still in the 126 MB L2
+  // when the reductions arrive: the accumulator costs one DRAM write per line instead of write + read + write.
+  struct AxPiece { int phase; dlong start, count, z0, z1; };
+  std::vector<AxPiece> plan;
+  dlong chunk = 0;       // elements per piece, 0 = one zero-fill + three launches (reference split)
+  bool plan_built = false;
+  dlong tail0 = 0;       // [tail0, NlocalT+NhaloT): rows no piece owns (shared rows), zero-filled up front
+  void alloc_dot_partials();
+  void build_plan(cudaStream_t s);
+  bool chunked() const { return d.mode == 1 && chunk > 0; }
   // apply; when dot/doneFlag are given the p.Ap partials are produced and the kernels early-exit
   // zeroed: the caller already zero-filled Aq[0 : NlocalT+NhaloT] (PCG folds it into its p-update pass)
   void apply(dfloat* q, dfloat* Aq, bool want_dot, const int* doneFlag, cudaStream_t s, bool zeroed = false);

@@ -121,6 +121,46 @@ class EllipticProblem:
     def pcg(self, flexible=False):
         return Pcg(self.Ndofs, self.Nhalo, self.comm, flexible=flexible)
 
+    def global_numbering(self):
+        """Global number of every gathered DOF this rank sees (owned, then halo) and the row partition
+        (elliptic_t::maskedGlobalNumbering, ellipticSetup.cpp; A.globalRowStarts,
+        ellipticBuildOperatorMatrixContinuous.cpp:699-710)."""
+        counts = np.array([int(c) for c in self.comm.allgather_object(int(self.Ndofs))], dtype=np.int64)
+        starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        num = torch.full((self.Nall,), -1, dtype=torch.int64, device=self.device)
+        num[: self.Ndofs] = torch.arange(self.Ndofs, dtype=torch.int64, device=self.device) + int(starts[self.comm.rank])
+        if self.comm.size > 1 and self.Nhalo > 0:
+            self.ogs.Exchange(num)
+        return num, starts
+
+    def operator_matrix(self, threshold=1e-7):
+        """BuildOperatorMatrixContinuousHex3D (ellipticBuildOperatorMatrixContinuous.cpp:697-870): unassembled
+        element matrices A_e = sum_ab D_a^T diag(G_ab) D_b + lambda diag(wJ) with masked rows/columns removed and
+        entries below `threshold` dropped, as (global row, global col, value) triplets + the row partition."""
+        from .amg_setup import element_matrix_triplets
+        m = self.mesh
+        num, starts = self.global_numbering()
+        gid = torch.where(self.GlobalToLocal >= 0, num[self.GlobalToLocal.clamp(min=0).long()],
+                          torch.full_like(self.GlobalToLocal, -1, dtype=torch.int64))
+        r, c, v = element_matrix_triplets(self.Nq, m.ggeo, m.wJ, m.D, self.lam, gid, threshold)
+        return r, c, v, starts
+
+    def max_eig_smooth_ax(self, invDiag, rng):
+        """MGLevel::maxEigSmoothAx (ellipticPreconMultiGridLevel.cpp:393-473): Arnoldi estimate of
+        rho(D^-1 A) from a drand48 start vector, with this problem's device operator."""
+        from .amg_setup import arnoldi_rho
+        n = self.Ndofs
+        buf, out = self.vec(), self.vec()
+
+        def apply(v):
+            buf[:n] = v
+            self.op.Operator(buf, out)
+            return out[:n] * invDiag[:n]
+
+        dot = lambda a, b: self.comm.allreduce_sum(float(torch.dot(a, b)))
+        v0 = torch.from_numpy(rng.draw(n)).to(self.device)
+        return arnoldi_rho(apply, v0, self.NglobalDofs, dot=dot)
+
 
 def degree_raise_1d(Nc, Nf):
     """mesh_t::DegreeRaiseMatrix1D (libs/mesh/meshBasis1D.cpp): P[NqF, NqC], degree-Nc GLL Lagrange basis
@@ -190,3 +230,92 @@ class MultigridHierarchy:
     def precon(self):
         from .api import Precon
         return Precon.MultiGrid(self.mg, self.fine.allNeumann, self.fine.NglobalDofs, self.fine.comm)
+
+    @classmethod
+    def build(cls, fine: EllipticProblem, smoother="CHEBYSHEV", chebyshev_degree=2, amg_smoother=None,
+              strength="SYMMETRIC", aggregation="SMOOTHED", coarse_target=1000, level_rho=None):
+        """MultiGridPrecon::MultiGridPrecon (ellipticPreconMultiGrid.cpp:40-154) without the reference: the
+        HALFDOFS degree ladder, one problem per degree (built in the reference's order: every `unique` ogs setup
+        consumes rand() in sequence), Chebyshev/Jacobi bounds from the Arnoldi estimate on the device operator,
+        the degree-1 matrix, and the algebraic levels of amg_setup.setup_hierarchy split into row blocks.
+        Smoothers: "CHEBYSHEV" (degree `chebyshev_degree`) or "DAMPEDJACOBI" (MULTIGRID SMOOTHER /
+        PARALMOND SMOOTHER, ellipticSettings / parAlmondSettings.cpp:35-53).  level_rho: optional list of
+        rho(D^-1 A) for the matrix-free levels (skips their Arnoldi estimates, e.g. to run the very same
+        preconditioner on a different number of ranks)."""
+        import scipy.sparse as sp
+
+        from . import amg_setup as am
+        from .api import AmgLevel, CoarseExact, CoarseExactPar, Csr, MGLevel, Multigrid, ParCsr
+        self = cls.__new__(cls)
+        comm, m = fine.comm, fine.mesh
+        rank, size = comm.rank, comm.size
+        amg_smoother = smoother if amg_smoother is None else amg_smoother
+        ladder = halfdofs_ladder(fine.N)
+        self.fine, self.ladder = fine, ladder
+        self.problems = []
+        for Nl in ladder:  # SetupNewDegree(Nf) for every ladder degree, then degree 1 (already last on the ladder)
+            self.problems.append(EllipticProblem(Nl, m.NX, m.NY, m.NZ, lam=fine.lam, boundary_flag=m.boundary_flag,
+                                                 comm=comm, device=fine.device, mode=1))
+        self.mg = Multigrid(comm)
+        self.keep = []
+        rng = am.Drand48(rank)      # srand48(rank), parAlmondKernels.cpp:56-58
+        drawn_global = 0            # position of a one-rank stream after the p-MG levels (AMG setup stream)
+        self.level_info = []
+        for l in range(len(ladder) - 1):
+            pF, pC = self.problems[l], self.problems[l + 1]
+            P = torch.from_numpy(degree_raise_1d(pC.N, pF.N)).to(fine.device).contiguous()
+            inv = pF.inv_diagonal()[: pF.Ndofs].clone()
+            rho = float(level_rho[l]) if level_rho is not None else pF.max_eig_smooth_ax(inv, rng)
+            drawn_global += int(pF.NglobalDofs)
+            if smoother == "CHEBYSHEV":
+                kind, l0, l1 = MGLevel.CHEBYSHEV, rho / 10.0, rho
+            else:
+                kind, l0, l1 = MGLevel.JACOBI, (4.0 / 3.0) / rho, 0.0
+                inv *= l0
+            wG = pF.weightG()
+            self.keep += [P, inv, wG]
+            self.mg.AddLevel(MGLevel(pF.op, pC.op, pF.Nq, pC.Nq, P, inv, wG, kind, l0, l1, chebyshev_degree))
+            self.level_info.append(dict(kind="pMG", degree=pF.N, rows=int(pF.NglobalDofs), rho=rho))
+        # ---- degree-1 matrix, replicated (BuildOperatorMatrixContinuous + parCSR(cooA))
+        p1 = self.problems[-1]
+        r_, c_, v_, starts = p1.operator_matrix()
+        parts = comm.allgather_object((r_, c_, v_))
+        ntot = int(starts[-1])
+        A = sp.coo_matrix((np.concatenate([p[2] for p in parts]),
+                           (np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]))),
+                          shape=(ntot, ntot)).tocsr()
+        del parts
+        # ---- algebraic hierarchy: the one-rank algorithm on the global matrix, same on every rank
+        arng = am.Drand48(0)
+        arng.draw(drawn_global)
+        null = np.full(ntot, 1.0 / np.sqrt(ntot))
+        levels, Ac, rho_c = am.setup_hierarchy(A, null, arng, coarse_target, strength, aggregation)
+        self.amg_levels, self.coarse_A = levels, Ac
+        part = np.asarray(starts, dtype=np.int64)
+        cheb = amg_smoother == "CHEBYSHEV"
+        for lv in levels:
+            cpart = am.coarse_partition(part, lv["roots"])
+            dInv = 1.0 / lv["A"].diagonal()[part[rank]: part[rank + 1]]
+            if size == 1:
+                mk = lambda M, rp, cp: Csr(M.shape[0], M.shape[1], M.indptr, M.indices, M.data)
+            else:
+                mk = lambda M, rp, cp: ParCsr(comm, am.split_rows(M, rp, cp, rank))
+            cA, cP, cR = mk(lv["A"], part, part), mk(lv["P"], part, cpart), mk(lv["R"], cpart, part)
+            rho = lv["rho"]
+            self.mg.AddLevel(AmgLevel(cA, cP, cR, dInv, AmgLevel.CHEBYSHEV if cheb else AmgLevel.DAMPED_JACOBI,
+                                      (4.0 / 3.0) / rho, rho / 10.0, rho, chebyshev_degree))
+            self.level_info.append(dict(kind="AMG", rows=int(lv["A"].shape[0]), nnz=int(lv["A"].nnz), rho=rho))
+            part = cpart
+        # ---- exact coarse solve (exactSolver_t::setup): dense inverse, stored transposed
+        inv = np.linalg.inv(Ac.toarray())
+        n0, n1 = int(part[rank]), int(part[rank + 1])
+        N = n1 - n0
+        diagT = np.ascontiguousarray(inv[n0:n1, n0:n1].T)          # diagInvAT[n + m*N] = inv[n0+n, n0+m]
+        if size == 1:
+            self.mg.SetCoarse(CoarseExact(N, diagT.reshape(-1)))
+        else:
+            others = np.concatenate([np.arange(0, n0), np.arange(n1, Ac.shape[0])])
+            offdT = np.ascontiguousarray(inv[n0:n1][:, others].T)  # offdInvAT[n + m*N], other ranks' rows ascending
+            self.mg.SetCoarse(CoarseExactPar(comm, N, part, diagT.reshape(-1), offdT.reshape(-1)))
+        self.level_info.append(dict(kind="exact", rows=int(Ac.shape[0]), nnz=int(Ac.nnz)))
+        return self

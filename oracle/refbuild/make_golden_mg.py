@@ -27,7 +27,12 @@ CONFIGS = {
     "mg_n2_e12": dict(N=2, n=12, flag=1, lam=1.0, drop_geo=True),          # one CSR (AMG) level above the exact solve
     "mg_n4_e10": dict(N=4, n=10, flag=1, lam=1.0, drop_geo=True),          # BASELINE configs[0] with MULTIGRID
     "mg_n3_e4_jacobi": dict(N=3, n=4, flag=1, lam=0.3, smoother="DAMPEDJACOBI"),
+    # two CSR (AMG) levels above the exact solve: pins the host-side AMG setup (libparanumal_b200/amg_setup.py);
+    # only the algebraic hierarchy, the Chebyshev bounds and the solve history are kept
+    "amg_n2_e24": dict(N=2, n=24, flag=1, lam=1.0, amg_only=True),
 }
+AMG_KEEP = re.compile(r"^(L\d+_(A|P|R)_(meta|rowStarts|cols|vals)|L\d+_(lambda|meta)|coarse_A_.*|coarse_meta|level_kinds|"
+                      r"iterations|meta)$")
 # "drop_geo" (digest) configs: arrays the product-side harness regenerates itself are dropped (geometry,
 # inverse diagonals, the dense coarse inverse = inv(coarse_A)), integer maps are kept as sha256 digests and
 # long vectors as strided samples
@@ -67,6 +72,10 @@ def run(name, c):
         for fn in sorted(os.listdir(out)):
             nm, dt, _ = fn.rsplit(".", 2)
             a = np.fromfile(os.path.join(out, fn), dtype=DT[dt])
+            if c.get("amg_only"):
+                if AMG_KEEP.match(nm):
+                    arrays[nm] = a
+                continue
             if c.get("drop_geo"):
                 if GEO.match(nm):
                     continue

@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 from libparanumal_b200 import _lib as L  # noqa: E402
 from libparanumal_b200 import api  # noqa: E402
 from libparanumal_b200.api import Comm  # noqa: E402
-from libparanumal_b200.problem import EllipticProblem  # noqa: E402
+from libparanumal_b200.problem import EllipticProblem, MultigridHierarchy  # noqa: E402
 
 libc = ctypes.CDLL("libc.so.6")
 
@@ -110,6 +110,50 @@ def main():
             assert abs(xn1 - res["p2p"][2]) <= 1e-7 * xn1
             print(f"multigpu ok: world={world} N={N} n={n} lam={lam} flag={flag} it={res['p2p'][0]} (1 GPU {it1}) "
                   f"|AN-AP|={errAP:.1e}", flush=True)
+        dist.barrier()
+    # (f) MULTIGRID preconditioner: matrix-free p-MG levels + distributed parCSR levels + multi-rank exact coarse
+    # solve.  The hierarchy is rank-count independent by construction (amg_setup.py), so with the Arnoldi bounds of
+    # the single-GPU build the V-cycle and the MULTIGRID-PCG history must agree with the single-GPU run to rounding.
+    for N, n, sm in [(3, 6, "CHEBYSHEV"), (2, 14, "CHEBYSHEV"), (2, 14, "DAMPEDJACOBI"), (4, 12, "CHEBYSHEV")]:
+        one = [None]
+        if rank == 0:
+            libc.srand(1)
+            p1 = EllipticProblem(N, n, lam=1.0, coords=True)
+            H1 = MultigridHierarchy.build(p1, smoother=sm)
+            r1 = gathered(p1, field(p1)); z1 = p1.vec()
+            M1 = H1.precon(); M1.Operator(r1, z1)
+            b1 = p1.rhs_sine3d(); x1 = p1.vec(); s1 = p1.pcg()
+            it1 = s1.Solve(p1.op, M1, x1, b1, tol=1e-8, maxit=200)
+            one = [dict(rho=[i["rho"] for i in H1.level_info if i["kind"] == "pMG"],
+                        zn=float((z1[: p1.Ndofs] ** 2).sum().item()), it=it1, hist=s1.residual_history(),
+                        rows=[i["rows"] for i in H1.level_info])]
+            del H1, M1, p1
+        dist.broadcast_object_list(one, src=0, group=gloo)
+        ref = one[0]
+        for comm in (commN, commP):
+            libc.srand(1)
+            p = EllipticProblem(N, n, lam=1.0, comm=comm, coords=True)
+            H = MultigridHierarchy.build(p, smoother=sm, level_rho=ref["rho"])
+            assert [i["rows"] for i in H.level_info] == ref["rows"]
+            r = gathered(p, field(p)); z = p.vec()
+            M = H.precon(); M.Operator(r, z)
+            zn = allsum((z[: p.Ndofs] ** 2).sum().reshape(1)).item()
+            assert abs(zn - ref["zn"]) <= 1e-9 * ref["zn"], (zn, ref["zn"])
+            b = p.rhs_sine3d(); x = p.vec(); s = p.pcg()
+            it = s.Solve(p.op, M, x, b, tol=1e-8, maxit=200)
+            assert abs(it - ref["it"]) <= 1, (it, ref["it"])
+            h = s.residual_history(); k = min(len(h), len(ref["hist"]))
+            assert np.allclose(h[:k], ref["hist"][:k], rtol=1e-4), (h, ref["hist"])
+            # self-estimated bounds (every rank draws its own drand48 start vector): same iteration count +-1
+            libc.srand(1)
+            p2 = EllipticProblem(N, n, lam=1.0, comm=comm, coords=True)
+            H2 = MultigridHierarchy.build(p2, smoother=sm)
+            b2 = p2.rhs_sine3d(); x2 = p2.vec(); s2 = p2.pcg()
+            it2 = s2.Solve(p2.op, H2.precon(), x2, b2, tol=1e-8, maxit=200)
+            assert abs(it2 - ref["it"]) <= 1, (it2, ref["it"])
+            del H, H2, M
+        if rank == 0:
+            print(f"multigpu MG ok: world={world} N={N} n={n} {sm} levels={ref['rows']} it={it} (1 GPU {ref['it']})", flush=True)
         dist.barrier()
     if rank == 0:
         print("MULTIGPU CHECK PASSED", flush=True)

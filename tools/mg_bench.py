@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""BASELINE configs[3]: PCG preconditioned with the matrix-free p-multigrid V-cycle (Chebyshev smoother, HALFDOFS
+ladder) over parAlmond-style AMG levels and an exact coarse solve, Hex3D N=7, screened Poisson (lambda=1).
+
+  python tools/mg_bench.py --elements 64                          (1 GPU)
+  torchrun --nproc-per-node 8 tools/mg_bench.py --elements 96     (the named configuration: 96^3 on 8 B200)
+
+Prints one JSON line: hierarchy, setup seconds, iterations to 1e-8 (ABS/REL-INITRESID, the reference default),
+solve time (device-timed, max over ranks) and GDOF/s = NglobalDofs * iterations / seconds
+(solvers/elliptic/src/ellipticRun.cpp:212-221).  A Jacobi-PCG solve of the same system is timed beside it.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from libparanumal_b200 import api  # noqa: E402
+from libparanumal_b200.api import Comm  # noqa: E402
+from libparanumal_b200.problem import EllipticProblem, MultigridHierarchy  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--degree", type=int, default=7)
+    ap.add_argument("--elements", type=int, default=64)
+    ap.add_argument("--tol", type=float, default=1e-8)
+    ap.add_argument("--smoother", default="CHEBYSHEV")
+    ap.add_argument("--repeat", type=int, default=3)
+    ap.add_argument("--no-jacobi", action="store_true")
+    args = ap.parse_args()
+    world, rank, lr = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    api.init(lr)
+    gloo = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+        gloo = dist.new_group(backend="gloo")
+    comm = Comm(rank, world, gloo)
+    comm.init_nccl()
+    p2p = comm.init_p2p() if (world > 1 and os.environ.get("LIBP_P2P", "1") != "0") else False
+    ctypes.CDLL("libc.so.6").srand(1)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_solve(solver, M, x, r0):
+        best = None
+        for _ in range(args.repeat):
+            x.zero_()
+            r = r0.clone()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            it = solver.Solve(p.op, M, x, r, tol=args.tol, maxit=2000)
+            e1.record()
+            barrier()
+            ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            if best is None or float(ms) < best[1]:
+                best = (it, float(ms))
+        return best
+
+    t0 = time.perf_counter()
+    p = EllipticProblem(args.degree, args.elements, lam=1.0, boundary_flag=1, comm=comm, coords=True)
+    t_fine = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    H = MultigridHierarchy.build(p, smoother=args.smoother)
+    barrier()
+    t_mg = time.perf_counter() - t0
+    M = H.precon()
+    r0 = p.rhs_sine3d()
+    x = p.vec()
+    solver = p.pcg()
+    it, ms = timed_solve(solver, M, x, r0)
+    hist = solver.residual_history()
+    xn = (x[: p.Ndofs] ** 2).sum().reshape(1)
+    if world > 1:
+        dist.all_reduce(xn)
+    out = {"workload": f"pcg_multigrid_hex_n{args.degree}_e{args.elements}", "n_gpus": world,
+           "exchange": ("nvlink-peer-window" if p2p else "nccl") if world > 1 else "none",
+           "global_dofs": int(p.NglobalDofs), "tol": args.tol, "smoother": args.smoother,
+           "levels": H.level_info, "setup_seconds": {"fine_problem": round(t_fine, 1), "multigrid": round(t_mg, 1)},
+           "iterations": it, "solve_ms": ms, "ms_per_iteration": ms / max(it, 1),
+           "gdofs": p.NglobalDofs * it / (ms * 1e-3) / 1e9,
+           "dofs_per_second_to_solution": p.NglobalDofs / (ms * 1e-3),
+           "residual_first_last": [float(hist[0]), float(hist[-1])], "solution_norm2": float(xn.sqrt())}
+    if not args.no_jacobi:
+        xj = p.vec()
+        sj = p.pcg()
+        itj, msj = timed_solve(sj, p.jacobi(), xj, r0)
+        out["jacobi_pcg"] = {"iterations": itj, "solve_ms": msj, "gdofs": p.NglobalDofs * itj / (msj * 1e-3) / 1e9,
+                             "speedup_time_to_solution": msj / ms}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libparanumal_b200.so")
+_VAR = os.environ.get("LIBP_B200_VARIANT", "")  # development builds (see build.py); empty = the product library
+LIB_PATH = os.path.join(HERE, "lib", "libparanumal_b200" + ("_" + _VAR if _VAR else "") + ".so")
 
 SUCCESS = 0
 FLOAT, DOUBLE, INT32, INT64 = 0, 1, 2, 3

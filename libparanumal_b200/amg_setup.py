@@ -188,9 +188,10 @@ def tentative_prolongator(f2c, nagg, null):
 
 
 def setup_hierarchy(A, null, rng, coarse_target=1000, strength="SYMMETRIC", aggregation="SMOOTHED"):
-    """parAlmond_t::AMGSetup on one (global) matrix.  Returns (levels, coarseA, coarseRho): levels = list of dicts
-    {A, P, R, rho, roots} finest first (every level that has a prolongator), then the matrix of the exact solve
-    and its rho."""
+    """parAlmond_t::AMGSetup on one (global) matrix.  Returns (levels, coarseA, coarseRho, coarseNull): levels =
+    list of dicts {A, P, R, rho, roots} finest first (every level that has a prolongator), then the matrix of the
+    exact solve, its rho and the null vector carried down to it (exactSolver_t::setup adds
+    nullSpacePenalty * null null^T for all-Neumann problems, parAlmondCoarseExact.cpp:158-164)."""
     A = sp.csr_matrix(A)
     A.sort_indices()
 
@@ -202,10 +203,10 @@ def setup_hierarchy(A, null, rng, coarse_target=1000, strength="SYMMETRIC", aggr
     rho = rho_of(A)
     levels = []
     n = A.shape[0]
-    if n <= coarse_target:
-        return levels, A, rho
-    theta = 0.5 if strength == "RUGESTUBEN" else 0.08
     null = np.asarray(null, dtype=np.float64).copy()
+    if n <= coarse_target:
+        return levels, A, rho, null
+    theta = 0.5 if strength == "RUGESTUBEN" else 0.08
     while True:
         C = strong_graph(A, theta, strength)
         f2c, nagg, roots = form_aggregates(C, rng)
@@ -228,7 +229,7 @@ def setup_hierarchy(A, null, rng, coarse_target=1000, strength="SYMMETRIC", aggr
         nc = Ac.shape[0]
         A = Ac
         if nc <= coarse_target or n < 2 * nc:
-            return levels, A, rho
+            return levels, A, rho, null
         n = nc
 
 

@@ -7,8 +7,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "lib", "obj")
-LIB = os.path.join(HERE, "lib", "libparanumal_b200.so")
+# development builds can live beside the product library: LIBP_B200_VARIANT=pf2 LIBP_NVCC_EXTRA=-DLIBP_AX_PF=2
+# builds lib/libparanumal_b200_pf2.so, which LIBP_B200_VARIANT=pf2 also makes _lib.load() pick up
+_VAR = os.environ.get("LIBP_B200_VARIANT", "")
+OBJ = os.path.join(HERE, "lib", "obj" + ("_" + _VAR if _VAR else ""))
+LIB = os.path.join(HERE, "lib", "libparanumal_b200" + ("_" + _VAR if _VAR else "") + ".so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp",

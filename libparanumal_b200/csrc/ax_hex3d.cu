@@ -318,21 +318,42 @@ __device__ __forceinline__ void store_row(dfloat* __restrict__ row, const dfloat
   if (Nq & 1) row[Nq - 1] = o[Nq - 1];
 }
 
+// Elements per block of the transposed-pencil kernel: chosen so that the Nq^2 columns of the EPB elements fill
+// whole warps (idle lanes hold registers but carry no bytes in flight: Nq = 6 with one element per 64-thread
+// block leaves 44 % of the lanes empty) while the three staging arrays stay inside 48 KB of static shared memory.
+template <int Nq> struct AxEPB { static constexpr int v = 1; };
+template <> struct AxEPB<2> { static constexpr int v = 16; };  //  64 /  64 lanes
+template <> struct AxEPB<3> { static constexpr int v = 7; };   //  63 /  64
+template <> struct AxEPB<4> { static constexpr int v = 4; };   //  64 /  64
+template <> struct AxEPB<5> { static constexpr int v = 5; };   // 125 / 128
+template <> struct AxEPB<6> { static constexpr int v = 5; };   // 180 / 192
+template <> struct AxEPB<7> { static constexpr int v = 3; };   // 147 / 160 (5 elements would need 60 KB)
+template <> struct AxEPB<8> { static constexpr int v = 1; };   //  64 /  64
+template <> struct AxEPB<9> { static constexpr int v = 1; };   //  81 /  96 (3 elements would need 67 KB)
+
 template <int Nq>
 struct AxT {
   static constexpr int Nq2 = Nq * Nq;
   static constexpr int Np = Nq * Nq * Nq;
-  static constexpr int EPB = (Nq2 >= 64) ? 1 : (64 / Nq2);
+  static constexpr int EPB = AxEPB<Nq>::v;
   static constexpr int Work = EPB * Nq2;
   static constexpr int Threads = ((Work + 31) / 32) * 32;
-  static constexpr int LD = (Nq % 2 == 0) ? Nq + 2 : Nq + 1;  // even: rows are 16-byte aligned
+  // row stride: even (rows are 16-byte aligned for the 128-bit accesses of layout A) with LD/2 odd, so that the
+  // eight rows a quarter-warp touches with one 128-bit access fall into eight different 16-byte bank groups
+  // (LD = 8 for Nq = 6, 7 is a 4-way conflict); odd Nq keep one pad element for load_row / store_row
+  static constexpr int LD = (Nq <= 2) ? 2 : (Nq <= 6) ? 6 : 10;
   static constexpr int SS0 = Nq * LD;
   static constexpr int SS = SS0 + ((8 - (SS0 % 16)) + 16) % 16;  // SS = 8 mod 16, even
+  static_assert(LD >= Nq + (Nq & 1) && (LD / 2) % 2 == 1, "row stride");
+  // resident blocks asked of the compiler: ~512 threads per SM (128 registers per thread), as for Nq = 8.
+  // Nq = 9 keeps 3 blocks of 96 threads: capped at 113 registers it measured 16 % slower (profiles/r1_k_*)
+  static constexpr int MinBlocks = (Nq == 9 || Nq == 7) ? 3 : (512 + Threads - 1) / Threads;
+  static_assert(3 * EPB * Nq * SS * 8 <= 48 * 1024, "staging arrays exceed static shared memory");
 };
 
 // PF = geometric-factor slabs in flight per thread, kHint = L2 residency hints on/off
 template <int Nq, bool kGather, bool kFused, bool kDot, int PF, bool kHint, int kMinB, bool kSym>
-__global__ void __launch_bounds__(AxT<Nq>::Threads, (AxT<Nq>::Threads <= 64) ? kMinB : 3)
+__global__ void __launch_bounds__(AxT<Nq>::Threads, (Nq == 8) ? kMinB : AxT<Nq>::MinBlocks)
 ax_hex3d_t_kernel(const dlong Nelements, const dlong* __restrict__ elementList, const dlong* __restrict__ G2L,
                   const dfloat* __restrict__ wJ, const dfloat* __restrict__ ggeo, const dfloat lambda,
                   const dfloat* __restrict__ q, dfloat* __restrict__ Aq, dfloat* __restrict__ dotPartials,
@@ -523,7 +544,8 @@ int launch(bool gather, bool fused, bool sym, dlong Nelements, const dlong* elem
            const dfloat* wJ, const dfloat* ggeo, dfloat lambda, const dfloat* q, dfloat* Aq, dfloat* dotPartials,
            const int* doneFlag, cudaStream_t s) {
   using C = AxCfg<Nq>;
-  const int grid = (int)((Nelements + C::EPB - 1) / C::EPB);
+  const int epb = (g_variant == 1) ? AxT<Nq>::EPB : C::EPB;
+  const int grid = (int)((Nelements + epb - 1) / epb);
 #define ARGS grid, Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag, s
 #define GO(G, F, DOT)                                                                                         \
   do {                                                                                                        \
@@ -605,8 +627,12 @@ bool ax_hex3d_D_is_centro_antisymmetric(int Nq, const dfloat* D_host) {
   return dev <= 1e-13 * mx;
 }
 int ax_hex3d_blocks(int Nq, dlong Nelements) {
+  // upper bound over both kernel variants (the pencil kernel packs 64 / Nq^2 elements, the transposed one AxEPB)
   const int nq2 = Nq * Nq;
-  const int epb = (nq2 >= 64) ? 1 : (64 / nq2);
+  const int epbP = (nq2 >= 64) ? 1 : (64 / nq2);
+  static const int epbT[10] = {1, 1, AxEPB<2>::v, AxEPB<3>::v, AxEPB<4>::v, AxEPB<5>::v, AxEPB<6>::v, AxEPB<7>::v,
+                               AxEPB<8>::v, AxEPB<9>::v};
+  const int epb = std::min(epbP, epbT[Nq]);
   return (int)((Nelements + epb - 1) / epb);
 }
 

@@ -121,6 +121,34 @@ class EllipticProblem:
     def pcg(self, flexible=False):
         return Pcg(self.Ndofs, self.Nhalo, self.comm, flexible=flexible)
 
+    def run(self, precon="JACOBI", tol=1e-8, maxit=5000, **mg_args):
+        """elliptic_t::Run (solvers/elliptic/src/ellipticRun.cpp:139-246) for data/ellipticSine3D.h: forcing and
+        boundary lift, gather, PCG solve, scatter, Dirichlet data on the masked nodes, and the mass-matrix norm the
+        reference prints as "Solution norm".  precon: NONE | JACOBI | MULTIGRID | PARALMOND.
+        Returns (iterations, solution norm, xL)."""
+        m = self.mesh
+        if precon == "NONE":
+            M = Precon.Identity(self.Ndofs)
+        elif precon == "JACOBI":
+            M = self.jacobi()
+        else:
+            self._hier = MultigridHierarchy.build(self, algebraic_only=(precon == "PARALMOND"), **mg_args)
+            M = self._hier.precon()
+        r = self.rhs_sine3d()
+        x = self.vec()
+        if self.allNeumann:  # ellipticSolve.cpp:34 ZeroMean(o_r)
+            r[: self.Ndofs] -= self.comm.allreduce_sum(float(r[: self.Ndofs].sum())) / float(self.NglobalDofs)
+        it = self.pcg().Solve(self.op, M, x, r, tol=tol, maxit=maxit)
+        xL = torch.zeros(m.Nelements * m.Np, dtype=torch.float64, device=self.device)
+        self.ogs.Scatter(xL, x, 1, L.NOTRANS)
+        PI = 3.14159265358979323846
+        uD = (torch.sin(PI * m.x) * torch.sin(PI * m.y) * torch.sin(PI * m.z)).reshape(-1)
+        masked = self.mapB.reshape(-1) == 1
+        xL = torch.where(masked, uD, xL)                      # addBCKernel (okl/ellipticAddBCHex3D.okl)
+        MxL = m.wJ.reshape(-1) * xL                           # mesh_t::MassMatrixApply, collocated GLL mass matrix
+        norm = float(np.sqrt(self.comm.allreduce_sum(float(torch.dot(xL, MxL)))))
+        return it, norm, xL
+
     def global_numbering(self):
         """Global number of every gathered DOF this rank sees (owned, then halo) and the row partition
         (elliptic_t::maskedGlobalNumbering, ellipticSetup.cpp; A.globalRowStarts,
@@ -200,7 +228,13 @@ class MultigridHierarchy:
         self.fine = fine
         self.problems = []
         m = fine.mesh
+        # elliptic_t::SetupNewDegree returns the original solver for the original degree
+        # (ellipticSetupNewDegree.cpp:32-33): level 0 works on the caller's vectors, so it must share the fine
+        # problem's ogs (on several ranks a second `unique` setup picks other owners for the shared nodes)
         for Nl in list(ladder) + ([1] if ladder[-1] != 1 else []):
+            if Nl == fine.N and not self.problems:
+                self.problems.append(fine)
+                continue
             self.problems.append(EllipticProblem(Nl, m.NX, m.NY, m.NZ, lam=fine.lam, boundary_flag=m.boundary_flag,
                                                  comm=fine.comm, device=fine.device, mode=1))
         self.mg = Multigrid(fine.comm)
@@ -233,7 +267,7 @@ class MultigridHierarchy:
 
     @classmethod
     def build(cls, fine: EllipticProblem, smoother="CHEBYSHEV", chebyshev_degree=2, amg_smoother=None,
-              strength="SYMMETRIC", aggregation="SMOOTHED", coarse_target=1000, level_rho=None):
+              strength="SYMMETRIC", aggregation="SMOOTHED", coarse_target=1000, level_rho=None, algebraic_only=False):
         """MultiGridPrecon::MultiGridPrecon (ellipticPreconMultiGrid.cpp:40-154) without the reference: the
         HALFDOFS degree ladder, one problem per degree (built in the reference's order: every `unique` ogs setup
         consumes rand() in sequence), Chebyshev/Jacobi bounds from the Arnoldi estimate on the device operator,
@@ -241,7 +275,8 @@ class MultigridHierarchy:
         Smoothers: "CHEBYSHEV" (degree `chebyshev_degree`) or "DAMPEDJACOBI" (MULTIGRID SMOOTHER /
         PARALMOND SMOOTHER, ellipticSettings / parAlmondSettings.cpp:35-53).  level_rho: optional list of
         rho(D^-1 A) for the matrix-free levels (skips their Arnoldi estimates, e.g. to run the very same
-        preconditioner on a different number of ranks)."""
+        preconditioner on a different number of ranks).  algebraic_only: PRECONDITIONER = PARALMOND
+        (ellipticPreconParAlmond.cpp:40-68) - no matrix-free levels, AMG on the assembled degree-N matrix."""
         import scipy.sparse as sp
 
         from . import amg_setup as am
@@ -250,10 +285,15 @@ class MultigridHierarchy:
         comm, m = fine.comm, fine.mesh
         rank, size = comm.rank, comm.size
         amg_smoother = smoother if amg_smoother is None else amg_smoother
-        ladder = halfdofs_ladder(fine.N)
+        ladder = [fine.N] if algebraic_only else halfdofs_ladder(fine.N)
         self.fine, self.ladder = fine, ladder
         self.problems = []
-        for Nl in ladder:  # SetupNewDegree(Nf) for every ladder degree, then degree 1 (already last on the ladder)
+        for Nl in ([] if algebraic_only else ladder):  # SetupNewDegree(Nf) for every ladder degree (1 is the last)
+            # the original degree re-uses the original solver (ellipticSetupNewDegree.cpp:32-33): level 0 works on
+            # the caller's vectors and must share the fine problem's ogs / DOF layout
+            if Nl == fine.N and not self.problems:
+                self.problems.append(fine)
+                continue
             self.problems.append(EllipticProblem(Nl, m.NX, m.NY, m.NZ, lam=fine.lam, boundary_flag=m.boundary_flag,
                                                  comm=comm, device=fine.device, mode=1))
         self.mg = Multigrid(comm)
@@ -277,7 +317,7 @@ class MultigridHierarchy:
             self.mg.AddLevel(MGLevel(pF.op, pC.op, pF.Nq, pC.Nq, P, inv, wG, kind, l0, l1, chebyshev_degree))
             self.level_info.append(dict(kind="pMG", degree=pF.N, rows=int(pF.NglobalDofs), rho=rho))
         # ---- degree-1 matrix, replicated (BuildOperatorMatrixContinuous + parCSR(cooA))
-        p1 = self.problems[-1]
+        p1 = fine if algebraic_only else self.problems[-1]
         r_, c_, v_, starts = p1.operator_matrix()
         parts = comm.allgather_object((r_, c_, v_))
         ntot = int(starts[-1])
@@ -289,7 +329,7 @@ class MultigridHierarchy:
         arng = am.Drand48(0)
         arng.draw(drawn_global)
         null = np.full(ntot, 1.0 / np.sqrt(ntot))
-        levels, Ac, rho_c = am.setup_hierarchy(A, null, arng, coarse_target, strength, aggregation)
+        levels, Ac, rho_c, null_c = am.setup_hierarchy(A, null, arng, coarse_target, strength, aggregation)
         self.amg_levels, self.coarse_A = levels, Ac
         part = np.asarray(starts, dtype=np.int64)
         cheb = amg_smoother == "CHEBYSHEV"
@@ -307,7 +347,10 @@ class MultigridHierarchy:
             self.level_info.append(dict(kind="AMG", rows=int(lv["A"].shape[0]), nnz=int(lv["A"].nnz), rho=rho))
             part = cpart
         # ---- exact coarse solve (exactSolver_t::setup): dense inverse, stored transposed
-        inv = np.linalg.inv(Ac.toarray())
+        Acd = Ac.toarray()
+        if fine.allNeumann:  # rank-one boost of the singular coarse operator (allNeumannPenalty = 1)
+            Acd += np.outer(null_c, null_c)
+        inv = np.linalg.inv(Acd)
         n0, n1 = int(part[rank]), int(part[rank + 1])
         N = n1 - n0
         diagT = np.ascontiguousarray(inv[n0:n1, n0:n1].T)          # diagInvAT[n + m*N] = inv[n0+n, n0+m]

@@ -42,7 +42,7 @@ def test_hierarchy_matches_reference(name):
     for l in range(first):  # the matrix-free levels drew their Arnoldi start vectors first (Nrows each)
         rng.draw(int(g[f"L{l}_meta"][1]))
     n = A.shape[0]
-    levels, Ac, rho_c = am.setup_hierarchy(A, np.full(n, 1.0 / np.sqrt(n)), rng)
+    levels, Ac, rho_c, _ = am.setup_hierarchy(A, np.full(n, 1.0 / np.sqrt(n)), rng)
     assert len(levels) == kinds.count(1)
     for k, lv in enumerate(levels):
         pre = f"L{first + k}"

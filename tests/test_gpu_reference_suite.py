@@ -1,0 +1,47 @@
+"""The reference's own regression tests for this path (test/testElliptic.py:95-98,199-213,244-248: Hex3D N=4 on a
+10^3 box, `Solution norm` within TOL = 1e-5 of referenceNorm, test/test.py:63,131) run end to end through the
+CUDA path: forcing + boundary lift, gather, PCG with each preconditioner, scatter, boundary data, mass-matrix norm
+(EllipticProblem.run mirrors elliptic_t::Run).  Iteration counts are those of the reference build measured in this
+container."""
+import ctypes
+
+import pytest
+
+from libparanumal_b200 import api
+from libparanumal_b200.problem import EllipticProblem
+
+pytestmark = pytest.mark.gpu
+libc = ctypes.CDLL("libc.so.6")
+TOL = 1.0e-5  # test/test.py:63
+
+# name, preconditioner, boundary flag, lambda, referenceNorm, multigrid arguments, reference iterations (or None)
+CASES = [
+    ("testEllipticHex_C0", "NONE", 1, 1.0, 0.353553390458384, {}, 113),
+    ("testEllipticHex_C0_Jacobi", "JACOBI", 1, 1.0, 0.353553400508458, {}, 97),
+    # the test-suite settings override PARALMOND AGGREGATION to UNSMOOTHED (test/testElliptic.py:41-45)
+    ("testEllipticHex_C0_ParAlmond", "PARALMOND", 1, 1.0, 0.353553400508458, dict(aggregation="UNSMOOTHED"), 22),
+    ("ParAlmond_smoothed", "PARALMOND", 1, 1.0, 0.353553400508458, {}, 11),
+    ("testEllipticHex_C0_Multigrid", "MULTIGRID", 1, 1.0, 0.353553400508458, dict(aggregation="UNSMOOTHED"), 6),
+    ("Multigrid_defaults", "MULTIGRID", 1, 1.0, 0.353553400508458, {}, 6),
+    # periodic box, lambda = 0: singular operator, ZeroMean + rank-one coarse boost (default precon MULTIGRID).
+    # test/testElliptic.py:244-248 lists 0.059540839002614; the unmodified reference built in this container
+    # prints 0.058046029189514 (5 iterations) for these settings, which is the value pinned here.
+    ("testEllipticHex_C0_AllNeumann", "MULTIGRID", -1, 0.0, 0.058046029189514, dict(aggregation="UNSMOOTHED"), 5),
+]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    api.init(0)
+    yield
+
+
+@pytest.mark.parametrize("name,precon,flag,lam,ref_norm,mg,ref_it", CASES, ids=[c[0] for c in CASES])
+def test_reference_suite_solution_norm(name, precon, flag, lam, ref_norm, mg, ref_it):
+    libc.srand(1)
+    p = EllipticProblem(4, 10, lam=lam, boundary_flag=flag, coords=True)
+    it, norm, _ = p.run(precon, **mg)
+    assert abs(norm - ref_norm) < TOL, (name, norm, ref_norm)
+    if ref_it is not None:
+        assert abs(it - ref_it) <= 1, (name, it, ref_it)
+    assert it < 400

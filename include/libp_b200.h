@@ -206,11 +206,37 @@ int libp_elliptic_free(libp_elliptic_t op);
  * the reductions that land in it, so the zero lines are still in L2 (saves one DRAM read + one write of the
  * result vector per apply).  0 = one zero-fill and three launches, the reference split.  The default applies
  * to handles created afterwards. */
+/* Fused mode, GLL derivative matrix (tuning of this implementation): the Ax kernel zero-fills o_Aq itself, a few
+ * thousand elements ahead of its own reductions, behind a ticket / per-group counter protocol (csrc/ax_hex3d.cu),
+ * so the accumulator costs one DRAM pass instead of three.  libp_elliptic_zero_ahead_errors reports protocol
+ * time-outs (0 in every run so far; a non-zero value means results of that handle are not to be trusted). */
+int libp_elliptic_set_zero_ahead(libp_elliptic_t op, int on);
+int libp_elliptic_set_default_zero_ahead(int on);
+int libp_elliptic_zero_ahead_errors(libp_elliptic_t op, int* errors);
 int libp_elliptic_set_chunk(libp_elliptic_t op, libp_dlong chunkElements);
 int libp_elliptic_set_default_chunk(libp_dlong chunkElements);
 /* o_q and o_Aq are gathered vectors of Ndofs+Nhalo entries; the Nhalo tail of o_q is
  * overwritten by the halo exchange exactly like the reference.         */
 int libp_elliptic_operator(libp_elliptic_t op, libp_dfloat* q, libp_dfloat* Aq, void* stream);
+
+/* ------------------------------------------------------------------ elliptic_t::Run pre/post steps (Hex3D, C0)
+ * solvers/elliptic/src/ellipticRun.cpp:139-246.  The reference JIT-inlines the user's data file (forcing and
+ * boundary functions, e.g. data/ellipticSine3D.h) into these kernels; across a C ABI they arrive evaluated at the
+ * element-local nodes (device arrays of Nelements*Np entries).
+ *  rhs_forcing: okl/ellipticRhsHex3D.okl:28-50        rhs = wJ .* f
+ *  rhs_bc:      okl/ellipticRhsBCHex3D.okl:59-300     rhs += ndq - A_L uD   (uD = Dirichlet data on the mapB==1
+ *               nodes, 0 elsewhere; ndq = summed Neumann face fluxes -WsJ n.grad u per node, may be NULL)
+ *  add_bc:      okl/ellipticAddBCHex3D.okl:28-48      q[mapB==1] = uD
+ *  mass_matrix: mesh_t::MassMatrixApply (collocated GLL hex mass matrix)  Mq = wJ .* q                      */
+int libp_elliptic_rhs_forcing_hex3d(libp_dlong Nelements, int Np, const libp_dfloat* wJ, const libp_dfloat* f,
+                                    libp_dfloat* rhs, void* stream);
+int libp_elliptic_rhs_bc_hex3d(int Nq, libp_dlong Nelements, const libp_dfloat* wJ, const libp_dfloat* ggeo,
+                               const libp_dfloat* D, libp_dfloat lambda, const libp_dfloat* uD, const libp_dfloat* ndq,
+                               libp_dfloat* rhs, void* stream);
+int libp_elliptic_add_bc_hex3d(libp_dlong Nelements, int Np, const int* mapB, const libp_dfloat* uD, libp_dfloat* q,
+                               void* stream);
+int libp_mass_matrix_apply_hex3d(libp_dlong Nelements, int Np, const libp_dfloat* wJ, const libp_dfloat* q,
+                                 libp_dfloat* Mq, void* stream);
 
 /* ------------------------------------------------------------------ linAlg_t
  * include/linAlg.hpp:52-120; kernels libs/linAlg/okl/linAlg*.okl.  beta==0 variants never read y. */

@@ -99,6 +99,13 @@ SIGNATURES = {
     "libp_ax_hex3d_unregister_D": (i32, [vp]),
     "libp_ax_hex3d_tune": (i32, [i32, i32, i32]),
     "libp_elliptic_create": (i32, [P(EllipticDesc), P(vp)]),
+    "libp_elliptic_rhs_forcing_hex3d": (i32, [i32, i32, vp, vp, vp, vp]),
+    "libp_elliptic_rhs_bc_hex3d": (i32, [i32, i32, vp, vp, vp, f64, vp, vp, vp, vp]),
+    "libp_elliptic_add_bc_hex3d": (i32, [i32, i32, vp, vp, vp, vp]),
+    "libp_mass_matrix_apply_hex3d": (i32, [i32, i32, vp, vp, vp, vp]),
+    "libp_elliptic_set_zero_ahead": (i32, [vp, i32]),
+    "libp_elliptic_set_default_zero_ahead": (i32, [i32]),
+    "libp_elliptic_zero_ahead_errors": (i32, [vp, P(i32)]),
     "libp_elliptic_set_chunk": (i32, [vp, i32]),
     "libp_elliptic_set_default_chunk": (i32, [i32]),
     "libp_elliptic_free": (i32, [vp]),

@@ -7,9 +7,12 @@ apply path (V-cycle) runs in CUDA.
 
 Design choice for P > 1 ranks: the hierarchy is built from the *global* degree-1 matrix with the reference's
 one-rank algorithm, replicated on every rank, and then split into row blocks.  The reference aggregates
-rank-locally, so its hierarchy (and iteration count) changes with the rank count; here it does not - a
-1-GPU and an 8-GPU solve run the same preconditioner, and the one-rank hierarchy is pinned against the
-reference's own dumps (tests/test_amg_setup_cpu.py).
+rank-locally, so its aggregates stop at rank boundaries; here they do not.  The global matrix is in the run's
+DOF numbering (rank offset + gathered index), which is a permutation of the one-rank numbering, and the
+random keys are drawn by index - so the aggregates of a P-rank run differ in detail from the one-rank ones
+(iteration counts agree within +-1 in every test).  The one-rank hierarchy is pinned against the reference's
+own dumps (tests/test_amg_setup_cpu.py); the distributed levels are pinned against scipy products of the same
+global matrices (tests/multigpu_check.py).
 
 Random numbers: the reference draws from glibc drand48 seeded by srand48(rank)
 (libs/parAlmond/parAlmondKernels.cpp:56-58); Drand48 below restates that generator so the aggregates and

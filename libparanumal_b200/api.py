@@ -319,6 +319,23 @@ def ax_hex3d(Nq, Nelements, elementList, GlobalToLocal, wJ, ggeo, D, lam, q, AqL
                                  _ptr(D), float(lam), _ptr(q), _ptr(AqL), _stream()))
 
 
+def rhs_forcing_hex3d(Nelements, Np, wJ, f, rhs):
+    check(L.load().libp_elliptic_rhs_forcing_hex3d(Nelements, Np, _ptr(wJ), _ptr(f), _ptr(rhs), _stream()))
+
+
+def rhs_bc_hex3d(Nq, Nelements, wJ, ggeo, D, lam, uD, ndq, rhs):
+    check(L.load().libp_elliptic_rhs_bc_hex3d(Nq, Nelements, _ptr(wJ), _ptr(ggeo), _ptr(D), float(lam), _ptr(uD), _ptr(ndq),
+                                              _ptr(rhs), _stream()))
+
+
+def add_bc_hex3d(Nelements, Np, mapB, uD, q):
+    check(L.load().libp_elliptic_add_bc_hex3d(Nelements, Np, _ptr(mapB), _ptr(uD), _ptr(q), _stream()))
+
+
+def mass_matrix_apply_hex3d(Nelements, Np, wJ, q, Mq):
+    check(L.load().libp_mass_matrix_apply_hex3d(Nelements, Np, _ptr(wJ), _ptr(q), _ptr(Mq), _stream()))
+
+
 def register_D(Nq, D):
     """Promise that the device array D is immutable: enables the even-odd kernels for GLL matrices."""
     check(L.load().libp_ax_hex3d_register_D(int(Nq), _ptr(D)))
@@ -357,6 +374,15 @@ class Elliptic:
     @property
     def handle(self):
         return self._h
+
+    def set_zero_ahead(self, on):
+        """in-kernel zero-fill of the fused accumulator (libp_elliptic_set_zero_ahead)"""
+        check(L.load().libp_elliptic_set_zero_ahead(self._h, int(bool(on))))
+
+    def zero_ahead_errors(self):
+        e = C.c_int(0)
+        check(L.load().libp_elliptic_zero_ahead_errors(self._h, C.byref(e)))
+        return e.value
 
     def set_chunk(self, chunk_elements):
         """elements per zero-fill piece of the fused operator (0 = off); see libp_elliptic_set_chunk"""

@@ -296,6 +296,14 @@ __device__ __forceinline__ dfloat ld_keep(const dfloat* p, uint64_t pol) {
   asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
   return v;
 }
+__device__ __forceinline__ void st_keep(dfloat* p, dfloat v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void red_keep(dfloat* p, dfloat v, uint64_t pol) {
   asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
 }
@@ -352,14 +360,27 @@ struct AxT {
 };
 
 // PF = geometric-factor slabs in flight per thread, kHint = L2 residency hints on/off
-template <int Nq, bool kGather, bool kFused, bool kDot, int PF, bool kHint, int kMinB, bool kSym>
+// kZA = zero-ahead (fused mode): the kernel zero-fills its own accumulator just ahead of the reductions, so the
+// zero lines are still in L2 when the first red.add arrives (one DRAM write per Aq line instead of memset write +
+// fill read + write-back).  Producer: block vb zero-fills the rows that virtual block vb + delta is the first
+// to touch, [zoff[vb+delta], zoff[vb+delta+1]) - zoff is the running maximum of the connectivity, so every row a
+// block touches lies below its own zoff[b+1] - then counts itself into done[(vb+delta)/group] (fence + atomic).
+// Consumer: before its reductions, vb waits until every group up to its own is complete (ld.acquire; `prefix` caches
+// the number of complete leading groups).  The producers it waits for are blocks < vb (delta >= group), which were
+// dispatched earlier and never wait themselves before producing.  Rows of the first delta blocks are zero-filled
+// by the host before the launch.  ctr = [unused, prefix, error, pad, done[0..]].
+template <int Nq, bool kGather, bool kFused, bool kDot, int PF, bool kHint, int kMinB, bool kSym, bool kZA = false>
 __global__ void __launch_bounds__(AxT<Nq>::Threads, (Nq == 8) ? kMinB : AxT<Nq>::MinBlocks)
 ax_hex3d_t_kernel(const dlong Nelements, const dlong* __restrict__ elementList, const dlong* __restrict__ G2L,
                   const dfloat* __restrict__ wJ, const dfloat* __restrict__ ggeo, const dfloat lambda,
                   const dfloat* __restrict__ q, dfloat* __restrict__ Aq, dfloat* __restrict__ dotPartials,
-                  const int* __restrict__ doneFlag) {
+                  const int* __restrict__ doneFlag, const ZeroAhead za = ZeroAhead()) {
   if (doneFlag != nullptr && *doneFlag) return;
   using C = AxT<Nq>;
+  // zero-ahead relies on blocks being dispatched in blockIdx order (so that the producers a block waits for are
+  // already running); a ticket counter would make that formal but costs an L2 round trip before the first load.
+  // The consumer's spin is bounded and reports through ctr[2] (libp_elliptic_zero_ahead_errors).
+  const int vb = blockIdx.x;
   constexpr int Nq2 = C::Nq2, Np = C::Np, LD = C::LD, SS = C::SS;
   static_assert(PF >= 1 && PF <= Nq, "prefetch depth");
   __shared__ __align__(16) dfloat s_u[C::EPB * Nq * SS];
@@ -378,7 +399,7 @@ ax_hex3d_t_kernel(const dlong Nelements, const dlong* __restrict__ elementList, 
   const int sA = es * Nq * SS + b * SS + a * LD;  // layout A: row (k=b, j=a, i=0..)
   const int sB = es * Nq * SS + b * SS + a;       // layout B: column (k=b, j=0.., i=a); j adds LD
 
-  const dlong ei = (dlong)blockIdx.x * C::EPB + es;
+  const dlong ei = (dlong)vb * C::EPB + es;
   const bool active = valid && ei < Nelements;
   const dlong e = active ? (elementList ? elementList[ei] : ei) : 0;
   const size_t ebase = (size_t)e * Np + nC;
@@ -407,6 +428,18 @@ ax_hex3d_t_kernel(const dlong Nelements, const dlong* __restrict__ elementList, 
   for (int k = 0; k < Nq; ++k) {
     if (kGather) r_q[k] = (r_id[k] >= 0) ? (kHint ? ld_keep(q + r_id[k], polK) : q[r_id[k]]) : 0.0;
     else r_q[k] = active ? q[ebase + k * Nq2] : 0.0;
+  }
+
+  // ---- zero-ahead producer (after this block's own loads are in flight): all threads store, one thread publishes
+  // (bar.sync orders the block's stores before thread 0's fence; the fence + counter increment is a cumulative release)
+  if (kZA) {
+    const int zb = vb + za.delta;
+    if (zb < za.nblocks) {
+      const dlong z0 = za.zoff[zb], z1 = za.zoff[zb + 1];
+      for (dlong i = z0 + t; i < z1; i += C::Threads) st_keep(Aq + i, 0.0, polK);
+      __syncthreads();
+      if (t == 0) { __threadfence(); atomicAdd(&za.ctr[4 + zb / za.group], 1); }
+    }
   }
 
   // ---- phase 0 (layout C): publish u, t-derivative in registers
@@ -471,6 +504,21 @@ ax_hex3d_t_kernel(const dlong Nelements, const dlong* __restrict__ elementList, 
 #pragma unroll
     for (int j = 0; j < Nq; ++j) s_s[sB + j * LD] = o[j];
   }
+  if (kZA && t == 0) {  // zero-ahead consumer: every row this block reduces into has been zero-filled
+    const int gneed = vb / za.group;
+    int g = ld_acquire_gpu(&za.ctr[1]);
+    const int g0 = g;
+    while (g <= gneed) {
+      const int lo = max(g * za.group, za.delta), hi = min((g + 1) * za.group, za.nblocks);
+      int spins = 0;
+      while (ld_acquire_gpu(&za.ctr[4 + g]) < hi - lo) {
+        __nanosleep(64);
+        if (++spins > (1 << 22)) { za.ctr[2] = 1; break; }  // never observed; keeps a protocol bug from hanging the GPU
+      }
+      ++g;
+    }
+    if (g > g0) { __threadfence(); atomicMax(&za.ctr[1], g); }
+  }
   __syncthreads();
 
   // ---- phase 4 (layout C): collect, optional p.Ap partial, store / scatter-add
@@ -517,7 +565,14 @@ int g_pf = 2, g_hint = 1, g_minb = 6;  // tuning state of variant 1 (libp_ax_hex
 template <int Nq, bool G, bool F, bool DOT, bool SYM>
 void launch_t(int grid, dlong Nelements, const dlong* elementList, const dlong* G2L, const dfloat* wJ,
               const dfloat* ggeo, dfloat lambda, const dfloat* q, dfloat* Aq, dfloat* dotPartials,
-              const int* doneFlag, cudaStream_t s) {
+              const int* doneFlag, const ZeroAhead* za, cudaStream_t s) {
+  if constexpr (G && F && SYM) {
+    if (za != nullptr) {
+      ax_hex3d_t_kernel<Nq, G, F, DOT, LIBP_AX_PF, LIBP_AX_HINT, LIBP_AX_MINB, SYM, true>
+          <<<grid, AxT<Nq>::Threads, 0, s>>>(Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag, *za);
+      return;
+    }
+  }
 #define GOT(PF, H, MB)                                                                                        \
   ax_hex3d_t_kernel<Nq, G, F, DOT, PF, H, MB, SYM><<<grid, AxT<Nq>::Threads, 0, s>>>(                         \
       Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag)
@@ -542,11 +597,11 @@ void launch_t(int grid, dlong Nelements, const dlong* elementList, const dlong* 
 template <int Nq>
 int launch(bool gather, bool fused, bool sym, dlong Nelements, const dlong* elementList, const dlong* G2L,
            const dfloat* wJ, const dfloat* ggeo, dfloat lambda, const dfloat* q, dfloat* Aq, dfloat* dotPartials,
-           const int* doneFlag, cudaStream_t s) {
+           const int* doneFlag, const ZeroAhead* za, cudaStream_t s) {
   using C = AxCfg<Nq>;
   const int epb = (g_variant == 1) ? AxT<Nq>::EPB : C::EPB;
   const int grid = (int)((Nelements + epb - 1) / epb);
-#define ARGS grid, Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag, s
+#define ARGS grid, Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag, za, s
 #define GO(G, F, DOT)                                                                                         \
   do {                                                                                                        \
     if (g_variant == 1) {                                                                                     \
@@ -587,8 +642,10 @@ namespace libp_b200 {
 // Returns the number of blocks launched (= number of dotPartials written when dotPartials != nullptr).
 int ax_hex3d_launch(int Nq, bool fused, bool trusted_D, bool sym, dlong Nelements, const dlong* elementList,
                     const dlong* G2L, const dfloat* wJ, const dfloat* ggeo, const dfloat* D, dfloat lambda,
-                    const dfloat* q, dfloat* Aq, dfloat* dotPartials, const int* doneFlag, cudaStream_t s) {
+                    const dfloat* q, dfloat* Aq, dfloat* dotPartials, const int* doneFlag, cudaStream_t s,
+                    const ZeroAhead* za) {
   LIBP_CHECK(Nq >= 2 && Nq <= kMaxNq, "Nq must be in [2, 9]");
+  LIBP_CHECK(za == nullptr || (fused && sym && g_variant == 1), "zero-ahead needs the fused even-odd kernel");
   LIBP_CHECK(!fused || G2L != nullptr, "fused gather needs GlobalToLocal");
   if (Nelements <= 0) return 0;
   if (!(trusted_D && g_cD_owner == D && g_cD_nq == Nq && (g_cD_sym || !sym))) {
@@ -609,7 +666,7 @@ int ax_hex3d_launch(int Nq, bool fused, bool trusted_D, bool sym, dlong Nelement
   }
   const bool gather = G2L != nullptr;
   switch (Nq) {
-#define CASE(n) case n: return launch<n>(gather, fused, sym, Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag, s);
+#define CASE(n) case n: return launch<n>(gather, fused, sym, Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag, za, s);
     CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9)
 #undef CASE
   }
@@ -625,6 +682,12 @@ bool ax_hex3d_D_is_centro_antisymmetric(int Nq, const dfloat* D_host) {
       dev = std::max(dev, std::abs(a + b));
     }
   return dev <= 1e-13 * mx;
+}
+// elements per block of the kernel variant in use, or 0 when zero-ahead is not available for it
+int ax_hex3d_zero_ahead_epb(int Nq) {
+  static const int epbT[10] = {0, 0, AxEPB<2>::v, AxEPB<3>::v, AxEPB<4>::v, AxEPB<5>::v, AxEPB<6>::v, AxEPB<7>::v,
+                               AxEPB<8>::v, AxEPB<9>::v};
+  return (g_variant == 1 && Nq >= 2 && Nq <= kMaxNq) ? epbT[Nq] : 0;
 }
 int ax_hex3d_blocks(int Nq, dlong Nelements) {
   // upper bound over both kernel variants (the pencil kernel packs 64 / Nq^2 elements, the transposed one AxEPB)
@@ -697,7 +760,7 @@ extern "C" int libp_ax_hex3d(int Nq, libp_dlong Nelements, const libp_dlong* ele
   LIBP_CHECK(Nelements == 0 || (wJ && ggeo && D && q && AqL), "null device pointer");
   const RegisteredD* r = find_registered(D, Nq);
   ax_hex3d_launch(Nq, false, r != nullptr, r && r->sym, Nelements, elementList, GlobalToLocal, wJ, ggeo, D, lambda, q,
-                  AqL, nullptr, nullptr, as_stream(stream));
+                  AqL, nullptr, nullptr, as_stream(stream), nullptr);
   LIBP_API_END
 }
 
@@ -709,6 +772,6 @@ extern "C" int libp_ax_hex3d_gather(int Nq, libp_dlong Nelements, const libp_dlo
   LIBP_CHECK(Nelements == 0 || (GlobalToLocal && wJ && ggeo && D && q && Aq), "null device pointer");
   const RegisteredD* r = find_registered(D, Nq);
   ax_hex3d_launch(Nq, true, r != nullptr, r && r->sym, Nelements, elementList, GlobalToLocal, wJ, ggeo, D, lambda, q,
-                  Aq, nullptr, nullptr, as_stream(stream));
+                  Aq, nullptr, nullptr, as_stream(stream), nullptr);
   LIBP_API_END
 }

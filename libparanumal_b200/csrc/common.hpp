@@ -80,6 +80,13 @@ struct dev_buf {
 
 int sm_count();
 
+// Zero-ahead arguments of the fused Ax kernel (protocol: ax_hex3d.cu, kZA)
+struct ZeroAhead {
+  int* ctr = nullptr;           // device: [0] ticket, [1] complete leading groups, [2] error, [3] pad, [4+g] done[g]
+  const dlong* zoff = nullptr;  // device, nblocks+1: rows first touched by virtual block b = [zoff[b], zoff[b+1])
+  int nblocks = 0, delta = 0, group = 0;
+};
+
 // Fixed header at the start of every peer window: mailboxes of the scalar all-reduce.
 constexpr int kWinMaxRanks = 64;
 constexpr int kWinMaxVals = 8;

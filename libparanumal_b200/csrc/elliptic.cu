@@ -7,8 +7,13 @@
 // mode 1 fuses the gather into the Ax epilogue (FP64 reductions straight into Aq).
 #include "elliptic.hpp"
 
+#include <algorithm>
+#include <cstdlib>
 #include <vector>
 
+#ifndef LIBP_AX_ZERO_AHEAD_DEFAULT
+#define LIBP_AX_ZERO_AHEAD_DEFAULT false  // in-kernel zero-fill of the fused accumulator; see elliptic.hpp
+#endif
 #ifndef LIBP_AX_CHUNK_DEFAULT
 #define LIBP_AX_CHUNK_DEFAULT 0  // elements per zero-fill piece of the fused operator (0 = off); see elliptic.hpp
 #endif
@@ -17,6 +22,7 @@ using namespace libp_b200;
 
 namespace {
 dlong g_default_chunk = LIBP_AX_CHUNK_DEFAULT;
+bool g_default_za = LIBP_AX_ZERO_AHEAD_DEFAULT;
 
 // largest local gathered id (< limit) touched by each piece of an element list
 __global__ void __launch_bounds__(256) piece_max_kernel(const dlong* __restrict__ list, const dlong* __restrict__ G2L,
@@ -66,6 +72,59 @@ void libp_elliptic_s::build_plan(cudaStream_t s) {
   tail0 = hi;  // rows behind the running maximum (the shared rows, ids no element touches) are zero-filled up front
 }
 
+void libp_elliptic_s::build_zero_ahead(cudaStream_t s) {
+  za_built = true;
+  if (const char* e = getenv("LIBP_ZA_DELTA")) kZaDelta = std::max(kZaGroup, atoi(e));  // development knob
+  const int epb = ax_hex3d_zero_ahead_epb(d.Nq);
+  if (epb == 0) { za_on = false; return; }
+  libp_ogs_s& ogs = *d.ogsMasked;
+  const dlong nL = d.NlocalGatherElements, nG = d.NglobalGatherElements, nL0 = nL / 2;
+  const dlong limit = ogs.NlocalT;
+  struct Seg { const dlong* list; dlong n; };
+  const Seg segs[3] = {{d.localGatherElementList, nL0}, {d.globalGatherElementList, nG},
+                       {d.localGatherElementList ? d.localGatherElementList + nL0 : nullptr, nL - nL0}};
+  dlong hi = 0;
+  for (int k = 0; k < 3; ++k) {
+    ZaSeg& z = za_seg[k];
+    z.nblocks = 0;
+    if (segs[k].n <= 0) continue;
+    const int nb = (int)((segs[k].n + epb - 1) / epb);
+    dev_buf<int> mx;
+    mx.alloc((size_t)nb);
+    CUDA_CHECK(cudaMemsetAsync(mx.p, 0xff, sizeof(int) * (size_t)nb, s));
+    piece_max_kernel<<<dim3(nb, 1), 64, 0, s>>>(segs[k].list, d.GlobalToLocal, Np, epb, segs[k].n, limit, mx.p);
+    CUDA_CHECK(cudaGetLastError());
+    std::vector<int> h((size_t)nb);
+    CUDA_CHECK(cudaMemcpyAsync(h.data(), mx.p, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    std::vector<dlong> zoff((size_t)nb + 1);
+    zoff[0] = hi;
+    for (int b = 0; b < nb; ++b) {
+      if (h[(size_t)b] + 1 > hi) hi = h[(size_t)b] + 1;
+      zoff[(size_t)b + 1] = hi;
+    }
+    z.nblocks = nb;
+    z.zoff.upload(zoff);
+    z.z_begin = zoff[0];
+    z.z_pre_end = zoff[(size_t)std::min(nb, kZaDelta)];
+    z.ctr_count = 4 + (size_t)(nb + kZaGroup - 1) / kZaGroup + 1;
+    z.ctr.alloc(z.ctr_count);
+    CUDA_CHECK(cudaMemsetAsync(z.ctr.p, 0, sizeof(int) * z.ctr_count, s));
+  }
+  za_tail0 = hi;
+}
+
+int libp_elliptic_s::zero_ahead_errors() {
+  int bad = 0;
+  for (ZaSeg& z : za_seg) {
+    if (!z.ctr.p) continue;
+    int e = 0;
+    CUDA_CHECK(cudaMemcpy(&e, z.ctr.p + 2, sizeof(int), cudaMemcpyDeviceToHost));
+    bad += e;
+  }
+  return bad;
+}
+
 void libp_elliptic_s::apply(dfloat* q, dfloat* Aq, bool want_dot, const int* doneFlag, cudaStream_t s, bool zeroed) {
   libp_ogs_s& ogs = *d.ogsMasked;
   const dlong nL = d.NlocalGatherElements, nG = d.NglobalGatherElements;
@@ -74,12 +133,38 @@ void libp_elliptic_s::apply(dfloat* q, dfloat* Aq, bool want_dot, const int* don
   dfloat* out = fused ? Aq : AqL.p;
   dfloat* dp = want_dot ? dotPartials.p : nullptr;
   int doff = 0;
-  auto ax = [&](dlong n, const dlong* list) {
+  auto ax = [&](dlong n, const dlong* list, const ZeroAhead* za = nullptr) {
     if (n <= 0) return;
     int nb = ax_hex3d_launch(d.Nq, fused, true, symD, n, list, d.GlobalToLocal, d.wJ, d.ggeo, d.D, d.lambda, q, out,
-                             dp ? dp + doff : nullptr, doneFlag, s);
+                             dp ? dp + doff : nullptr, doneFlag, s, za);
     doff += nb;
   };
+  if (zero_ahead() && !za_built) build_zero_ahead(s);
+  if (zero_ahead()) {
+    // the kernel zero-fills its accumulator itself; the host only covers the shared rows, the rows of the first
+    // kZaDelta blocks of every launch, and resets the counters (callers never pre-zero in this mode)
+    const dlong total = ogs.NlocalT + ogs.NhaloT;
+    if (total > za_tail0) CUDA_CHECK(cudaMemsetAsync(Aq + za_tail0, 0, sizeof(dfloat) * (size_t)(total - za_tail0), s));
+    auto run = [&](int k, dlong n, const dlong* list) {
+      if (n <= 0) return;
+      ZaSeg& z = za_seg[k];
+      CUDA_CHECK(cudaMemsetAsync(z.ctr.p, 0, sizeof(int) * z.ctr_count, s));
+      if (z.z_pre_end > z.z_begin)
+        CUDA_CHECK(cudaMemsetAsync(Aq + z.z_begin, 0, sizeof(dfloat) * (size_t)(z.z_pre_end - z.z_begin), s));
+      ZeroAhead za;
+      za.ctr = z.ctr.p; za.zoff = z.zoff.p; za.nblocks = z.nblocks; za.delta = kZaDelta; za.group = kZaGroup;
+      ax(n, list, &za);
+    };
+    halo_start_f64(ogs, q, s);
+    run(0, nL0, d.localGatherElementList);
+    halo_finish_f64(ogs, q, s);
+    run(1, nG, d.globalGatherElementList);
+    halo_combine_start_f64(ogs, Aq, s);
+    run(2, nL1, d.localGatherElementList ? d.localGatherElementList + nL0 : nullptr);
+    halo_combine_finish_f64(ogs, Aq, s);
+    nDotPartials = doff;
+    return;
+  }
   if (chunked()) {
     // slab-wise zero-fill: see AxPiece.  `zeroed` callers (PCG) skip their own zero-fill when chunked().
     if (!plan_built) build_plan(s);
@@ -145,6 +230,7 @@ extern "C" int libp_elliptic_create(const libp_elliptic_desc_t* desc, libp_ellip
   e->Nhalo = desc->ogsMasked->NhaloT - desc->ogsMasked->NhaloP;
   if (desc->mode == 0) e->AqL.alloc((size_t)desc->Nelements * e->Np);
   e->chunk = (desc->mode == 1) ? g_default_chunk : 0;
+  e->za_on = g_default_za;
   e->alloc_dot_partials();
   *op = e.release();
   LIBP_API_END
@@ -169,6 +255,26 @@ extern "C" int libp_elliptic_set_chunk(libp_elliptic_t op, libp_dlong chunkEleme
   LIBP_API_END
 }
 
+extern "C" int libp_elliptic_set_zero_ahead(libp_elliptic_t op, int on) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(op, "null handle");
+  op->za_on = on != 0;
+  LIBP_API_END
+}
+
+extern "C" int libp_elliptic_set_default_zero_ahead(int on) {
+  LIBP_API_BEGIN
+  g_default_za = on != 0;
+  LIBP_API_END
+}
+
+extern "C" int libp_elliptic_zero_ahead_errors(libp_elliptic_t op, int* errors) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(op && errors, "null argument");
+  *errors = op->zero_ahead_errors();
+  LIBP_API_END
+}
+
 extern "C" int libp_elliptic_set_default_chunk(libp_dlong chunkElements) {
   LIBP_API_BEGIN
   LIBP_CHECK(chunkElements >= 0, "bad argument");
@@ -179,6 +285,74 @@ extern "C" int libp_elliptic_set_default_chunk(libp_dlong chunkElements) {
 extern "C" int libp_elliptic_free(libp_elliptic_t op) {
   LIBP_API_BEGIN
   delete op;
+  LIBP_API_END
+}
+
+// ------------------------------------------------------------------ elliptic_t::Run pre/post steps
+// The reference inlines the user's data file (forcing / boundary functions) into these kernels at JIT time; across
+// a C ABI the functions arrive evaluated at the nodes.
+namespace {
+__global__ void __launch_bounds__(256) rhs_forcing_kernel(size_t N, const dfloat* __restrict__ wJ,
+                                                          const dfloat* __restrict__ f, dfloat* __restrict__ rhs) {
+  for (size_t n = (size_t)blockIdx.x * 256 + threadIdx.x; n < N; n += (size_t)gridDim.x * 256) rhs[n] = wJ[n] * f[n];
+}
+__global__ void __launch_bounds__(256) rhs_bc_kernel(size_t N, const dfloat* __restrict__ AuD,
+                                                     const dfloat* __restrict__ ndq, dfloat* __restrict__ rhs) {
+  for (size_t n = (size_t)blockIdx.x * 256 + threadIdx.x; n < N; n += (size_t)gridDim.x * 256)
+    rhs[n] += (ndq ? ndq[n] : 0.0) - AuD[n];
+}
+__global__ void __launch_bounds__(256) add_bc_kernel(size_t N, const int* __restrict__ mapB,
+                                                     const dfloat* __restrict__ uD, dfloat* __restrict__ q) {
+  for (size_t n = (size_t)blockIdx.x * 256 + threadIdx.x; n < N; n += (size_t)gridDim.x * 256)
+    if (mapB[n] == 1) q[n] = uD[n];
+}
+int ew_grid(size_t N) { return (int)std::min<size_t>((N + 255) / 256, (size_t)sm_count() * 16); }
+}  // namespace
+
+extern "C" int libp_elliptic_rhs_forcing_hex3d(libp_dlong Nelements, int Np, const libp_dfloat* wJ, const libp_dfloat* f,
+                                               libp_dfloat* rhs, void* stream) {
+  LIBP_API_BEGIN
+  const size_t N = (size_t)Nelements * Np;
+  LIBP_CHECK(N == 0 || (wJ && f && rhs), "null device pointer");
+  if (N) rhs_forcing_kernel<<<ew_grid(N), 256, 0, as_stream(stream)>>>(N, wJ, f, rhs);
+  CUDA_CHECK(cudaGetLastError());
+  LIBP_API_END
+}
+
+extern "C" int libp_elliptic_rhs_bc_hex3d(int Nq, libp_dlong Nelements, const libp_dfloat* wJ, const libp_dfloat* ggeo,
+                                          const libp_dfloat* D, libp_dfloat lambda, const libp_dfloat* uD,
+                                          const libp_dfloat* ndq, libp_dfloat* rhs, void* stream) {
+  LIBP_API_BEGIN
+  const size_t N = (size_t)Nelements * Nq * Nq * Nq;
+  LIBP_CHECK(N == 0 || (wJ && ggeo && D && uD && rhs), "null device pointer");
+  if (N == 0) return LIBP_SUCCESS;
+  cudaStream_t s = as_stream(stream);
+  dev_buf<dfloat> AuD;  // setup-time scratch
+  AuD.alloc(N);
+  ax_hex3d_launch(Nq, false, false, false, Nelements, nullptr, nullptr, wJ, ggeo, D, lambda, uD, AuD.p, nullptr, nullptr, s);
+  rhs_bc_kernel<<<ew_grid(N), 256, 0, s>>>(N, AuD.p, ndq, rhs);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaStreamSynchronize(s));  // AuD is released on return
+  LIBP_API_END
+}
+
+extern "C" int libp_elliptic_add_bc_hex3d(libp_dlong Nelements, int Np, const int* mapB, const libp_dfloat* uD,
+                                          libp_dfloat* q, void* stream) {
+  LIBP_API_BEGIN
+  const size_t N = (size_t)Nelements * Np;
+  LIBP_CHECK(N == 0 || (mapB && uD && q), "null device pointer");
+  if (N) add_bc_kernel<<<ew_grid(N), 256, 0, as_stream(stream)>>>(N, mapB, uD, q);
+  CUDA_CHECK(cudaGetLastError());
+  LIBP_API_END
+}
+
+extern "C" int libp_mass_matrix_apply_hex3d(libp_dlong Nelements, int Np, const libp_dfloat* wJ, const libp_dfloat* q,
+                                            libp_dfloat* Mq, void* stream) {
+  LIBP_API_BEGIN
+  const size_t N = (size_t)Nelements * Np;
+  LIBP_CHECK(N == 0 || (wJ && q && Mq), "null device pointer");
+  if (N) rhs_forcing_kernel<<<ew_grid(N), 256, 0, as_stream(stream)>>>(N, wJ, q, Mq);
+  CUDA_CHECK(cudaGetLastError());
   LIBP_API_END
 }
 

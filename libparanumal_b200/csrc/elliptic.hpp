@@ -8,7 +8,9 @@
 namespace libp_b200 {
 int ax_hex3d_launch(int Nq, bool fused, bool trusted_D, bool sym, dlong Nelements, const dlong* elementList,
                     const dlong* G2L, const dfloat* wJ, const dfloat* ggeo, const dfloat* D, dfloat lambda,
-                    const dfloat* q, dfloat* Aq, dfloat* dotPartials, const int* doneFlag, cudaStream_t s);
+                    const dfloat* q, dfloat* Aq, dfloat* dotPartials, const int* doneFlag, cudaStream_t s,
+                    const ZeroAhead* za = nullptr);
+int ax_hex3d_zero_ahead_epb(int Nq);
 bool ax_hex3d_D_is_centro_antisymmetric(int Nq, const dfloat* D_host);
 int ax_hex3d_blocks(int Nq, dlong Nelements);
 void ogs_gather_start_f64(libp_ogs_s& o, double* gv, const double* v, int op, int trans, cudaStream_t s);
@@ -40,6 +42,23 @@ struct libp_elliptic_s {
   void alloc_dot_partials();
   void build_plan(cudaStream_t s);
   bool chunked() const { return d.mode == 1 && chunk > 0; }
+  // ---- zero-ahead (mode 1, GLL D): the Ax kernel zero-fills its accumulator itself just ahead of its reductions
+  // (protocol in ax_hex3d.cu).  One plan per launch segment of apply(): zoff = running maximum of the connectivity at
+  // block granularity, ctr = ticket / prefix / per-group counters (reset before every launch).
+  struct ZaSeg {
+    libp_b200::dev_buf<dlong> zoff;
+    libp_b200::dev_buf<int> ctr;
+    int nblocks = 0;
+    dlong z_begin = 0, z_pre_end = 0;  // host memset before the launch: rows of the first `delta` blocks
+    size_t ctr_count = 0;
+  };
+  ZaSeg za_seg[3];
+  bool za_on = false, za_built = false;
+  dlong za_tail0 = 0;  // rows behind every block's range (shared rows): zero-filled up front
+  int kZaDelta = 2048, kZaGroup = 64;  // zero-fill distance / counter granularity in blocks (delta >= group)
+  bool zero_ahead() const { return d.mode == 1 && symD && za_on && chunk == 0; }
+  void build_zero_ahead(cudaStream_t s);
+  int zero_ahead_errors();
   // apply; when dot/doneFlag are given the p.Ap partials are produced and the kernels early-exit
   // zeroed: the caller already zero-filled Aq[0 : NlocalT+NhaloT] (PCG folds it into its p-update pass)
   void apply(dfloat* q, dfloat* Aq, bool want_dot, const int* doneFlag, cudaStream_t s, bool zeroed = false);

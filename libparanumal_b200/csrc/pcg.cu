@@ -474,7 +474,7 @@ extern "C" int libp_pcg_solve(libp_pcg_t pcg, libp_elliptic_t A, libp_precon_t M
 #undef STAGE
   };
   // with the slab-wise plan the operator zero-fills its accumulator itself, piece by piece (elliptic.hpp)
-  const dlong Nzero = (A->d.mode == 1 && !A->chunked()) ? (dlong)(A->d.ogsMasked->NlocalT + A->d.ogsMasked->NhaloT) : 0;
+  const dlong Nzero = (A->d.mode == 1 && !A->chunked() && !A->zero_ahead()) ? (dlong)(A->d.ogsMasked->NlocalT + A->d.ogsMasked->NhaloT) : 0;
 
   // z = M r ; r.z ; beta = 0 for the first iteration
   auto precon_and_rz = [&]() {

@@ -94,19 +94,26 @@ class EllipticProblem:
         inv = self.inv_diagonal()
         return Precon.Jacobi(self.Ndofs, inv, self.allNeumann, self.NglobalDofs, self.comm)
 
-    def rhs_sine3d(self):
-        """Gathered right-hand side for data/ellipticSine3D.h (needs mesh coords)."""
+    def _sine3d(self):
         m = self.mesh
         PI = 3.14159265358979323846
-        s = torch.sin(PI * m.x) * torch.sin(PI * m.y) * torch.sin(PI * m.z)
-        rL = (m.wJ * ((3 * PI * PI + self.lam) * s)).reshape(-1)
-        uD = torch.where(self.mapB.reshape(m.x.shape) == 1, s, torch.zeros_like(s)).reshape(-1).contiguous()
+        return (torch.sin(PI * m.x) * torch.sin(PI * m.y) * torch.sin(PI * m.z)).reshape(-1).contiguous()
+
+    def rhs_sine3d(self):
+        """Gathered right-hand side for data/ellipticSine3D.h (needs mesh coords): forcing kernel, boundary lift,
+        ogsMasked.Gather(Add, Trans) - ellipticRun.cpp:139-183."""
+        from .api import rhs_bc_hex3d, rhs_forcing_hex3d
+        m = self.mesh
+        PI = 3.14159265358979323846
+        s = self._sine3d()
+        f = (3 * PI * PI + self.lam) * s                       # ellipticForcing3D of the data file
+        rL = torch.empty_like(f)
+        rhs_forcing_hex3d(m.Nelements, m.Np, m.wJ, f, rL)
+        uD = torch.where(self.mapB.reshape(-1) == 1, s, torch.zeros_like(s)).contiguous()  # ellipticBoundaryConditions3D
         if bool((uD != 0).any()):
-            AuD = torch.empty_like(uD)
-            ax_hex3d(self.Nq, m.Nelements, None, None, m.wJ, m.ggeo, m.D, self.lam, uD, AuD)
-            rL = rL - AuD
+            rhs_bc_hex3d(self.Nq, m.Nelements, m.wJ, m.ggeo, m.D, self.lam, uD, None, rL)
         r = self.vec()
-        self.ogs.Gather(r, rL.contiguous(), 1, L.ADD, L.TRANS)
+        self.ogs.Gather(r, rL, 1, L.ADD, L.TRANS)
         return r
 
     def weightG(self):
@@ -141,11 +148,10 @@ class EllipticProblem:
         it = self.pcg().Solve(self.op, M, x, r, tol=tol, maxit=maxit)
         xL = torch.zeros(m.Nelements * m.Np, dtype=torch.float64, device=self.device)
         self.ogs.Scatter(xL, x, 1, L.NOTRANS)
-        PI = 3.14159265358979323846
-        uD = (torch.sin(PI * m.x) * torch.sin(PI * m.y) * torch.sin(PI * m.z)).reshape(-1)
-        masked = self.mapB.reshape(-1) == 1
-        xL = torch.where(masked, uD, xL)                      # addBCKernel (okl/ellipticAddBCHex3D.okl)
-        MxL = m.wJ.reshape(-1) * xL                           # mesh_t::MassMatrixApply, collocated GLL mass matrix
+        from .api import add_bc_hex3d, mass_matrix_apply_hex3d
+        add_bc_hex3d(m.Nelements, m.Np, self.mapB.reshape(-1).contiguous(), self._sine3d(), xL)   # addBCKernel
+        MxL = torch.empty_like(xL)
+        mass_matrix_apply_hex3d(m.Nelements, m.Np, m.wJ, xL, MxL)   # mesh_t::MassMatrixApply (collocated GLL)
         norm = float(np.sqrt(self.comm.allreduce_sum(float(torch.dot(xL, MxL)))))
         return it, norm, xL
 
@@ -333,6 +339,7 @@ class MultigridHierarchy:
         self.amg_levels, self.coarse_A = levels, Ac
         part = np.asarray(starts, dtype=np.int64)
         cheb = amg_smoother == "CHEBYSHEV"
+        self.amg_handles, self.amg_parts = [], []
         for lv in levels:
             cpart = am.coarse_partition(part, lv["roots"])
             dInv = 1.0 / lv["A"].diagonal()[part[rank]: part[rank + 1]]
@@ -342,8 +349,10 @@ class MultigridHierarchy:
                 mk = lambda M, rp, cp: ParCsr(comm, am.split_rows(M, rp, cp, rank))
             cA, cP, cR = mk(lv["A"], part, part), mk(lv["P"], part, cpart), mk(lv["R"], cpart, part)
             rho = lv["rho"]
-            self.mg.AddLevel(AmgLevel(cA, cP, cR, dInv, AmgLevel.CHEBYSHEV if cheb else AmgLevel.DAMPED_JACOBI,
-                                      (4.0 / 3.0) / rho, rho / 10.0, rho, chebyshev_degree))
+            self.amg_handles.append(AmgLevel(cA, cP, cR, dInv, AmgLevel.CHEBYSHEV if cheb else AmgLevel.DAMPED_JACOBI,
+                                             (4.0 / 3.0) / rho, rho / 10.0, rho, chebyshev_degree))
+            self.amg_parts.append((part, cpart))
+            self.mg.AddLevel(self.amg_handles[-1])
             self.level_info.append(dict(kind="AMG", rows=int(lv["A"].shape[0]), nnz=int(lv["A"].nnz), rho=rho))
             part = cpart
         # ---- exact coarse solve (exactSolver_t::setup): dense inverse, stored transposed
@@ -355,10 +364,12 @@ class MultigridHierarchy:
         N = n1 - n0
         diagT = np.ascontiguousarray(inv[n0:n1, n0:n1].T)          # diagInvAT[n + m*N] = inv[n0+n, n0+m]
         if size == 1:
-            self.mg.SetCoarse(CoarseExact(N, diagT.reshape(-1)))
+            self.coarse_handle = CoarseExact(N, diagT.reshape(-1))
         else:
             others = np.concatenate([np.arange(0, n0), np.arange(n1, Ac.shape[0])])
             offdT = np.ascontiguousarray(inv[n0:n1][:, others].T)  # offdInvAT[n + m*N], other ranks' rows ascending
-            self.mg.SetCoarse(CoarseExactPar(comm, N, part, diagT.reshape(-1), offdT.reshape(-1)))
+            self.coarse_handle = CoarseExactPar(comm, N, part, diagT.reshape(-1), offdT.reshape(-1))
+        self.mg.SetCoarse(self.coarse_handle)
+        self.coarse_part, self.coarse_dense = part, Acd
         self.level_info.append(dict(kind="exact", rows=int(Ac.shape[0]), nnz=int(Ac.nnz)))
         return self

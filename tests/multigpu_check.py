@@ -50,6 +50,73 @@ def hist_close(h1, h2):
     return np.allclose(a[early], b[early], rtol=1e-3) and np.allclose(a, b, rtol=0.5)
 
 
+def check_amg_levels(H, rank, sm):
+    """distributed parCSR level operations / coarse solve == scipy on the global matrices (local slice)"""
+    def dvec(n, vals=None):
+        v = torch.zeros(max(int(n), 1), dtype=torch.float64, device="cuda")
+        if vals is not None:
+            v[: len(vals)] = torch.from_numpy(np.ascontiguousarray(vals)).cuda()
+        return v
+
+    def rel(a, b):
+        return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+    for lv, level, (part, cpart) in zip(H.amg_levels, H.amg_handles, H.amg_parts):
+        A, P, R = lv["A"], lv["P"], lv["R"]
+        n, nc = A.shape[0], P.shape[1]
+        g = np.random.default_rng(11 + n)
+        xg, bg, xcg = g.standard_normal(n), g.standard_normal(n), g.standard_normal(nc)
+        sl, slc = slice(int(part[rank]), int(part[rank + 1])), slice(int(cpart[rank]), int(cpart[rank + 1]))
+        nl, ncl = sl.stop - sl.start, slc.stop - slc.start
+        cA, cP, cR = level.keep
+        cols = max(cA.Ncols, cR.Ncols, nl)
+        x, b, res = dvec(cols, xg[sl]), dvec(cols, bg[sl]), dvec(cols)
+        level.residual(b, x, res)
+        rg = bg - A @ xg
+        assert rel(res[:nl].cpu().numpy(), rg[sl]) < 1e-12 or nl == 0
+        res[:nl] = torch.from_numpy(rg[sl]).cuda()
+        rc = dvec(max(ncl, cP.Ncols))
+        level.coarsen(res, rc)
+        assert ncl == 0 or rel(rc[:ncl].cpu().numpy(), (R @ rg)[slc]) < 1e-12
+        xc = dvec(max(cP.Ncols, ncl), xcg[slc])
+        x2 = dvec(cols, xg[sl])
+        level.prolongate(xc, x2)
+        assert nl == 0 or rel(x2[:nl].cpu().numpy(), (xg + P @ xcg)[sl]) < 1e-12
+        # smoother restated on the global matrix (parCSR::smoothChebyshev / smoothDampedJacobi)
+        rho, dinv = lv["rho"], 1.0 / A.diagonal()
+        for x_is_zero in (True, False):
+            xr = np.zeros(n) if x_is_zero else xg.copy()
+            if sm == "DAMPEDJACOBI":
+                xr = xr + (4.0 / 3.0) / rho * dinv * (bg - A @ xr)
+            else:
+                l0, l1 = rho / 10.0, rho
+                theta, delta = 0.5 * (l1 + l0), 0.5 * (l1 - l0)
+                sigma = theta / delta
+                rho_n = 1.0 / sigma
+                rr = dinv * (bg - A @ xr)
+                d = rr / theta
+                xr = xr + d
+                for _ in range(2):
+                    rr = rr - dinv * (A @ d)
+                    rho_np1 = 1.0 / (2.0 * sigma - rho_n)
+                    d = rho_np1 * rho_n * d + 2.0 * rho_np1 / delta * rr
+                    xr = xr + d
+                    rho_n = rho_np1
+            xs = dvec(cols) if x_is_zero else dvec(cols, xg[sl])
+            level.smooth(b, xs, x_is_zero)
+            assert nl == 0 or rel(xs[:nl].cpu().numpy(), xr[sl]) < 1e-11, (sm, x_is_zero)
+    part, Acd = H.coarse_part, H.coarse_dense
+    g = np.random.default_rng(5)
+    bg = g.standard_normal(Acd.shape[0])
+    sl = slice(int(part[rank]), int(part[rank + 1]))
+    nl = sl.stop - sl.start
+    xo = dvec(nl)
+    H.coarse_handle.solve(dvec(nl, bg[sl]), xo)
+    if nl:
+        xs = np.linalg.solve(Acd, bg)
+        assert rel(xo[:nl].cpu().numpy(), xs[sl]) < 1e-9
+
+
 def main():
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     api.init(lr)
@@ -119,8 +186,11 @@ def main():
                   f"|AN-AP|={errAP:.1e}", flush=True)
         dist.barrier()
     # (f) MULTIGRID preconditioner: matrix-free p-MG levels + distributed parCSR levels + multi-rank exact coarse
-    # solve.  The hierarchy is rank-count independent by construction (amg_setup.py), so with the Arnoldi bounds of
-    # the single-GPU build the V-cycle and the MULTIGRID-PCG history must agree with the single-GPU run to rounding.
+    # solve.  (1) every distributed CSR level operation and the coarse solve against scipy / numpy on the same global
+    # matrices; (2) with the Arnoldi bounds of the single-GPU build a hierarchy without CSR levels is identical on
+    # any number of ranks: V-cycle and history agree to rounding; (3) with CSR levels the aggregates depend on the
+    # DOF numbering (a permutation of the single-GPU one), so the solve is compared through iteration count +-1
+    # and the solution.
     for N, n, sm in [(3, 6, "CHEBYSHEV"), (2, 14, "CHEBYSHEV"), (2, 14, "DAMPEDJACOBI"), (4, 12, "CHEBYSHEV")]:
         one = [None]
         if rank == 0:
@@ -133,7 +203,7 @@ def main():
             it1 = s1.Solve(p1.op, M1, x1, b1, tol=1e-8, maxit=200)
             one = [dict(rho=[i["rho"] for i in H1.level_info if i["kind"] == "pMG"],
                         zn=float((z1[: p1.Ndofs] ** 2).sum().item()), it=it1, hist=s1.residual_history(),
-                        rows=[i["rows"] for i in H1.level_info])]
+                        xn=float((x1[: p1.Ndofs] ** 2).sum().item()), rows=[i["rows"] for i in H1.level_info])]
             del H1, M1, p1
         dist.broadcast_object_list(one, src=0, group=gloo)
         ref = one[0]
@@ -141,16 +211,24 @@ def main():
             libc.srand(1)
             p = EllipticProblem(N, n, lam=1.0, comm=comm, coords=True)
             H = MultigridHierarchy.build(p, smoother=sm, level_rho=ref["rho"])
-            assert [i["rows"] for i in H.level_info] == ref["rows"]
+            has_csr = len(H.amg_handles) > 0
+            check_amg_levels(H, rank, sm)
             r = gathered(p, field(p)); z = p.vec()
             M = H.precon(); M.Operator(r, z)
             zn = allsum((z[: p.Ndofs] ** 2).sum().reshape(1)).item()
-            assert abs(zn - ref["zn"]) <= 1e-9 * ref["zn"], (zn, ref["zn"])
             b = p.rhs_sine3d(); x = p.vec(); s = p.pcg()
             it = s.Solve(p.op, M, x, b, tol=1e-8, maxit=200)
-            assert abs(it - ref["it"]) <= 1, (it, ref["it"])
+            xn = allsum((x[: p.Ndofs] ** 2).sum().reshape(1)).item()
             h = s.residual_history(); k = min(len(h), len(ref["hist"]))
-            assert np.allclose(h[:k], ref["hist"][:k], rtol=1e-3), (h, ref["hist"])
+            assert abs(it - ref["it"]) <= 1, (it, ref["it"])
+            assert abs(xn - ref["xn"]) <= 1e-7 * ref["xn"], (xn, ref["xn"])
+            if not has_csr:
+                assert [i["rows"] for i in H.level_info] == ref["rows"]
+                assert abs(zn - ref["zn"]) <= 1e-9 * ref["zn"], (zn, ref["zn"])
+                assert np.allclose(h[:k], ref["hist"][:k], rtol=1e-3), (h, ref["hist"])
+            else:
+                assert abs(zn - ref["zn"]) <= 2e-2 * ref["zn"], (zn, ref["zn"])
+                assert np.allclose(h[:3], ref["hist"][:3], rtol=0.2), (h, ref["hist"])
             # self-estimated bounds (every rank draws its own drand48 start vector): same iteration count +-1
             libc.srand(1)
             p2 = EllipticProblem(N, n, lam=1.0, comm=comm, coords=True)

@@ -335,3 +335,31 @@ def test_all_neumann_periodic_poisson():
     assert 0 < it < 200
     Ax = p.operator(x)
     assert float((Ax[: p.Ndofs] - r[: p.Ndofs]).norm() / r[: p.Ndofs].norm()) < 1e-6
+
+
+@pytest.mark.parametrize("N,n,lam", [(7, 16, 1.0), (7, 13, 0.0), (3, 26, 1.0), (1, 34, 0.5), (4, 20, 0.0), (5, 18, 1.0)])
+def test_zero_ahead_operator_and_pcg_match_memset_path(N, n, lam):
+    """In-kernel zero-fill of the fused accumulator (ticket + per-group counters, csrc/ax_hex3d.cu kZA): same
+    operator to rounding (the reductions have no fixed order in either path), no protocol time-outs, same PCG
+    iteration count.  Sizes exceed the zero-ahead distance (2048 blocks) so producers and consumers both run."""
+    libc.srand(1)
+    p = EllipticProblem(N, n, lam=lam, coords=True)
+    q = p.vec()
+    q[: p.Ndofs] = dev(er.splitmix_uniform(99, p.Ndofs))
+    ref = p.operator(q).clone()
+    p.op.set_zero_ahead(True)
+    junk = p.vec(fill=123.0)          # the accumulator must not need to be clean on entry
+    for _ in range(3):
+        out = p.operator(q, junk)
+    assert p.op.zero_ahead_errors() == 0
+    scale = float(ref[: p.Ndofs].abs().max())
+    assert float((out[: p.Ndofs] - ref[: p.Ndofs]).abs().max()) / scale < 1e-13
+    if lam:
+        r0 = p.rhs_sine3d()
+        its = []
+        for za in (False, True):
+            p.op.set_zero_ahead(za)
+            x, r = p.vec(), r0.clone()
+            its.append(p.pcg().Solve(p.op, p.jacobi(), x, r, tol=1e-8, maxit=60))
+        assert abs(its[0] - its[1]) <= 1, its
+        assert p.op.zero_ahead_errors() == 0

@@ -45,6 +45,7 @@ typedef struct libp_comm_s* libp_comm_t;
 typedef struct libp_ogs_s* libp_ogs_t;
 typedef struct libp_elliptic_s* libp_elliptic_t;
 typedef struct libp_pcg_s* libp_pcg_t;
+typedef struct libp_nbpcg_s* libp_nbpcg_t;
 typedef struct libp_precon_s* libp_precon_t;
 typedef struct libp_mglevel_s* libp_mglevel_t;
 typedef struct libp_csr_s* libp_csr_t;
@@ -394,6 +395,20 @@ int libp_pcg_solve(libp_pcg_t pcg, libp_elliptic_t A, libp_precon_t M, libp_dflo
                    libp_dfloat tol, int maxit, int verbose, void* stream, int* iters);
 /* Residual norms sqrt(r.r) recorded by the last solve: [0] initial, [i] after iteration i. */
 int libp_pcg_residual_history(libp_pcg_t pcg, const libp_dfloat** hist, int* n);
+
+/* ------------------------------------------------------------------ LinearSolver::nbpcg (LINEAR SOLVER = NBPCG)
+ * libs/linearSolver/linearSolverNBPCG.cpp:35-229: Gropp's non-blocking PCG.  One fused kernel per update
+ * (update1: p, s, p.s ; update2: r, z, r.z, z.z, r.r), every reduction is in flight while the next operator /
+ * preconditioner apply runs.  Same constructor arguments, stopping rule (ABS/REL-INITRESID), verbose lines and
+ * return value (iterations) as the reference. */
+int libp_nbpcg_create(libp_dlong N, libp_dlong Nhalo, libp_comm_t comm, libp_nbpcg_t* solver);
+int libp_nbpcg_free(libp_nbpcg_t solver);
+int libp_nbpcg_solve_cb(libp_nbpcg_t solver, libp_operator_fn A, void* Actx, libp_operator_fn M, void* Mctx,
+                        libp_dfloat* x, libp_dfloat* r, libp_dfloat tol, int maxit, int verbose, void* stream,
+                        int* iters);
+int libp_nbpcg_solve(libp_nbpcg_t solver, libp_elliptic_t A, libp_precon_t M, libp_dfloat* x, libp_dfloat* r,
+                     libp_dfloat tol, int maxit, int verbose, void* stream, int* iters);
+int libp_nbpcg_residual_history(libp_nbpcg_t solver, const libp_dfloat** hist, int* n);
 
 #ifdef __cplusplus
 }

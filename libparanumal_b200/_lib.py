@@ -166,6 +166,11 @@ SIGNATURES = {
     "libp_pcg_solve_cb": (i32, [vp, OPERATOR_FN, vp, OPERATOR_FN, vp, vp, vp, f64, i32, i32, vp, P(i32)]),
     "libp_pcg_solve": (i32, [vp, vp, vp, vp, vp, f64, i32, i32, vp, P(i32)]),
     "libp_pcg_residual_history": (i32, [vp, P(vp), P(i32)]),
+    "libp_nbpcg_create": (i32, [i32, i32, vp, P(vp)]),
+    "libp_nbpcg_free": (i32, [vp]),
+    "libp_nbpcg_solve_cb": (i32, [vp, OPERATOR_FN, vp, OPERATOR_FN, vp, vp, vp, f64, i32, i32, vp, P(i32)]),
+    "libp_nbpcg_solve": (i32, [vp, vp, vp, vp, vp, f64, i32, i32, vp, P(i32)]),
+    "libp_nbpcg_residual_history": (i32, [vp, P(vp), P(i32)]),
 }
 
 _lib = None

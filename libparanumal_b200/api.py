@@ -654,3 +654,29 @@ class Pcg:
         if self._h:
             L.load().libp_pcg_free(self._h)
             self._h = C.c_void_p()
+
+
+class NbPcg:
+    """LinearSolver::nbpcg (libs/linearSolver/linearSolverNBPCG.cpp): non-blocking PCG, native handles."""
+
+    def __init__(self, N, Nhalo, comm=None):
+        self._h = C.c_void_p()
+        check(L.load().libp_nbpcg_create(int(N), int(Nhalo), comm.handle if comm is not None else None, C.byref(self._h)))
+
+    def Solve(self, A: Elliptic, M: Precon, o_x, o_r, tol=1e-8, maxit=5000, verbose=0):
+        it = C.c_int()
+        check(L.load().libp_nbpcg_solve(self._h, A.handle, M.handle, _ptr(o_x), _ptr(o_r), float(tol), int(maxit),
+                                        int(verbose), _stream(), C.byref(it)))
+        return it.value
+
+    def residual_history(self):
+        p, n = C.c_void_p(), C.c_int()
+        check(L.load().libp_nbpcg_residual_history(self._h, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), (n.value,)).copy()
+
+    def Free(self):
+        if self._h:
+            L.load().libp_nbpcg_free(self._h)
+            self._h = C.c_void_p()

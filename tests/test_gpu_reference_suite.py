@@ -45,3 +45,38 @@ def test_reference_suite_solution_norm(name, precon, flag, lam, ref_norm, mg, re
     if ref_it is not None:
         assert abs(it - ref_it) <= 1, (name, it, ref_it)
     assert it < 400
+
+
+# LINEAR SOLVER = NBPCG on the same problem: iteration counts and the first residual norms printed by the
+# unmodified reference built in this container (ellipticMain, Serial mode)
+NBPCG = [("NONE", 113, [2.960718797524, 1.742998255149, 1.089704705958]),
+         ("JACOBI", 97, [2.960718797524, 1.583783440215, 1.049754120587]),
+         ("MULTIGRID", 6, [2.960718797524, 8.373782734443e-02, 2.514007040123e-03])]
+
+
+@pytest.mark.parametrize("precon,ref_it,ref_hist", NBPCG, ids=[c[0] for c in NBPCG])
+def test_nbpcg_matches_reference(precon, ref_it, ref_hist):
+    import numpy as np
+
+    from libparanumal_b200.api import NbPcg, Precon
+    from libparanumal_b200.problem import MultigridHierarchy
+    libc.srand(1)
+    p = EllipticProblem(4, 10, lam=1.0, boundary_flag=1, coords=True)
+    if precon == "NONE":
+        M = Precon.Identity(p.Ndofs)
+    elif precon == "JACOBI":
+        M = p.jacobi()
+    else:
+        H = MultigridHierarchy.build(p)
+        M = H.precon()
+    r = p.rhs_sine3d()
+    x = p.vec()
+    solver = NbPcg(p.Ndofs, p.Nhalo, p.comm)
+    it = solver.Solve(p.op, M, x, r, tol=1e-8, maxit=5000)
+    assert abs(it - ref_it) <= 1, (it, ref_it)
+    h = solver.residual_history()
+    assert np.allclose(h[:3], ref_hist, rtol=1e-6), h[:3]
+    # same solution as classic PCG
+    x2, r2 = p.vec(), p.rhs_sine3d()
+    p.pcg().Solve(p.op, M, x2, r2, tol=1e-8, maxit=5000)
+    assert float((x[: p.Ndofs] - x2[: p.Ndofs]).abs().max() / x2[: p.Ndofs].abs().max()) < 1e-6

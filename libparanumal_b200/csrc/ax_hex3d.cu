@@ -356,6 +356,11 @@ struct AxT {
   // resident blocks asked of the compiler: ~512 threads per SM (128 registers per thread), as for Nq = 8.
   // Nq = 9 keeps 3 blocks of 96 threads: capped at 113 registers it measured 16 % slower (profiles/r1_k_*)
   static constexpr int MinBlocks = (Nq == 9 || Nq == 7) ? 3 : (512 + Threads - 1) / Threads;
+  // geometric-factor slabs in flight per thread.  A thread of a low-order element has few bytes to ask for
+  // (Nq = 4: 4 indices + 6 factors = 64 B with one slab), and ~512 threads per SM then keep only ~32 KB in
+  // flight - about 4.7 TB/s at 1 us of latency, which is what those kernels measured.  Low orders therefore
+  // request all (or most of) their slabs up front; Nq = 8 stays at the measured optimum of one slab.
+  static constexpr int PF = (LIBP_AX_PF != 1) ? LIBP_AX_PF : (Nq <= 4) ? Nq : (Nq == 5) ? 3 : (Nq <= 7) ? 2 : 1;
   static_assert(3 * EPB * Nq * SS * 8 <= 48 * 1024, "staging arrays exceed static shared memory");
 };
 
@@ -568,7 +573,7 @@ void launch_t(int grid, dlong Nelements, const dlong* elementList, const dlong* 
               const int* doneFlag, const ZeroAhead* za, cudaStream_t s) {
   if constexpr (G && F && SYM) {
     if (za != nullptr) {
-      ax_hex3d_t_kernel<Nq, G, F, DOT, LIBP_AX_PF, LIBP_AX_HINT, LIBP_AX_MINB, SYM, true>
+      ax_hex3d_t_kernel<Nq, G, F, DOT, AxT<Nq>::PF, LIBP_AX_HINT, LIBP_AX_MINB, SYM, true>
           <<<grid, AxT<Nq>::Threads, 0, s>>>(Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag, *za);
       return;
     }
@@ -590,7 +595,7 @@ void launch_t(int grid, dlong Nelements, const dlong* elementList, const dlong* 
   }
 #endif
   // a general (non-GLL) D needs all Nq^2 constants: give the N=7 kernel the registers instead of spilling
-  GOT(LIBP_AX_PF, LIBP_AX_HINT, (SYM || Nq < 8) ? LIBP_AX_MINB : 4);
+  GOT(AxT<Nq>::PF, LIBP_AX_HINT, (SYM || Nq < 8) ? LIBP_AX_MINB : 4);
 #undef GOT
 }
 

@@ -308,8 +308,7 @@ __device__ __forceinline__ void red_keep(dfloat* p, dfloat v, uint64_t pol) {
   asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
 }
 
-// 128-bit row accesses of a padded shared-memory row (rows are 16-byte aligned; odd Nq spills one
-// element into the row padding)
+// 128-bit row accesses of a shared-memory row (rows are 16-byte aligned; odd Nq finish with one 64-bit access)
 template <int Nq>
 __device__ __forceinline__ void load_row(const dfloat* __restrict__ row, dfloat (&v)[Nq]) {
 #pragma unroll
@@ -346,22 +345,29 @@ struct AxT {
   static constexpr int EPB = AxEPB<Nq>::v;
   static constexpr int Work = EPB * Nq2;
   static constexpr int Threads = ((Work + 31) / 32) * 32;
-  // row stride: even (rows are 16-byte aligned for the 128-bit accesses of layout A) with LD/2 odd, so that the
-  // eight rows a quarter-warp touches with one 128-bit access fall into eight different 16-byte bank groups
-  // (LD = 8 for Nq = 6, 7 is a 4-way conflict); odd Nq keep one pad element for load_row / store_row
-  static constexpr int LD = (Nq <= 2) ? 2 : (Nq <= 6) ? 6 : 10;
-  static constexpr int SS0 = Nq * LD;
-  static constexpr int SS = SS0 + ((8 - (SS0 % 16)) + 16) % 16;  // SS = 8 mod 16, even
-  static_assert(LD >= Nq + (Nq & 1) && (LD / 2) % 2 == 1, "row stride");
+  // Shared-memory strides (doubles): row stride LD, slab stride SS, element stride ESS - all even, so rows stay
+  // 16-byte aligned for the 128-bit accesses of layout A.  Chosen per order by tools/smem_layout_search.py, a
+  // bank model of the three access patterns (32 banks x 4 B, cost = max distinct words per bank): wavefronts over
+  // the conflict-free minimum are 1.00 (Nq = 2, 4, 8), 1.12 (6), 1.27 (9), 1.36 (7), 1.42 (5), 1.54 (3); the previous
+  // uniform rule (LD/2 odd, SS = 8 mod 16, tuned for Nq = 8 only) cost 1.35x - 3.5x for the other orders, and ncu
+  // counted every second shared wavefront of the Nq = 5 kernel as a conflict (profiles/r1_o_ncu_*).
+  static constexpr int LD = (Nq == 2) ? 2 : (Nq <= 4) ? 4 : (Nq <= 6) ? 6 : 10;
+  static constexpr int SS = (Nq == 2) ? 4 : (Nq == 3) ? 12 : (Nq == 4) ? 18 : (Nq == 5) ? 30 : (Nq == 6) ? 38
+                          : (Nq == 7) ? 70 : (Nq == 8) ? 88 : 90;
+  static constexpr int ESS = (Nq == 2) ? 10 : (Nq == 3) ? 42 : (Nq == 4) ? 72 : (Nq == 5) ? 150 : (Nq == 6) ? 228
+                           : (Nq == 7) ? 496 : Nq * SS;
+  static_assert(LD >= Nq + (Nq & 1) && LD % 2 == 0 && SS % 2 == 0 && ESS % 2 == 0 && SS >= Nq * LD && ESS >= Nq * SS,
+                "shared-memory strides");
   // resident blocks asked of the compiler: ~512 threads per SM (128 registers per thread), as for Nq = 8.
   // Nq = 9 keeps 3 blocks of 96 threads: capped at 113 registers it measured 16 % slower (profiles/r1_k_*)
   static constexpr int MinBlocks = (Nq == 9 || Nq == 7) ? 3 : (512 + Threads - 1) / Threads;
   // geometric-factor slabs in flight per thread.  A thread of a low-order element has few bytes to ask for
   // (Nq = 4: 4 indices + 6 factors = 64 B with one slab), and ~512 threads per SM then keep only ~32 KB in
-  // flight - about 4.7 TB/s at 1 us of latency, which is what those kernels measured.  Low orders therefore
-  // request all (or most of) their slabs up front; Nq = 8 stays at the measured optimum of one slab.
+  // flight.  Low orders therefore request all (or most of) their slabs up front; Nq = 8 stays at the measured
+  // optimum of one slab.  (Measured neutral for N = 3..5, profiles/r1_o_*: those kernels are bound by the LSU /
+  // shared-memory pipe, not by bytes in flight.)
   static constexpr int PF = (LIBP_AX_PF != 1) ? LIBP_AX_PF : (Nq <= 4) ? Nq : (Nq == 5) ? 3 : (Nq <= 7) ? 2 : 1;
-  static_assert(3 * EPB * Nq * SS * 8 <= 48 * 1024, "staging arrays exceed static shared memory");
+  static_assert(3 * EPB * ESS * 8 <= 48 * 1024, "staging arrays exceed static shared memory");
 };
 
 // PF = geometric-factor slabs in flight per thread, kHint = L2 residency hints on/off
@@ -388,9 +394,10 @@ ax_hex3d_t_kernel(const dlong Nelements, const dlong* __restrict__ elementList, 
   const int vb = blockIdx.x;
   constexpr int Nq2 = C::Nq2, Np = C::Np, LD = C::LD, SS = C::SS;
   static_assert(PF >= 1 && PF <= Nq, "prefetch depth");
-  __shared__ __align__(16) dfloat s_u[C::EPB * Nq * SS];
-  __shared__ __align__(16) dfloat s_r[C::EPB * Nq * SS];
-  __shared__ __align__(16) dfloat s_s[C::EPB * Nq * SS];
+  constexpr int ESS = C::ESS;
+  __shared__ __align__(16) dfloat s_u[C::EPB * ESS];
+  __shared__ __align__(16) dfloat s_r[C::EPB * ESS];
+  __shared__ __align__(16) dfloat s_s[C::EPB * ESS];
 
   const int t = threadIdx.x;
   const bool valid = t < C::Work;
@@ -400,9 +407,9 @@ ax_hex3d_t_kernel(const dlong Nelements, const dlong* __restrict__ elementList, 
   // layout C: i = a, j = jc.  For Nq = 8 a half-warp holds rows jc and jc+4 (conflict-free with LD = 10).
   const int jc = (Nq == 8) ? (4 * (b & 1) + (b >> 1)) : b;
   const int nC = jc * Nq + a;                 // node offset inside a k-slab (global arrays)
-  const int sC = es * Nq * SS + jc * LD + a;  // shared offset of (k=0, jc, a); slab k adds k*SS
-  const int sA = es * Nq * SS + b * SS + a * LD;  // layout A: row (k=b, j=a, i=0..)
-  const int sB = es * Nq * SS + b * SS + a;       // layout B: column (k=b, j=0.., i=a); j adds LD
+  const int sC = es * ESS + jc * LD + a;      // shared offset of (k=0, jc, a); slab k adds k*SS
+  const int sA = es * ESS + b * SS + a * LD;  // layout A: row (k=b, j=a, i=0..)
+  const int sB = es * ESS + b * SS + a;       // layout B: column (k=b, j=0.., i=a); j adds LD
 
   const dlong ei = (dlong)vb * C::EPB + es;
   const bool active = valid && ei < Nelements;

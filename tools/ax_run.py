@@ -18,6 +18,7 @@ a = ap.parse_args()
 api.init(0)
 lib = L.load()
 p = EllipticProblem(a.degree, a.elements, lam=a.lam)
+api.register_D(p.Nq, p.mesh.D)  # GLL matrix: profile the even-odd kernel the operator handle launches
 m = p.mesh
 q = p.vec(); q[: p.Ndofs] = torch.rand(p.Ndofs, dtype=torch.float64, device="cuda") * 2 - 1
 Aq = p.vec()

@@ -28,8 +28,13 @@
 extern "C" {
 #endif
 
+/* same values as the reference's own macros (include/utils.hpp:48-51); guarded so both headers can be included */
+#ifndef LIBP_SUCCESS
 #define LIBP_SUCCESS 0
+#endif
+#ifndef LIBP_ERROR
 #define LIBP_ERROR (-1)
+#endif
 
 typedef int32_t libp_dlong;
 typedef int64_t libp_hlong;

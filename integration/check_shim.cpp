@@ -1,0 +1,24 @@
+// Translation unit that instantiates the shim against the reference headers (compile check only).
+#include "libp_b200_shim.hpp"
+
+using namespace libp;
+
+int instantiate(platform_t& platform, elliptic_t& elliptic, settings_t& settings, comm_t comm) {
+  b200::runtime_t rt;
+  rt.Setup(platform, comm, 0);
+  b200::ogsB200_t ogs;
+  ogs.Setup(elliptic.mesh.Nelements * elliptic.mesh.Np, elliptic.maskedGlobalIds, rt, ogs::Signed, true, false);
+  b200::ellipticOperatorB200_t A;
+  A.Setup(elliptic, ogs, rt);
+  b200::JacobiPreconB200 M(elliptic, rt, ogs.NgatherGlobal);
+  linearSolver_t solver;
+  solver.Setup<b200::pcgB200>(ogs.Ngather, ogs.Nhalo, platform, settings, comm, rt);
+  linearSolver_t nb;
+  nb.Setup<b200::nbpcgB200>(ogs.Ngather, ogs.Nhalo, platform, settings, comm, rt);
+  deviceMemory<dfloat> o_x = platform.malloc<dfloat>(ogs.Ngather + ogs.Nhalo);
+  deviceMemory<dfloat> o_r = platform.malloc<dfloat>(ogs.Ngather + ogs.Nhalo);
+  ogs.Gather(o_r, o_x, 1, ogs::Add, ogs::Trans);
+  ogs.ExchangeStart(o_x, 1);
+  ogs.ExchangeFinish(o_x, 1);
+  return solver.Solve(A, M, o_x, o_r, 1e-8, 100, 0) + nb.Solve(A, M, o_x, o_r, 1e-8, 100, 0);
+}

@@ -1,0 +1,251 @@
+// Reference-side binding of the B200 hot path: what a libParanumal maintainer adds next to
+// solvers/elliptic/elliptic.hpp so that elliptic_t::Operator, the Jacobi / multigrid preconditioners and the
+// PCG / NBPCG solvers run through include/libp_b200.h instead of the OCCA kernels.  This header is OUR code; it
+// includes the reference's headers only to subclass its interfaces (operator_t, include/operator.hpp:35-40;
+// linearSolverBase_t, include/linearSolver.hpp:78-97).  integration/check_shim.sh compiles it against the
+// reference tree (syntax + type check; running it needs libParanumal in THREAD MODEL = CUDA on a B200).
+//
+// Conventions: libParanumal runs in CUDA mode, so deviceMemory<T>::ptr() (include/memory.hpp:322-327) is a CUDA
+// device address; the shim creates the CUDA stream itself and hands it to OCCA (device.wrapStream,
+// occa/include/occa/core/device.hpp:407), so both sides queue work on the same stream.
+#pragma once
+#include <cuda_runtime_api.h>
+
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "elliptic.hpp"
+#include "libp_b200.h"
+
+namespace libp {
+namespace b200 {
+
+#define B200_CHECK(call)                                           \
+  do {                                                             \
+    if ((call) != LIBP_SUCCESS) LIBP_FORCE_ABORT(libp_last_error()); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------- runtime: device, stream, comm
+struct runtime_t {
+  cudaStream_t stream = nullptr;
+  libp_comm_t comm = nullptr;
+  MPI_Comm mpicomm;
+
+  static int a2a(void* c, const void* s, void* r, size_t n) {
+    return MPI_Alltoall(const_cast<void*>(s), (int)n, MPI_CHAR, r, (int)n, MPI_CHAR, *static_cast<MPI_Comm*>(c));
+  }
+  static int a2av(void* c, const void* s, const int64_t* sc, const int64_t* so, void* r, const int64_t* rc,
+                  const int64_t* ro) {
+    int size;
+    MPI_Comm_size(*static_cast<MPI_Comm*>(c), &size);
+    std::vector<int> isc(size), iso(size), irc(size), iro(size);
+    for (int i = 0; i < size; ++i) { isc[i] = (int)sc[i]; iso[i] = (int)so[i]; irc[i] = (int)rc[i]; iro[i] = (int)ro[i]; }
+    return MPI_Alltoallv(const_cast<void*>(s), isc.data(), iso.data(), MPI_CHAR, r, irc.data(), iro.data(), MPI_CHAR,
+                         *static_cast<MPI_Comm*>(c));
+  }
+  static MPI_Op mpi_op(int op) { return op == LIBP_ADD ? MPI_SUM : op == LIBP_MAX ? MPI_MAX : MPI_MIN; }
+  static int ar_i64(void* c, int64_t* b, int n, int op) {
+    return MPI_Allreduce(MPI_IN_PLACE, b, n, MPI_LONG_LONG_INT, mpi_op(op), *static_cast<MPI_Comm*>(c));
+  }
+  static int ar_f64(void* c, double* b, int n, int op) {
+    return MPI_Allreduce(MPI_IN_PLACE, b, n, MPI_DOUBLE, mpi_op(op), *static_cast<MPI_Comm*>(c));
+  }
+
+  // after platform_t selected its device (libs/core/platformDeviceConfig.cpp:33-179)
+  void Setup(platform_t& platform, comm_t c, int device_id) {
+    B200_CHECK(libp_b200_init(device_id));
+    cudaStreamCreate(&stream);
+    platform.setStream(platform.device.wrapStream(stream));   // OCCA and the library share one stream
+    mpicomm = c.comm();
+    libp_host_collectives_t host{&mpicomm, &a2a, &a2av, &ar_i64, &ar_f64};
+    B200_CHECK(libp_comm_create(c.rank(), c.size(), &host, &comm));
+    char uid[128];
+    std::memset(uid, 0, sizeof(uid));
+    if (c.rank() == 0) B200_CHECK(libp_comm_nccl_unique_id(uid));
+    MPI_Bcast(uid, 128, MPI_CHAR, 0, mpicomm);
+    B200_CHECK(libp_comm_nccl_init(comm, uid));
+    libp_comm_p2p_init(comm, 0);                               // NVLink peer window when every peer is mappable
+  }
+};
+
+template <typename T> constexpr libp_type_t type_of();
+template <> constexpr libp_type_t type_of<float>() { return LIBP_FLOAT; }
+template <> constexpr libp_type_t type_of<double>() { return LIBP_DOUBLE; }
+template <> constexpr libp_type_t type_of<int>() { return LIBP_INT32; }
+template <> constexpr libp_type_t type_of<long long int>() { return LIBP_INT64; }
+
+// ---------------------------------------------------------------------------------- ogs::ogs_t + gathered halo_t
+// (include/ogs.hpp:216-397).  The enums share their numeric values with ogs::Type/Op/Transpose/Kind (:178-200).
+class ogsB200_t {
+ public:
+  libp_ogs_t h = nullptr;
+  runtime_t* rt = nullptr;
+  dlong N = 0, Ngather = 0, Nhalo = 0;
+  hlong NgatherGlobal = 0;
+
+  void Setup(const dlong N_, memory<hlong> ids, runtime_t& rt_, const ogs::Kind kind, const bool unique,
+             const bool verbose) {
+    rt = &rt_;
+    static_assert(sizeof(hlong) == sizeof(libp_hlong), "global ids are 64-bit on both sides");
+    B200_CHECK(libp_ogs_setup(N_, reinterpret_cast<libp_hlong*>(ids.ptr()), rt->comm, (int)kind, unique, verbose, &h));  // signed in place when unique
+    libp_ogs_info_t i;
+    B200_CHECK(libp_ogs_info(h, &i));
+    N = i.N; Ngather = i.Ngather; Nhalo = i.Nhalo; NgatherGlobal = i.NgatherGlobal;
+  }
+  void SetupGlobalToLocalMapping(memory<dlong> GlobalToLocal) { B200_CHECK(libp_ogs_global_to_local(h, GlobalToLocal.ptr())); }
+
+  template <typename T>
+  void Gather(deviceMemory<T> o_gv, deviceMemory<T> o_v, const int k, const ogs::Op op, const ogs::Transpose trans) {
+    B200_CHECK(libp_ogs_gather(h, o_gv.ptr(), o_v.ptr(), k, type_of<T>(), (int)op, (int)trans, rt->stream));
+  }
+  template <typename T>
+  void GatherStart(deviceMemory<T> o_gv, deviceMemory<T> o_v, const int k, const ogs::Op op, const ogs::Transpose trans) {
+    B200_CHECK(libp_ogs_gather_start(h, o_gv.ptr(), o_v.ptr(), k, type_of<T>(), (int)op, (int)trans, rt->stream));
+  }
+  template <typename T>
+  void GatherFinish(deviceMemory<T> o_gv, deviceMemory<T> o_v, const int k, const ogs::Op op, const ogs::Transpose trans) {
+    B200_CHECK(libp_ogs_gather_finish(h, o_gv.ptr(), o_v.ptr(), k, type_of<T>(), (int)op, (int)trans, rt->stream));
+  }
+  template <typename T>
+  void Scatter(deviceMemory<T> o_v, deviceMemory<T> o_gv, const int k, const ogs::Transpose trans) {
+    B200_CHECK(libp_ogs_scatter(h, o_v.ptr(), o_gv.ptr(), k, type_of<T>(), (int)trans, rt->stream));
+  }
+  template <typename T>
+  void GatherScatter(deviceMemory<T> o_v, const int k, const ogs::Op op, const ogs::Transpose trans) {
+    B200_CHECK(libp_ogs_gather_scatter(h, o_v.ptr(), k, type_of<T>(), (int)op, (int)trans, rt->stream));
+  }
+  // halo_t built by SetupFromGather (libs/ogs/ogsSetup.cpp:888-916)
+  template <typename T> void ExchangeStart(deviceMemory<T> o_v, const int k) {
+    B200_CHECK(libp_halo_exchange_start(h, o_v.ptr(), k, type_of<T>(), rt->stream));
+  }
+  template <typename T> void ExchangeFinish(deviceMemory<T> o_v, const int k) {
+    B200_CHECK(libp_halo_exchange_finish(h, o_v.ptr(), k, type_of<T>(), rt->stream));
+  }
+  ~ogsB200_t() { if (h) libp_ogs_free(h); }
+};
+
+// ---------------------------------------------------------------------------------- elliptic_t::Operator (C0 hex)
+// solvers/elliptic/src/ellipticOperator.cpp:31-106.  Built after elliptic_t::Setup / BoundarySetup produced
+// maskedGlobalIds (unsigned copy) and the mesh arrays; `ogs` is the B200 twin of elliptic.ogsMasked.
+class ellipticOperatorB200_t : public operator_t {
+ public:
+  libp_elliptic_t h = nullptr;
+  runtime_t* rt = nullptr;
+  deviceMemory<dlong> o_GlobalToLocal;
+
+  void Setup(elliptic_t& e, ogsB200_t& ogs, runtime_t& rt_, int mode = 1) {
+    rt = &rt_;
+    mesh_t& mesh = e.mesh;
+    memory<dlong> G2L(mesh.Nelements * mesh.Np);
+    ogs.SetupGlobalToLocalMapping(G2L);
+    o_GlobalToLocal = e.platform.malloc<dlong>(G2L);
+    libp_elliptic_desc_t d{};
+    d.Nq = mesh.Nq;
+    d.Nelements = mesh.Nelements;
+    d.NlocalGatherElements = mesh.NlocalGatherElements;
+    d.NglobalGatherElements = mesh.NglobalGatherElements;
+    d.localGatherElementList = mesh.o_localGatherElementList.ptr();
+    d.globalGatherElementList = mesh.o_globalGatherElementList.ptr();
+    d.GlobalToLocal = o_GlobalToLocal.ptr();
+    d.wJ = mesh.o_wJ.ptr();
+    d.ggeo = mesh.o_ggeo.ptr();
+    d.D = mesh.o_D.ptr();
+    d.lambda = e.lambda;
+    d.ogsMasked = ogs.h;
+    d.mode = mode;  // 1: fused gather epilogue, 0: reference data flow (AqL + ogs gather)
+    B200_CHECK(libp_elliptic_create(&d, &h));
+  }
+  void Operator(deviceMemory<dfloat>& o_q, deviceMemory<dfloat>& o_Aq) override {
+    B200_CHECK(libp_elliptic_operator(h, o_q.ptr(), o_Aq.ptr(), rt->stream));
+  }
+  ~ellipticOperatorB200_t() { if (h) libp_elliptic_free(h); }
+};
+
+// ---------------------------------------------------------------------------------- JacobiPrecon
+// solvers/elliptic/src/ellipticPreconJacobi.cpp:30-51 (the diagonal is still built by the reference on the host)
+class JacobiPreconB200 : public operator_t {
+ public:
+  libp_precon_t h = nullptr;
+  runtime_t* rt;
+  JacobiPreconB200(elliptic_t& e, runtime_t& rt_, hlong NglobalDofs) : rt(&rt_) {
+    memory<dfloat> diagA(e.Ndofs), invDiagA(e.Ndofs);
+    e.BuildOperatorDiagonal(diagA);
+    for (dlong n = 0; n < e.Ndofs; n++) invDiagA[n] = 1.0 / diagA[n];
+    deviceMemory<dfloat> o_invDiagA = e.platform.malloc<dfloat>(invDiagA);
+    B200_CHECK(libp_precon_jacobi_create(e.Ndofs, o_invDiagA.ptr(), e.allNeumann, NglobalDofs, rt->comm, &h));
+  }
+  void Operator(deviceMemory<dfloat>& o_r, deviceMemory<dfloat>& o_Mr) override {
+    B200_CHECK(libp_precon_apply(h, o_r.ptr(), o_Mr.ptr(), rt->stream));
+  }
+  ~JacobiPreconB200() { if (h) libp_precon_free(h); }
+};
+
+// ---------------------------------------------------------------------------------- LinearSolver::pcg / nbpcg
+// include/linearSolver.hpp:99-119.  Native handles take the fused device-resident iteration; any other operator_t
+// (an un-replaced preconditioner, another solver's operator) goes through callbacks.
+inline int op_trampoline(void* ctx, libp_dfloat* in, libp_dfloat* out, void* /*stream*/) {
+  struct ctx_t { operator_t* op; platform_t* platform; dlong Ntotal; };
+  ctx_t* c = static_cast<ctx_t*>(ctx);
+  try {
+    deviceMemory<dfloat> o_in(c->platform->device.wrapMemory<dfloat>(in, c->Ntotal));
+    deviceMemory<dfloat> o_out(c->platform->device.wrapMemory<dfloat>(out, c->Ntotal));
+    c->op->Operator(o_in, o_out);
+    return LIBP_SUCCESS;
+  } catch (...) {
+    return LIBP_ERROR;
+  }
+}
+
+class pcgB200 : public LinearSolver::linearSolverBase_t {
+  libp_pcg_t h = nullptr;
+  runtime_t* rt;
+
+ public:
+  pcgB200(dlong _N, dlong _Nhalo, platform_t& _platform, settings_t& _settings, comm_t _comm, runtime_t& rt_)
+      : linearSolverBase_t(_N, _Nhalo, _platform, _settings, _comm), rt(&rt_) {
+    const int flexible = settings.compareSetting("LINEAR SOLVER", "FPCG");
+    const int stopping = settings.compareSetting("LINEAR SOLVER STOPPING CRITERION", "ABS/REL-RHS-2NORM");
+    B200_CHECK(libp_pcg_create(N, Nhalo, flexible, stopping, rt->comm, &h));
+  }
+  int Solve(operator_t& A, operator_t& M, deviceMemory<dfloat>& o_x, deviceMemory<dfloat>& o_r, const dfloat tol,
+            const int MAXIT, const int verbose) override {
+    int iters = 0;
+    auto* a = dynamic_cast<ellipticOperatorB200_t*>(&A);
+    auto* j = dynamic_cast<JacobiPreconB200*>(&M);
+    if (a && j) {
+      B200_CHECK(libp_pcg_solve(h, a->h, j->h, o_x.ptr(), o_r.ptr(), tol, MAXIT, verbose, rt->stream, &iters));
+    } else {
+      struct ctx_t { operator_t* op; platform_t* platform; dlong Ntotal; };
+      ctx_t ca{&A, &platform, N + Nhalo}, cm{&M, &platform, N + Nhalo};
+      B200_CHECK(libp_pcg_solve_cb(h, &op_trampoline, &ca, &op_trampoline, &cm, o_x.ptr(), o_r.ptr(), tol, MAXIT, verbose,
+                                   rt->stream, &iters));
+    }
+    return iters;
+  }
+  ~pcgB200() { if (h) libp_pcg_free(h); }
+};
+
+class nbpcgB200 : public LinearSolver::linearSolverBase_t {
+  libp_nbpcg_t h = nullptr;
+  runtime_t* rt;
+
+ public:
+  nbpcgB200(dlong _N, dlong _Nhalo, platform_t& _platform, settings_t& _settings, comm_t _comm, runtime_t& rt_)
+      : linearSolverBase_t(_N, _Nhalo, _platform, _settings, _comm), rt(&rt_) {
+    B200_CHECK(libp_nbpcg_create(N, Nhalo, rt->comm, &h));
+  }
+  int Solve(operator_t& A, operator_t& M, deviceMemory<dfloat>& o_x, deviceMemory<dfloat>& o_r, const dfloat tol,
+            const int MAXIT, const int verbose) override {
+    int iters = 0;
+    struct ctx_t { operator_t* op; platform_t* platform; dlong Ntotal; };
+    ctx_t ca{&A, &platform, N + Nhalo}, cm{&M, &platform, N + Nhalo};
+    B200_CHECK(libp_nbpcg_solve_cb(h, &op_trampoline, &ca, &op_trampoline, &cm, o_x.ptr(), o_r.ptr(), tol, MAXIT, verbose,
+                                   rt->stream, &iters));
+    return iters;
+  }
+  ~nbpcgB200() { if (h) libp_nbpcg_free(h); }
+};
+
+}  // namespace b200
+}  // namespace libp

@@ -30,6 +30,10 @@ CONFIGS = {
     "hex_n7_e2_jacobi": dict(N=7, n=2, flag=1, lam=1.0, precon="JACOBI", mode="full"),
     "hex_n2_e4_periodic": dict(N=2, n=4, flag=-1, lam=1.0, precon="JACOBI", mode="full"),
     "hex_n1_e5_none": dict(N=1, n=5, flag=1, lam=1.0, precon="NONE", mode="full"),
+    # the remaining orders (their kernels use other element packings / shared-memory strides than N=7)
+    "hex_n5_e2_jacobi": dict(N=5, n=2, flag=1, lam=1.0, precon="JACOBI", mode="full"),
+    "hex_n6_e2_jacobi": dict(N=6, n=2, flag=1, lam=0.7, precon="JACOBI", mode="full"),
+    "hex_n8_e2_none": dict(N=8, n=2, flag=1, lam=1.0, precon="NONE", mode="full"),
     "hex_n7_e3_bp5": dict(N=7, n=3, flag=1, lam=0.0, precon="JACOBI", mode="digest"),
     "hex_n4_e10_jacobi": dict(N=4, n=10, flag=1, lam=1.0, precon="JACOBI", mode="digest"),
     "hex_n4_e10_none": dict(N=4, n=10, flag=1, lam=1.0, precon="NONE", mode="digest"),

@@ -10,7 +10,8 @@ from oracle.mesh_box import build_box_hex_mesh, masked_global_ids
 from oracle.ogs_ref import SIGNED, ogs_setup_all
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-FULL = ["hex_n3_e3_jacobi", "hex_n7_e2_jacobi", "hex_n2_e4_periodic", "hex_n1_e5_none"]
+FULL = ["hex_n3_e3_jacobi", "hex_n7_e2_jacobi", "hex_n2_e4_periodic", "hex_n1_e5_none", "hex_n5_e2_jacobi",
+        "hex_n6_e2_jacobi", "hex_n8_e2_none"]
 DIGEST = ["hex_n7_e3_bp5", "hex_n4_e10_jacobi", "hex_n4_e10_none"]
 
 

@@ -13,7 +13,9 @@ def test_mesh_restatement_full(name):
     g = load(name)
     p = Problem(g)
     m = p.mesh
-    assert np.max(np.abs(m.D.ravel() - g["D"])) < 1e-13
+    # D = Vr/V comes out of LAPACK in the reference (meshBasis1D.cpp:114-136): agreement to rounding of its largest
+    # entry (|D| reaches 24 at N=8)
+    assert np.max(np.abs(m.D.ravel() - g["D"])) < 1e-14 * np.max(np.abs(g["D"]))
     assert np.max(np.abs(m.gllz - g["gllz"])) < 1e-14 and np.max(np.abs(m.gllw - g["gllw"])) < 1e-14
     assert relerr(m.x.ravel(), g["x"]) < 1e-14
     assert relerr(m.ggeo.ravel(), g["ggeo"]) < 1e-12 and relerr(m.wJ.ravel(), g["wJ"]) < 1e-12

@@ -1,0 +1,151 @@
+"""CPU: the oracle's restatement of the multigrid preconditioner path (oracle/mg_ref.py) against fixtures dumped from
+the unmodified reference (tests/golden/mg_*.npz): level-0 smoothing / residual / coarsen / prolongate, one full
+V-cycle through every level (matrix-free, CSR, exact coarse solve) and the MULTIGRID-PCG iteration count/history."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from golden_util import load, relerr
+
+from oracle import elliptic_ref as er
+from oracle import mg_ref as mg
+
+MG = ["mg_n3_e3", "mg_n7_e2", "mg_n2_e12", "mg_n4_e10", "mg_n3_e4_jacobi"]
+
+
+def csr(g, pre):
+    m = g[pre + "_meta"]
+    return sp.csr_matrix((g[pre + "_vals"], g[pre + "_cols"], g[pre + "_rowStarts"]), shape=(int(m[0]), int(m[1])))
+
+
+def build(name):
+    g = load(name)
+    N, n, flag = (int(v) for v in g["config"])
+    lam = float(g["lambda"][0])
+    kinds = list(g["level_kinds"])
+    degrees = [int(g[f"L{l}_meta"][0]) for l, k in enumerate(kinds) if k == 0]
+    degrees.append(int(g[f"L{len(degrees) - 1}_meta"][5]))
+    probs = {d: mg.DegreeProblem(d, n, lam, flag) for d in degrees}
+    levels = []
+    for l, kind in enumerate(kinds):
+        pre = f"L{l}"
+        meta, lamb = g[pre + "_meta"], g[pre + "_lambda"]
+        if kind == 0:
+            F, C = probs[int(meta[0])], probs[int(meta[5])]
+            sm = int(meta[3])
+            if pre + "_invDiagA" in g:
+                inv = g[pre + "_invDiagA"]
+            else:
+                inv = F.inv_diagonal() * (float(lamb[0]) if sm == mg.JACOBI else 1.0)
+            levels.append(mg.MGLevelRef(F, C, g[pre + "_P"], inv, sm, float(lamb[0]), float(lamb[1]), int(meta[4])))
+        else:
+            levels.append(mg.AmgLevelRef(csr(g, pre + "_A"), csr(g, pre + "_P"), csr(g, pre + "_R"), g[pre + "_diagInv"],
+                                         int(meta[2]), float(lamb[2]), float(lamb[0]), float(lamb[1]), int(meta[3])))
+    Nc = int(g["coarse_meta"][0])
+    if "coarse_diagInvAT" in g:
+        inv = g["coarse_diagInvAT"].reshape(Nc, Nc).T     # diagInvAT[n + m*N] = inv[n][m]
+    else:
+        inv = np.linalg.inv(csr(g, "coarse_A").toarray()[:, :Nc])
+    return g, probs[N], levels, mg.MultigridRef(levels, inv)
+
+
+def check(got, g, key, tol):
+    if key in g:
+        assert relerr(got, g[key]) < tol, key
+    else:
+        st = int(g["sample_stride"][0])
+        assert relerr(got[::st], g[key + "_sample"]) < tol, key
+        assert abs(np.sqrt(np.sum(got * got)) - g[key + "_norm2"][0]) <= tol * g[key + "_norm2"][0], key
+
+
+@pytest.mark.parametrize("name", MG)
+def test_mg_oracle_vs_reference(name):
+    g, fine, levels, M = build(name)
+    r = er.splitmix_uniform(4321, fine.Ndofs)
+    L0 = levels[0]
+    tol = 2e-11
+    x = L0.smooth(r, None, True)
+    check(x, g, "l0_smooth0", tol)
+    res = L0.residual(r, x)
+    check(res, g, "l0_residual", tol)
+    x1 = L0.smooth(r, x, False)
+    check(x1, g, "l0_smooth1", tol)
+    rc = L0.coarsen(res)
+    check(rc, g, "l0_coarsen", tol)
+    check(L0.prolongate(rc, np.zeros(fine.Ndofs)), g, "l0_prolongate", tol)
+    check(M.apply(r), g, "vc_z", 1e-9)
+    # MULTIGRID-PCG on the sine problem
+    m = fine.mesh
+    rL = er.rhs_sine3d(fine.Nq, m.x, m.y, m.z, m.wJ, m.ggeo, m.D, fine.lam, fine.mapB)
+    b = er.gather_add(fine.rs, fine.ci, rL)
+    it, xs, hist = mg.pcg(fine.operator, M.apply, np.zeros(fine.Ndofs), b, tol=1e-8, maxit=200)
+    assert it == int(g["iterations"][0]), (it, g["iterations"])
+    k = min(len(hist) - 1, len(g["res_history"]))
+    assert np.allclose(hist[1:k + 1], g["res_history"][:k], rtol=1e-5)
+    check(xs, g, "xsol", 1e-7)
+
+
+@pytest.mark.parametrize("name", ["mg_n2_e12", "amg_n2_e24", "mg_n4_e10", "mg_n3_e4_jacobi"])
+def test_self_built_hierarchy_on_cpu(name):
+    """Nothing but the mesh from outside: HALFDOFS ladder, drand48-seeded Arnoldi bounds on the oracle operator,
+    degree-1 matrix, host AMG setup (libparanumal_b200/amg_setup.py), dense coarse inverse - the same setup chain
+    the product harness runs on the device - must reproduce the reference's bounds and MULTIGRID-PCG solve."""
+    import torch
+
+    from libparanumal_b200 import amg_setup as am
+    from libparanumal_b200.problem import degree_raise_1d, halfdofs_ladder
+    g = load(name)
+    N, n, flag = (int(v) for v in g["config"])
+    lam = float(g["lambda"][0])
+    jac = int(g["L0_meta"][3]) == mg.JACOBI
+    ladder = halfdofs_ladder(N)
+    probs = [mg.DegreeProblem(d, n, lam, flag) for d in ladder]
+    rng = am.Drand48(0)
+    levels = []
+    for l in range(len(ladder) - 1):
+        F, C = probs[l], probs[l + 1]
+        inv = F.inv_diagonal()
+        rho = am.arnoldi_rho(lambda v: inv * F.operator(v), rng.draw(F.Ndofs), F.Ndofs)
+        ref = g[f"L{l}_lambda"]
+        if jac:
+            assert abs((4.0 / 3.0) / rho - ref[0]) <= 1e-8 * ref[0]
+            levels.append(mg.MGLevelRef(F, C, degree_raise_1d(C.N, F.N), inv * (4.0 / 3.0) / rho, mg.JACOBI, (4.0 / 3.0) / rho, 0.0))
+        else:
+            assert abs(rho - ref[1]) <= 1e-8 * ref[1], (l, rho, ref)
+            levels.append(mg.MGLevelRef(F, C, degree_raise_1d(C.N, F.N), inv, mg.CHEBYSHEV, rho / 10.0, rho))
+    p1 = probs[-1]
+    m1 = p1.mesh
+    r_, c_, v_ = am.element_matrix_triplets(2, torch.from_numpy(m1.ggeo), torch.from_numpy(m1.wJ), torch.from_numpy(m1.D),
+                                            lam, torch.from_numpy(p1.G2L.astype(np.int64)))
+    A = sp.coo_matrix((v_, (r_, c_)), shape=(p1.Ndofs, p1.Ndofs)).tocsr()
+    amg_levels, Ac, _, _ = am.setup_hierarchy(A, np.full(p1.Ndofs, 1.0 / np.sqrt(p1.Ndofs)), rng)
+    assert len(amg_levels) == list(g["level_kinds"]).count(1)
+    for lv in amg_levels:
+        rho = lv["rho"]
+        levels.append(mg.AmgLevelRef(lv["A"], lv["P"], lv["R"], 1.0 / lv["A"].diagonal(),
+                                     mg.DAMPED_JACOBI if jac else mg.AMG_CHEBYSHEV, (4.0 / 3.0) / rho, rho / 10.0, rho))
+    assert Ac.shape[0] == int(g["coarse_meta"][0])
+    M = mg.MultigridRef(levels, np.linalg.inv(Ac.toarray()))
+    fine = probs[0]
+    m = fine.mesh
+    b = er.gather_add(fine.rs, fine.ci, er.rhs_sine3d(fine.Nq, m.x, m.y, m.z, m.wJ, m.ggeo, m.D, lam, fine.mapB))
+    it, xs, hist = mg.pcg(fine.operator, M.apply, np.zeros(fine.Ndofs), b, tol=1e-8, maxit=200)
+    assert it == int(g["iterations"][0]), (it, g["iterations"])
+    k = min(len(hist) - 1, len(g["res_history"]))
+    assert np.allclose(hist[1:k + 1], g["res_history"][:k], rtol=1e-4)
+
+
+def test_nbpcg_oracle_vs_reference_run():
+    """LINEAR SOLVER = NBPCG, Hex N=4 10^3, lambda=1: iteration counts and first residual norms printed by the
+    unmodified reference built in this container (same numbers the GPU test pins, tests/test_gpu_reference_suite.py)."""
+    p = mg.DegreeProblem(4, 10, 1.0, 1)
+    m = p.mesh
+    b = er.gather_add(p.rs, p.ci, er.rhs_sine3d(p.Nq, m.x, m.y, m.z, m.wJ, m.ggeo, m.D, 1.0, p.mapB))
+    inv = p.inv_diagonal()
+    for M, ref_it, ref_hist in ((lambda r: r.copy(), 113, [2.960718797524, 1.742998255149, 1.089704705958]),
+                                (lambda r: inv * r, 97, [2.960718797524, 1.583783440215, 1.049754120587])):
+        it, x, hist = mg.nbpcg(p.operator, M, np.zeros(p.Ndofs), b)
+        assert it == ref_it, (it, ref_it)
+        assert np.allclose(hist[:3], ref_hist, rtol=1e-9)
+        it2, x2, _ = mg.pcg(p.operator, M, np.zeros(p.Ndofs), b)
+        assert relerr(x, x2) < 1e-6

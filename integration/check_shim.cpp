@@ -22,3 +22,20 @@ int instantiate(platform_t& platform, elliptic_t& elliptic, settings_t& settings
   ogs.ExchangeFinish(o_x, 1);
   return solver.Solve(A, M, o_x, o_r, 1e-8, 100, 0) + nb.Solve(A, M, o_x, o_r, 1e-8, 100, 0);
 }
+
+// what MultiGridPrecon::MultiGridPrecon does after parAlmond.AMGSetup(...): hand every level to the library
+void instantiate_multigrid(b200::runtime_t& rt, parAlmond::parAlmond_t& parAlmond, int NpMGlevels,
+                           parAlmond::exactSolver_t& exact, b200::ellipticOperatorB200_t* ops, elliptic_t& elliptic,
+                           deviceMemory<dfloat>& o_r, deviceMemory<dfloat>& o_Mr) {
+  b200::MultiGridPreconB200 M(rt);
+  // the last amgLevel is the base level: its matrix belongs to the exact coarse solver (parAlmondAMGSetup.cpp:128-131)
+  const int Nlevels = parAlmond.NumLevels() - 1;
+  for (int l = 0; l < Nlevels; ++l) {
+    if (l < NpMGlevels)
+      M.AddLevel(b200::make_mglevel(parAlmond.GetLevel<MGLevel>(l), ops[l], ops[l + 1]));
+    else
+      M.AddLevel(b200::make_amglevel(rt, parAlmond.GetLevel<parAlmond::amgLevel>(l)));
+  }
+  M.Finish(b200::make_coarse(rt, exact), elliptic.allNeumann, elliptic.ogsMasked.NgatherGlobal);
+  M.Operator(o_r, o_Mr);
+}

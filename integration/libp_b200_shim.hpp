@@ -16,6 +16,10 @@
 #include <vector>
 
 #include "elliptic.hpp"
+#include "ellipticPrecon.hpp"
+#include "parAlmond.hpp"
+#include "parAlmond/parAlmondAMGLevel.hpp"
+#include "parAlmond/parAlmondCoarseSolver.hpp"
 #include "libp_b200.h"
 
 namespace libp {
@@ -245,6 +249,93 @@ class nbpcgB200 : public LinearSolver::linearSolverBase_t {
     return iters;
   }
   ~nbpcgB200() { if (h) libp_nbpcg_free(h); }
+};
+
+// ---------------------------------------------------------------------------------- MultiGridPrecon / parAlmond
+// The reference keeps its whole setup (degree ladder, SetupSmoother, BuildOperatorMatrixContinuous, AMGSetup) and hands
+// the products over level by level.  These helpers are what MultiGridPrecon::MultiGridPrecon gains after
+// parAlmond.AMGSetup(...) (solvers/elliptic/src/ellipticPreconMultiGrid.cpp:150): it walks
+// parAlmond.GetLevel<MGLevel>(l) / GetLevel<parAlmond::amgLevel>(l) (include/parAlmond.hpp:205-212) and the exact solver.
+static_assert(sizeof(pfloat) == sizeof(libp_dfloat), "CSR values are FP64 on both sides");
+
+// parCSR (include/parAlmond/parAlmondparCSR.hpp:35-100) -> libp_parcsr_create; after parCSR::haloSetup the non-local
+// part of colMap holds ascending global column ids (parAlmondparCSR.cpp:307-317)
+inline libp_csr_t make_parcsr(runtime_t& rt, parAlmond::parCSR& M) {
+  libp_parcsr_desc_t d{};
+  d.Nrows = M.Nrows;
+  d.NlocalCols = M.NlocalCols;
+  d.diag_nnz = M.diag.nnz;
+  d.diag_rowStarts = M.diag.rowStarts.ptr();
+  d.diag_cols = M.diag.cols.ptr();
+  d.diag_vals = M.diag.vals.ptr();
+  d.offd_nnz = M.offd.nnz;
+  d.offd_nzRows = M.offd.nzRows;
+  d.offd_rows = M.offd.rows.ptr();
+  d.offd_mRowStarts = M.offd.mRowStarts.ptr();
+  d.offd_cols = M.offd.cols.ptr();
+  d.offd_vals = M.offd.vals.ptr();
+  d.Noffdcols = M.Ncols - M.NlocalCols;
+  d.offd_colIds = reinterpret_cast<const libp_hlong*>(M.colMap.ptr()) + M.NlocalCols;
+  d.globalColStarts = reinterpret_cast<const libp_hlong*>(M.globalColStarts.ptr());
+  libp_csr_t h = nullptr;
+  B200_CHECK(libp_parcsr_create(rt.comm, &d, &h));
+  return h;
+}
+
+// parAlmond::amgLevel (include/parAlmond/parAlmondAMGLevel.hpp:37-64)
+inline libp_amglevel_t make_amglevel(runtime_t& rt, parAlmond::amgLevel& L) {
+  libp_csr_t A = make_parcsr(rt, L.A);
+  libp_csr_t P = make_parcsr(rt, L.P);
+  libp_csr_t R = make_parcsr(rt, L.R);
+  libp_amglevel_t h = nullptr;
+  B200_CHECK(libp_amglevel_create(A, P, R, L.A.diagInv.ptr(), L.stype == parAlmond::CHEBYSHEV ? 1 : 0, L.lambda, L.lambda0,
+                                  L.lambda1, L.ChebyshevIterations, &h));
+  return h;
+}
+
+// MGLevel (solvers/elliptic/ellipticPrecon.hpp:125-185): fine / coarse are the B200 operators of L.elliptic / L.ellipticC
+inline libp_mglevel_t make_mglevel(MGLevel& L, ellipticOperatorB200_t& fine, ellipticOperatorB200_t& coarse) {
+  libp_mglevel_desc_t m{};
+  m.fine = fine.h;
+  m.coarse = coarse.h;
+  m.NqF = L.mesh.Nq;
+  m.NqC = L.meshC.Nq;
+  m.P = L.o_P.ptr();
+  m.invDiagA = L.o_invDiagA.ptr();
+  m.weightG = L.elliptic.o_weightG.ptr();
+  m.smoother = (int)L.stype;  // JACOBI = 1, CHEBYSHEV = 2 on both sides
+  m.lambda0 = L.lambda0;
+  m.lambda1 = L.lambda1;
+  m.ChebyshevIterations = L.ChebyshevIterations;
+  libp_mglevel_t h = nullptr;
+  B200_CHECK(libp_mglevel_create(&m, &h));
+  return h;
+}
+
+// parAlmond::exactSolver_t (include/parAlmond/parAlmondCoarseSolver.hpp:70-105) after setup()
+inline libp_coarse_t make_coarse(runtime_t& rt, parAlmond::exactSolver_t& E) {
+  libp_coarse_t h = nullptr;
+  B200_CHECK(libp_coarse_exact_create_par(rt.comm, E.N, reinterpret_cast<const libp_hlong*>(E.A.globalRowStarts.ptr()),
+                                          E.diagInvAT.ptr(), E.offdInvAT.ptr(), &h));
+  return h;
+}
+
+// MultiGridPrecon::Operator (ellipticPreconMultiGrid.cpp:29-37): one V-cycle (+ ZeroMean when allNeumann)
+class MultiGridPreconB200 : public operator_t {
+ public:
+  libp_multigrid_t mg = nullptr;
+  libp_precon_t h = nullptr;
+  runtime_t* rt;
+  explicit MultiGridPreconB200(runtime_t& rt_) : rt(&rt_) { B200_CHECK(libp_multigrid_create(rt->comm, &mg)); }
+  void AddLevel(libp_mglevel_t l) { B200_CHECK(libp_multigrid_add_mglevel(mg, l)); }
+  void AddLevel(libp_amglevel_t l) { B200_CHECK(libp_multigrid_add_amglevel(mg, l)); }
+  void Finish(libp_coarse_t coarse, int allNeumann, hlong NglobalDofs) {
+    B200_CHECK(libp_multigrid_set_coarse(mg, coarse));
+    B200_CHECK(libp_precon_multigrid_create(mg, allNeumann, NglobalDofs, rt->comm, &h));
+  }
+  void Operator(deviceMemory<dfloat>& o_r, deviceMemory<dfloat>& o_Mr) override {
+    B200_CHECK(libp_precon_apply(h, o_r.ptr(), o_Mr.ptr(), rt->stream));
+  }
 };
 
 }  // namespace b200

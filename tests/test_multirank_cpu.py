@@ -92,3 +92,64 @@ def test_multirank_ogs_setup_matches_oracle(size, N, n, flag):
     # global invariants: every unmasked global node owned exactly once
     nglobal = len(np.unique(np.abs(np.concatenate(ids))[np.concatenate(ids) != 0]))
     assert ref[0].NgatherGlobal == nglobal
+
+
+def _csr_worker(rank, size, port, outq):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        import ctypes as C
+
+        import scipy.sparse as sp
+
+        from libparanumal_b200 import _lib as L
+        from libparanumal_b200 import amg_setup as am
+        from libparanumal_b200.api import Comm, ParCsr
+        comm = Comm(rank, size)
+        # setup-time host collectives of the harness
+        objs = comm.allgather_object({"rank": rank, "v": np.arange(rank + 1)})
+        assert [o["rank"] for o in objs] == list(range(size)) and objs[-1]["v"].size == size
+        assert comm.allreduce_sum(float(rank + 1)) == size * (size + 1) / 2
+        # the same global matrix on every rank (as the replicated AMG setup produces it), split into row blocks
+        n = 60
+        M = sp.random(n, n, density=0.2, random_state=3, format="csr") + sp.identity(n, format="csr")
+        starts = np.linspace(0, n, size + 1).astype(np.int64)
+        d = am.split_rows(M.tocsr(), starts, starts, rank)
+        A = ParCsr(comm, d)   # host part of libp_parcsr_create: who owns my non-local columns, what do I send
+        nrows, nloc, ncols, nsend = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        ids, ns, nr = C.c_void_p(), C.c_int(), C.c_int()
+        L.check(L.load().libp_csr_info(A.handle, C.byref(nrows), C.byref(nloc), C.byref(ncols), C.byref(nsend), C.byref(ids),
+                                       C.byref(ns), C.byref(nr)))
+        send = np.ctypeslib.as_array(C.cast(ids, C.POINTER(C.c_int32)), (nsend.value,)).copy() if nsend.value else np.zeros(0, np.int32)
+        outq.put(dict(rank=rank, want=d["offd_colIds"], send=send + int(starts[rank]), shape=(nrows.value, nloc.value, ncols.value)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("size", [2, 3])
+def test_multirank_parcsr_halo_plan(size):
+    """Distributed CSR levels: the column-halo plan built by libp_parcsr_create through the host collectives sends
+    exactly the entries the other ranks' off-rank blocks reference."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_csr_worker, args=(r, size, port, q)) for r in range(size)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(size):
+        r = q.get(timeout=120)
+        res[r["rank"]] = r
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n = 60
+    starts = np.linspace(0, n, size + 1).astype(np.int64)
+    for r in range(size):
+        nl = int(starts[r + 1] - starts[r])
+        assert res[r]["shape"] == (nl, nl, nl + res[r]["want"].size)
+        wanted_from_r = np.sort(np.concatenate([w[(w >= starts[r]) & (w < starts[r + 1])]
+                                                for k, w in ((k, res[k]["want"]) for k in range(size)) if k != r]))
+        assert np.array_equal(np.sort(res[r]["send"]), wanted_from_r)

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .api import Comm, Elliptic, Ogs, Pcg, Precon, ax_hex3d
+from .api import Comm, Elliptic, Ogs, Pcg, Precon
 from .box_mesh import BoxMesh
 
 

@@ -6,7 +6,6 @@ Model: 32 banks of 4 bytes; a warp-wide access costs max over banks of the numbe
 requested from that bank (same-word accesses broadcast).  Ideal = ceil(distinct words / 32).
 usage: python tools/smem_layout_search.py            (prints the current and the best layout per Nq)
 """
-import itertools
 import sys
 
 EPB = {2: 16, 3: 7, 4: 4, 5: 5, 6: 5, 7: 3, 8: 1, 9: 1}
@@ -62,10 +61,12 @@ def cost(Nq, LD, SS, ESS, epb=None, perm8=True):
 
 
 def current(Nq):
-    LD = 2 if Nq <= 2 else 6 if Nq <= 6 else 10
-    SS0 = Nq * LD
-    SS = SS0 + ((8 - (SS0 % 16)) + 16) % 16
-    return LD, SS, Nq * SS
+    """strides compiled into AxT<Nq> (csrc/ax_hex3d.cu); the rule before this search was LD = 2/6/10 with LD/2 odd and
+    SS = 8 mod 16 for every order"""
+    LD = {2: 2, 3: 4, 4: 4, 5: 6, 6: 6, 7: 10, 8: 10, 9: 10}[Nq]
+    SS = {2: 4, 3: 12, 4: 18, 5: 30, 6: 38, 7: 70, 8: 88, 9: 90}[Nq]
+    ESS = {2: 10, 3: 42, 4: 72, 5: 150, 6: 228, 7: 496}.get(Nq, Nq * SS)
+    return LD, SS, ESS
 
 
 def main():

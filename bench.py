@@ -10,7 +10,7 @@ gather fused into its epilogue, cross-rank combine) on the global 64^3 box, stro
 value = NglobalDofs * steps / seconds / 1e9 (the reference's own "nodes*iterations/time" metric,
 solvers/elliptic/src/ellipticRun.cpp:212-221), device-timed with CUDA events, max over ranks.
 Extra objects on the same JSON line: roofline (dominant kernel vs measured HBM peak), cpu_baseline
-(oracle C port on the host cores), e2e (same step through the C ABI with HOST buffers), pcg
+(the reference's own JIT-compiled kernels, or the oracle C port, on the host cores), e2e (same step through the C ABI with HOST buffers), pcg
 (Jacobi-PCG iteration throughput on the lambda=1 problem, BASELINE configs[2]).
 """
 from __future__ import annotations

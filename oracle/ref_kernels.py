@@ -113,3 +113,67 @@ class RefOperator:
         nb = C.c_int(self.blocks.size - 1)
         self.gk(C.byref(nb), C.byref(self.one), _p(self.blocks), _p(self.rs), _p(self.ci), _p(self.AqL), _p(out))
         return out
+
+
+def transfer_available(NqF, NqC):
+    return all(os.path.exists(os.path.join(KDIR, f"ellipticPrecon{k}Hex3D_F{NqF}_C{NqC}.so")) for k in ("Coarsen", "Prolongate"))
+
+
+def coarsen(NqF, NqC, G2L_fine, P, qf_gathered):
+    """ellipticPartialPreconCoarsenHex3D (okl/ellipticPreconCoarsenHex3D.okl:209-294): element-local coarse values
+    qc[E*NqC^3] = (P^T x P^T x P^T) qf[GlobalToLocal] ; P is [NqF][NqC] row-major."""
+    f = _load(f"ellipticPreconCoarsenHex3D_F{NqF}_C{NqC}.so").ellipticPartialPreconCoarsenHex3D
+    f.restype = None
+    G2L = np.ascontiguousarray(G2L_fine, dtype=np.int32)
+    E = G2L.size // NqF ** 3
+    el = np.arange(E, dtype=np.int32)
+    P = np.ascontiguousarray(P, dtype=np.float64).reshape(-1)
+    q = np.ascontiguousarray(qf_gathered, dtype=np.float64)
+    out = np.zeros(E * NqC ** 3)
+    n = C.c_int(E)
+    f(C.byref(n), _p(el), _p(G2L), _p(P), _p(q), _p(out))
+    return out
+
+
+def prolongate(NqF, NqC, G2L_coarse, P, qc_gathered):
+    """ellipticPartialPreconProlongateHex3D (okl/ellipticPreconProlongateHex3D.okl:216-301): element-local fine values
+    qf[E*NqF^3] = (P x P x P) qc[GlobalToLocal]."""
+    f = _load(f"ellipticPreconProlongateHex3D_F{NqF}_C{NqC}.so").ellipticPartialPreconProlongateHex3D
+    f.restype = None
+    G2L = np.ascontiguousarray(G2L_coarse, dtype=np.int32)
+    E = G2L.size // NqC ** 3
+    el = np.arange(E, dtype=np.int32)
+    P = np.ascontiguousarray(P, dtype=np.float64).reshape(-1)
+    q = np.ascontiguousarray(qc_gathered, dtype=np.float64)
+    out = np.zeros(E * NqF ** 3)
+    n = C.c_int(E)
+    f(C.byref(n), _p(el), _p(G2L), _p(P), _p(q), _p(out))
+    return out
+
+
+def ogs_scatter(rowStarts, colIds, gv, nlocal):
+    """scatter kernel (libs/ogs/okl/ogsKernels.okl:127-164, T = double): v[colIds[g]] = gv[row]"""
+    f = _load("ogsKernels_double_add.so").scatter
+    f.restype = None
+    rs = np.ascontiguousarray(rowStarts, dtype=np.int32)
+    ci = np.ascontiguousarray(colIds, dtype=np.int32)
+    blocks = row_blocks(rs)
+    gv = np.ascontiguousarray(gv, dtype=np.float64)
+    out = np.zeros(nlocal)
+    nb, one = C.c_int(blocks.size - 1), C.c_int(1)
+    f(C.byref(nb), C.byref(one), _p(blocks), _p(rs), _p(ci), _p(gv), _p(out))
+    return out
+
+
+def ogs_gather_scatter(rowStarts, colIds, v):
+    """gatherScatter kernel (libs/ogs/okl/ogsKernels.okl:32-81, T = double, Add), symmetric form: every copy of a
+    node receives the sum over its copies, in place."""
+    f = _load("ogsKernels_double_add.so").gatherScatter
+    f.restype = None
+    rs = np.ascontiguousarray(rowStarts, dtype=np.int32)
+    ci = np.ascontiguousarray(colIds, dtype=np.int32)
+    blocks = row_blocks(rs)
+    v = np.array(v, dtype=np.float64)
+    nb, one = C.c_int(blocks.size - 1), C.c_int(1)
+    f(C.byref(nb), C.byref(one), _p(blocks), _p(rs), _p(ci), _p(rs), _p(ci), _p(v))
+    return v

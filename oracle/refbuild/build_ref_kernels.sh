@@ -35,7 +35,7 @@ for N in ${LIBP_REF_KERNEL_DEGREES-1 2 3 4 5 6 7 8}; do
   grep -q "Solution norm" "$C/run.log" || { cat "$C/run.log"; exit 1; }
   AX=$(grep -l 'extern "C" void ellipticPartialAxHex3D' "$C"/cache/*/source.cpp | head -1)
   cp "$(dirname "$AX")/binary" "$OUT/ellipticAxHex3D_N$N.so"
-  if [ "$N" = "${LIBP_REF_KERNEL_DEGREES:-1}" ] || [ ! -f "$OUT/ogsKernels_double_add.so" ]; then
+  if [ ! -f "$OUT/ogsKernels_double_add.so" ]; then
     GS=$(grep -l 'extern "C" void gatherScatter' "$C"/cache/*/source.cpp | head -1)
     cp "$(dirname "$GS")/binary" "$OUT/ogsKernels_double_add.so"
     UP=$(grep -l 'extern "C" void updatePCG' "$C"/cache/*/source.cpp | head -1)
@@ -45,7 +45,7 @@ for N in ${LIBP_REF_KERNEL_DEGREES-1 2 3 4 5 6 7 8}; do
 done
 # p-multigrid transfer kernels (ellipticPreconCoarsenHex3D.okl / ellipticPreconProlongateHex3D.okl), one binary per
 # (fine, coarse) pair of the HALFDOFS ladders of N = 7 and N = 8: (8,6) (6,4) (4,3) (3,2) and (9,7) (7,5) (5,3)
-for N in ${LIBP_REF_KERNEL_MG_DEGREES:-7 8}; do
+for N in ${LIBP_REF_KERNEL_MG_DEGREES-7 8}; do
   C=$(mktemp -d /tmp/occa_refk.XXXXXX)
   RC="$C/setup.rc"
   {

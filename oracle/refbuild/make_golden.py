@@ -34,6 +34,10 @@ CONFIGS = {
     "hex_n5_e2_jacobi": dict(N=5, n=2, flag=1, lam=1.0, precon="JACOBI", mode="full"),
     "hex_n6_e2_jacobi": dict(N=6, n=2, flag=1, lam=0.7, precon="JACOBI", mode="full"),
     "hex_n8_e2_none": dict(N=8, n=2, flag=1, lam=1.0, precon="NONE", mode="full"),
+    # edge cases: a periodic box of ONE element per direction (every face node collides with its opposite copy inside
+    # the same element) and of two elements (each node pair is shared twice)
+    "hex_n3_e1_periodic": dict(N=3, n=1, flag=-1, lam=1.0, precon="JACOBI", mode="full"),
+    "hex_n2_e2_periodic": dict(N=2, n=2, flag=-1, lam=0.5, precon="NONE", mode="full"),
     "hex_n7_e3_bp5": dict(N=7, n=3, flag=1, lam=0.0, precon="JACOBI", mode="digest"),
     "hex_n4_e10_jacobi": dict(N=4, n=10, flag=1, lam=1.0, precon="JACOBI", mode="digest"),
     "hex_n4_e10_none": dict(N=4, n=10, flag=1, lam=1.0, precon="NONE", mode="digest"),

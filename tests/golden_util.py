@@ -12,6 +12,11 @@ from oracle.ogs_ref import SIGNED, ogs_setup_all
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FULL = ["hex_n3_e3_jacobi", "hex_n7_e2_jacobi", "hex_n2_e4_periodic", "hex_n1_e5_none", "hex_n5_e2_jacobi",
         "hex_n6_e2_jacobi", "hex_n8_e2_none"]
+# Edge cases for the ogs setup: periodic boxes of one / two elements per direction.  The reference's connectivity pass
+# identifies more nodes there than the torus lattice does (an element is its own neighbour), so ids repeat many times
+# inside one element - the mesh producer is not restated for them (out of scope); the reference's own ids are fed to
+# the ogs setup instead (heavy in-element collisions, rows of up to 27 copies).
+EDGE = ["hex_n3_e1_periodic", "hex_n2_e2_periodic"]
 DIGEST = ["hex_n7_e3_bp5", "hex_n4_e10_jacobi", "hex_n4_e10_none"]
 
 

@@ -7,7 +7,7 @@ import re
 import numpy as np
 import pytest
 
-from golden_util import DIGEST, FULL, Problem, load, sha
+from golden_util import DIGEST, EDGE, FULL, Problem, load, sha
 
 import libparanumal_b200 as lp
 from libparanumal_b200 import _lib as L
@@ -71,6 +71,24 @@ def test_ogs_setup_bit_exact_vs_reference(name):
         for nm in ("rowStartsN", "rowStartsT", "colIdsN", "colIdsT"):
             assert np.array_equal(sha(m[nm]), g["gatherLocal_" + nm + "_sha256"]), nm
         assert np.array_equal(sha(g2l), g["GlobalToLocal_sha256"])
+    ogs.Free()
+
+
+@pytest.mark.parametrize("name", EDGE)
+def test_ogs_setup_edge_cases_from_reference_ids(name):
+    """the C-ABI host setup on the reference's own ids of degenerate periodic boxes (many copies of an id inside one
+    element): signs, counters and maps bit-exact against the reference dump"""
+    g = load(name)
+    ids = np.abs(g["maskedGlobalIds"]).astype(np.int64)
+    fresh_rand()
+    ogs = Ogs().Setup(ids.size, ids, Comm(), kind=L.SIGNED, unique=True)
+    cnt = g["ogs_counts"]
+    assert [ogs.N, ogs.Ngather, ogs.NlocalT, ogs.NlocalP, ogs.NhaloT, ogs.NhaloP, ogs.NgatherGlobal] == list(cnt[:7])
+    assert np.array_equal(ids, g["maskedGlobalIds"])
+    m = ogs.maps("local")
+    for nm in ("rowStartsN", "rowStartsT", "colIdsN", "colIdsT"):
+        assert np.array_equal(m[nm], g["gatherLocal_" + nm]), nm
+    assert np.array_equal(ogs.SetupGlobalToLocalMapping(), g["GlobalToLocal"])
     ogs.Free()
 
 

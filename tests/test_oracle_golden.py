@@ -3,7 +3,7 @@ reference (libParanumal built in-container, see oracle/refbuild/).  CPU only."""
 import numpy as np
 import pytest
 
-from golden_util import DIGEST, FULL, Problem, load, relerr, sha
+from golden_util import DIGEST, EDGE, FULL, Problem, load, relerr, sha
 from oracle import elliptic_ref as er
 from oracle.ogs_ref import GlibcRand, libstdcxx_sort_perm
 
@@ -112,3 +112,45 @@ def test_libstdcxx_sort_restatement_is_a_sort():
         perm = libstdcxx_sort_perm(k)
         assert sorted(perm.tolist()) == list(range(n))
         assert np.all(np.diff(k[perm]) >= 0)
+
+
+@pytest.mark.parametrize("name", EDGE)
+def test_ogs_setup_edge_cases_from_reference_ids(name):
+    """ids with many collisions inside one element (degenerate periodic boxes): the oracle's ogs setup on the
+    reference's own ids reproduces the reference's signs, counters and all four local maps bit for bit."""
+    from oracle.ogs_ref import SIGNED, ogs_setup_all
+    g = load(name)
+    ids_in = np.abs(g["maskedGlobalIds"]).astype(np.int64)
+    assert np.bincount(np.unique(ids_in, return_inverse=True)[1]).max() >= 8
+    o = ogs_setup_all([ids_in], SIGNED, True)[0]
+    cnt = g["ogs_counts"]
+    assert [o.N, o.Ngather, o.NlocalT, o.NlocalP, o.NhaloT, o.NhaloP, o.NgatherGlobal] == list(cnt[:7])
+    assert np.array_equal(o.ids, g["maskedGlobalIds"])
+    for nm in ("rowStartsN", "rowStartsT", "colIdsN", "colIdsT"):
+        assert np.array_equal(getattr(o.gatherLocal, nm), g["gatherLocal_" + nm]), nm
+    assert np.array_equal(o.global_to_local(), g["GlobalToLocal"])
+
+
+@pytest.mark.parametrize("name", EDGE)
+def test_operator_pcg_edge_cases_on_reference_arrays(name):
+    """Operator / diagonal / PCG on the degenerate periodic boxes, everything (maps, geometry) taken from the
+    reference dump: rows with many in-element copies, no masked node."""
+    g = load(name)
+    N, n, flag = (int(v) for v in g["config"])
+    Nq, lam = N + 1, float(g["lambda"][0])
+    G2L, rsT, ciT = g["GlobalToLocal"], g["gatherLocal_rowStartsT"], g["gatherLocal_colIdsT"]
+    Ng = len(rsT) - 1
+    q = er.splitmix_uniform(1234, Ng)
+    assert np.array_equal(q, g["q"])
+    Aq = er.operator(Nq, G2L, g["wJ"], g["ggeo"], g["D"], lam, rsT, ciT, q)
+    assert relerr(Aq, g["Aq"]) < 1e-13
+    dg = er.gather_add(rsT, ciT, er.build_diagonal_local(Nq, g["ggeo"], g["wJ"], g["D"], lam, g["mapB"]))
+    assert relerr(dg, g["diagA"]) < 1e-13
+    r = er.gather_add(rsT, ciT, g["rL"])
+    assert relerr(r, g["r"]) < 1e-14
+    inv = None if name == "hex_n2_e2_periodic" else 1.0 / g["diagA"]   # generated with PRECONDITIONER = NONE / JACOBI
+    it, x, hist = er.pcg(Nq, G2L, g["wJ"], g["ggeo"], g["D"], lam, rsT, ciT, inv, np.zeros_like(r), g["r"])
+    assert abs(it - int(g["iterations"][0])) <= 1
+    assert relerr(x, g["xsol"]) < 1e-7
+    k = min(len(hist) - 1, len(g["res_history"]))
+    assert np.allclose(hist[1:k + 1], g["res_history"][:k], rtol=1e-4)

@@ -152,5 +152,7 @@ def test_operator_pcg_edge_cases_on_reference_arrays(name):
     it, x, hist = er.pcg(Nq, G2L, g["wJ"], g["ggeo"], g["D"], lam, rsT, ciT, inv, np.zeros_like(r), g["r"])
     assert abs(it - int(g["iterations"][0])) <= 1
     assert relerr(x, g["xsol"]) < 1e-7
-    k = min(len(hist) - 1, len(g["res_history"]))
-    assert np.allclose(hist[1:k + 1], g["res_history"][:k], rtol=1e-4)
+    # 30 unknowns, 32 iterations: past the exact-arithmetic termination CG is rounding-driven, so only the first
+    # iterations are compared entry by entry
+    k = min(len(hist) - 1, len(g["res_history"]), 10)
+    assert np.allclose(hist[1:k + 1], g["res_history"][:k], rtol=1e-6)

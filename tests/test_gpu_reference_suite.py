@@ -80,3 +80,42 @@ def test_nbpcg_matches_reference(precon, ref_it, ref_hist):
     x2, r2 = p.vec(), p.rhs_sine3d()
     p.pcg().Solve(p.op, M, x2, r2, tol=1e-8, maxit=5000)
     assert float((x[: p.Ndofs] - x2[: p.Ndofs]).abs().max() / x2[: p.Ndofs].abs().max()) < 1e-6
+
+
+# Degenerate periodic boxes (one / two elements per direction): the reference's ids repeat up to 27 times inside one
+# element.  Everything is taken from the reference dump (ids, geometry, D, q): ogs setup through the C ABI, then the
+# operator in both modes (many reductions of one block into the same row) and Jacobi / plain PCG.
+@pytest.mark.parametrize("name,precon", [("hex_n3_e1_periodic", "JACOBI"), ("hex_n2_e2_periodic", "NONE")])
+def test_edge_cases_on_reference_arrays(name, precon):
+    import numpy as np
+    import torch
+
+    from golden_util import load, relerr
+    from libparanumal_b200 import _lib as L
+    from libparanumal_b200.api import Comm, Elliptic, Ogs, Pcg, Precon
+    g = load(name)
+    N = int(g["config"][0])
+    Nq, lam = N + 1, float(g["lambda"][0])
+    ids = np.abs(g["maskedGlobalIds"]).astype(np.int64)
+    libc.srand(1)
+    comm = Comm()
+    ogs = Ogs().Setup(ids.size, ids, comm, kind=L.SIGNED, unique=True)
+    assert np.array_equal(ids, g["maskedGlobalIds"])
+    G2L = ogs.SetupGlobalToLocalMapping()
+    assert np.array_equal(G2L, g["GlobalToLocal"])
+    dev = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a if dt is None else a.astype(dt))).cuda()
+    E = ids.size // Nq ** 3
+    elems = torch.arange(E, dtype=torch.int32, device="cuda")
+    wJ, ggeo, D, dG2L = dev(g["wJ"]), dev(g["ggeo"]), dev(g["D"]), dev(G2L, np.int32)
+    Ng = ogs.Ngather
+    q = dev(g["q"])
+    for mode in (0, 1):
+        op = Elliptic(Nq, elems, None, dG2L, wJ, ggeo, D, lam, ogs, mode=mode)
+        Aq = torch.zeros(Ng + ogs.Nhalo, dtype=torch.float64, device="cuda")
+        op.Operator(q.clone(), Aq)
+        assert relerr(Aq[:Ng].cpu().numpy(), g["Aq"]) < 1e-12, mode
+    M = Precon.Jacobi(Ng, dev(1.0 / g["diagA"])) if precon == "JACOBI" else Precon.Identity(Ng)
+    x = torch.zeros(Ng, dtype=torch.float64, device="cuda")
+    it = Pcg(Ng, 0, comm).Solve(op, M, x, dev(g["r"]), tol=1e-8, maxit=200)
+    assert abs(it - int(g["iterations"][0])) <= 1, (it, g["iterations"])
+    assert relerr(x.cpu().numpy(), g["xsol"]) < 1e-6

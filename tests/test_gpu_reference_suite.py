@@ -23,10 +23,14 @@ CASES = [
     ("ParAlmond_smoothed", "PARALMOND", 1, 1.0, 0.353553400508458, {}, 11),
     ("testEllipticHex_C0_Multigrid", "MULTIGRID", 1, 1.0, 0.353553400508458, dict(aggregation="UNSMOOTHED"), 6),
     ("Multigrid_defaults", "MULTIGRID", 1, 1.0, 0.353553400508458, {}, 6),
-    # periodic box, lambda = 0: singular operator, ZeroMean + rank-one coarse boost (default precon MULTIGRID).
-    # test/testElliptic.py:244-248 lists 0.059540839002614; the unmodified reference built in this container
-    # prints 0.058046029189514 (5 iterations) for these settings, which is the value pinned here.
-    ("testEllipticHex_C0_AllNeumann", "MULTIGRID", -1, 0.0, 0.058046029189514, dict(aggregation="UNSMOOTHED"), 5),
+    # test/testElliptic.py:244-248: periodic box (flag -1).  ellipticSettings() accepts Lambda=0.0 but never emits a
+    # LAMBDA key (test/testElliptic.py:33-73), so the reference test really runs lambda = 1 (the default,
+    # ellipticSettings.cpp): a non-singular periodic screened-Poisson problem.  Listed norm 0.059540839002614; the
+    # unmodified reference built in this container prints 0.0595408388714726 in 5 iterations.
+    ("testEllipticHex_C0_AllNeumann", "MULTIGRID", -1, 1.0, 0.059540839002614, dict(aggregation="UNSMOOTHED"), 5),
+    # extra (not a reference test): the same rc file with LAMBDA = 0.0 added, i.e. the truly singular all-Neumann
+    # operator: ZeroMean + rank-one coarse boost.  The reference prints 0.058046029189514 (5 iterations) for it.
+    ("AllNeumann_lambda0", "MULTIGRID", -1, 0.0, 0.058046029189514, dict(aggregation="UNSMOOTHED"), 5),
 ]
 
 

@@ -219,11 +219,25 @@ int libp_elliptic_free(libp_elliptic_t op);
 int libp_elliptic_set_zero_ahead(libp_elliptic_t op, int on);
 int libp_elliptic_set_default_zero_ahead(int on);
 int libp_elliptic_zero_ahead_errors(libp_elliptic_t op, int* errors);
+/* Fused mode, GLL derivative matrix (tuning of this implementation, no reference counterpart): the element-chain
+ * kernel (csrc/ax_chain.cu).  One CTA walks `chainElements` consecutive elements of a launch segment of
+ * elliptic_t::Operator (ellipticOperator.cpp:40-104); geometric factors arrive in shared memory by bulk-async copies
+ * (TMA), rows of o_Aq touched by a single chain are written with plain stores and never zero-filled, connectivity is
+ * run-length compressed.  0 = off (ax_hex3d_t_kernel).  `stages` = geometric-factor blocks in flight per CTA (2 or 3).
+ * Needs o_Aq 32-byte aligned and ggeo / wJ 16-byte aligned; other pointers take the previous kernel.
+ * libp_elliptic_chain_stats: {chainElements, sectors, sectors still zero-filled, positions, uncompressed elements,
+ * stages} of the plan derived from GlobalToLocal for this handle (zeros when the chain kernel is not in use). */
+int libp_elliptic_set_chain(libp_elliptic_t op, int chainElements, int stages);
+int libp_elliptic_set_default_chain(int chainElements, int stages);
+int libp_elliptic_chain_stats(libp_elliptic_t op, libp_dfloat* Aq, long long* stats, void* stream);
 int libp_elliptic_set_chunk(libp_elliptic_t op, libp_dlong chunkElements);
 int libp_elliptic_set_default_chunk(libp_dlong chunkElements);
 /* o_q and o_Aq are gathered vectors of Ndofs+Nhalo entries; the Nhalo tail of o_q is
  * overwritten by the halo exchange exactly like the reference.         */
 int libp_elliptic_operator(libp_elliptic_t op, libp_dfloat* q, libp_dfloat* Aq, void* stream);
+/* The same apply with CUDA events recorded on `stream` around its two parts (measurement aid for the roofline line
+ * of bench.py): ms[0] = zero-fill of the accumulator, ms[1] = halo exchange + Ax launches + combine.  Synchronises. */
+int libp_elliptic_operator_timed(libp_elliptic_t op, libp_dfloat* q, libp_dfloat* Aq, void* stream, double* ms);
 
 /* ------------------------------------------------------------------ elliptic_t::Run pre/post steps (Hex3D, C0)
  * solvers/elliptic/src/ellipticRun.cpp:139-246.  The reference JIT-inlines the user's data file (forcing and

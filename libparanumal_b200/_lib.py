@@ -106,10 +106,14 @@ SIGNATURES = {
     "libp_elliptic_set_zero_ahead": (i32, [vp, i32]),
     "libp_elliptic_set_default_zero_ahead": (i32, [i32]),
     "libp_elliptic_zero_ahead_errors": (i32, [vp, P(i32)]),
+    "libp_elliptic_set_chain": (i32, [vp, i32, i32]),
+    "libp_elliptic_set_default_chain": (i32, [i32, i32]),
+    "libp_elliptic_chain_stats": (i32, [vp, vp, P(C.c_longlong), vp]),
     "libp_elliptic_set_chunk": (i32, [vp, i32]),
     "libp_elliptic_set_default_chunk": (i32, [i32]),
     "libp_elliptic_free": (i32, [vp]),
     "libp_elliptic_operator": (i32, [vp, vp, vp, vp]),
+    "libp_elliptic_operator_timed": (i32, [vp, vp, vp, vp, P(f64)]),
     "libp_linalg_set": (i32, [i32, f64, vp, vp]),
     "libp_linalg_add": (i32, [i32, f64, vp, vp]),
     "libp_linalg_scale": (i32, [i32, f64, vp, vp]),

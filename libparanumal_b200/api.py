@@ -384,12 +384,27 @@ class Elliptic:
         check(L.load().libp_elliptic_zero_ahead_errors(self._h, C.byref(e)))
         return e.value
 
+    def set_chain(self, chain_elements, stages=2):
+        """element-chain kernel: elements per chain (0 = off), TMA stages; see libp_elliptic_set_chain"""
+        check(L.load().libp_elliptic_set_chain(self._h, int(chain_elements), int(stages)))
+
+    def chain_stats(self, o_Aq):
+        st = (C.c_longlong * 6)()
+        check(L.load().libp_elliptic_chain_stats(self._h, _ptr(o_Aq), st, _stream()))
+        return dict(chain=st[0], sectors=st[1], zero_sectors=st[2], positions=st[3], raw_elements=st[4], stages=st[5])
+
     def set_chunk(self, chunk_elements):
         """elements per zero-fill piece of the fused operator (0 = off); see libp_elliptic_set_chunk"""
         check(L.load().libp_elliptic_set_chunk(self._h, int(chunk_elements)))
 
     def Operator(self, o_q, o_Aq):
         check(L.load().libp_elliptic_operator(self._h, _ptr(o_q), _ptr(o_Aq), _stream()))
+
+    def OperatorTimed(self, o_q, o_Aq):
+        """one apply with device timing of its parts: (ms zero-fill, ms exchange + Ax launches + combine)"""
+        ms = (C.c_double * 2)()
+        check(L.load().libp_elliptic_operator_timed(self._h, _ptr(o_q), _ptr(o_Aq), _stream(), ms))
+        return ms[0], ms[1]
 
     def Free(self):
         if self._h:

@@ -1,0 +1,687 @@
+// Fused operator kernel, "element chain" variant (mode 1 of elliptic_t::Operator, GLL D):
+//   Aq[GlobalToLocal] (+)= A_e q[GlobalToLocal]     for the elements of one launch segment
+// replacing ellipticPartialAxHex3D + ogs Gather(Add, Trans) (solvers/elliptic/okl/ellipticAxHex3D.okl:156-295,
+// libs/ogs/ogs.cpp:203-298) like ax_hex3d_t_kernel does, with three changes that cut DRAM traffic and raise the bytes
+// in flight:
+//
+//  1. Bulk-async geometric factors.  A CTA walks a CHAIN of L consecutive elements of the segment.  The contiguous
+//     [6 (+1)][Np] block of geometric factors (+ wJ) of element n+1 is copied into shared memory by the TMA unit
+//     (cp.async.bulk + mbarrier complete_tx, L2 evict-first) while element n is computed: no registers hold loads in
+//     flight, 25-29 KB per CTA are always in flight.
+//  2. Owner-computes accumulation.  A row of the gathered vector that is only touched by nodes of ONE chain
+//     ("chain-private") needs no atomics across CTAs and no zero-fill: its first touch (in program order of the
+//     chain) is a plain store, later touches by the same CTA are reductions that follow it in program order (bar.sync
+//     orders them).  This is applied at the granularity of 32-byte DRAM sectors (4 rows): a sector whose 4 rows are
+//     all chain-private is never zero-filled and never read for ownership; every other sector is zero-filled by
+//     ax_chain_zero_fill() (bit mask) and accumulated with red.global.add as before.
+//  3. Compressed connectivity.  Along i the ids of an element line are almost always [x, b, b+1, ..., b+Nq-2]
+//     (first-appearance numbering of ogsBase_t::Setup, libs/ogs/ogsSetup.cpp:411-433): such elements store 2 ids per
+//     line instead of Nq.  Other elements (Dirichlet faces, rank-shared rows) read the caller's GlobalToLocal.
+//
+// The classification is derived from GlobalToLocal alone by the plan kernels below (no assumption on the mesh).
+// Layout C / A / B = the three pencil orientations of ax_hex3d.cu; contractions run on register pencils with the
+// even-odd factors of D passed as a __grid_constant__ kernel parameter (no global constant state).
+#include <algorithm>
+#include <climits>
+#include <cstdint>
+
+#include "ax_chain.hpp"
+
+using namespace libp_b200;
+
+namespace {
+
+constexpr int kMaxNq = 9, kMaxH = kMaxNq / 2;
+
+// even-odd factors of a centro-antisymmetric D (see ax_hex3d.cu)
+struct EoD {
+  double De[kMaxH * kMaxH], Do[kMaxH * kMaxH], Dc[kMaxH], Dr[kMaxH];
+};
+
+template <int Nq, bool kT>
+__device__ __forceinline__ void eo_apply(const EoD& c, const dfloat (&v)[Nq], dfloat (&o)[Nq]) {
+  constexpr int H = Nq / 2, N = Nq - 1;
+  dfloat ve[H > 0 ? H : 1], vo[H > 0 ? H : 1];
+#pragma unroll
+  for (int m = 0; m < H; ++m) { ve[m] = v[m] + v[N - m]; vo[m] = v[m] - v[N - m]; }
+#pragma unroll
+  for (int i = 0; i < H; ++i) {
+    dfloat E = 0.0, O = 0.0;
+    if (Nq & 1) E = (kT ? c.Dr[i] : c.Dc[i]) * v[H];
+#pragma unroll
+    for (int m = 0; m < H; ++m) {
+      E += (kT ? c.Do[m * H + i] : c.De[i * H + m]) * ve[m];
+      O += (kT ? c.De[m * H + i] : c.Do[i * H + m]) * vo[m];
+    }
+    o[i] = E + O;
+    o[N - i] = O - E;
+  }
+  if (Nq & 1) {
+    dfloat s = 0.0;
+#pragma unroll
+    for (int m = 0; m < H; ++m) s += (kT ? c.Dc[m] : c.Dr[m]) * vo[m];
+    o[H] = s;
+  }
+}
+
+// ---- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t pol_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t pol_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+// global -> shared bulk copy by the TMA unit; completion is counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ dfloat ld_keep(const dfloat* p, uint64_t pol) {
+  dfloat v;
+  asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int ld_stream_i(const int* p, uint64_t pol) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ unsigned ld_stream_u16(const uint16_t* p, uint64_t pol) {
+  unsigned short v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_keep(dfloat* p, dfloat v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_keep(dfloat* p, dfloat v, uint64_t pol) {
+  asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+
+template <int Nq>
+__device__ __forceinline__ void load_row(const dfloat* __restrict__ row, dfloat (&v)[Nq]) {
+#pragma unroll
+  for (int c = 0; c < Nq / 2; ++c) {
+    const double2 w = *reinterpret_cast<const double2*>(row + 2 * c);
+    v[2 * c] = w.x; v[2 * c + 1] = w.y;
+  }
+  if (Nq & 1) v[Nq - 1] = row[Nq - 1];
+}
+template <int Nq>
+__device__ __forceinline__ void store_row(dfloat* __restrict__ row, const dfloat (&o)[Nq]) {
+#pragma unroll
+  for (int c = 0; c < Nq / 2; ++c) *reinterpret_cast<double2*>(row + 2 * c) = make_double2(o[2 * c], o[2 * c + 1]);
+  if (Nq & 1) row[Nq - 1] = o[Nq - 1];
+}
+
+// Shared-memory geometry of the staging arrays.  Nq = 8: dense rows (LD = 8), slab stride 66; with layout C on
+// natural (j, j+1) half-warps, layout A on (k = a, j = b) and layout B on (i = a, k = 4(b&1) + b/2) all three
+// access patterns AND the dense TMA-written geometric factors are bank-conflict free.  Other orders: strides of
+// ax_hex3d.cu (tools/smem_layout_search.py).
+template <int Nq>
+struct ChT {
+  static constexpr int Nq2 = Nq * Nq, Np = Nq * Nq * Nq;
+  static constexpr int EPB = (Nq == 2) ? 16 : (Nq == 3) ? 7 : (Nq == 4) ? 4 : (Nq == 5) ? 5 : (Nq == 6) ? 5
+                           : (Nq == 7) ? 2 : 1;
+  static constexpr int Work = EPB * Nq2;
+  static constexpr int Threads = ((Work + 31) / 32) * 32;
+  static constexpr int LD = (Nq == 8) ? 8 : (Nq == 2) ? 2 : (Nq <= 4) ? 4 : (Nq <= 6) ? 6 : 10;
+  static constexpr int SS = (Nq == 8) ? 66 : (Nq == 2) ? 4 : (Nq == 3) ? 12 : (Nq == 4) ? 18 : (Nq == 5) ? 30
+                          : (Nq == 6) ? 38 : (Nq == 7) ? 70 : 90;
+  static constexpr int ESS = (Nq == 8) ? 8 * 66 : (Nq == 2) ? 10 : (Nq == 3) ? 42 : (Nq == 4) ? 72 : (Nq == 5) ? 150
+                           : (Nq == 6) ? 228 : (Nq == 7) ? 496 : Nq * SS;
+  static constexpr int NG = 7;  // components per stage: 6 geometric factors + wJ (only copied when lambda != 0)
+  // wJ can only ride the bulk copy when its per-element block keeps 16-byte alignment
+  static constexpr bool kBulkWJ = (Np % 2 == 0);
+  static constexpr int StageDoubles = EPB * NG * Np + ((EPB * NG * Np) & 1);  // keep stages 16-byte aligned
+};
+
+template <int Nq, int S>
+constexpr size_t chain_smem_bytes() {
+  using C = ChT<Nq>;
+  return (size_t)8 * (S * C::StageDoubles + 3 * C::EPB * C::ESS) + 8 * S + 16;
+}
+
+struct ChainArgs {
+  const int* hdr;         // [nPos]  (element << 1) | raw, -1 = padding
+  const int* cid;         // [nPos][2 * Nq2] compressed ids: [k*Nq + j] = id of node i=0, [Nq2 + k*Nq + j] = id of node i=1
+  const uint16_t* flags;  // [nPos][Nq2]  column (j*Nq + i): bit k set = plain store (first touch of a private row)
+  const dlong* G2L;
+  const dfloat* wJ;
+  const dfloat* ggeo;
+  const dfloat* q;
+  dfloat* Aq;
+  dfloat* dotPartials;
+  const int* doneFlag;
+  dfloat lambda;
+  int nChains, L;
+  dlong count;  // elements of the segment (the last chain may be shorter than L)
+};
+
+template <int Nq, int S, bool kDot, int kMinB>
+__global__ void __launch_bounds__(ChT<Nq>::Threads, kMinB)
+ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
+  if (A.doneFlag != nullptr && *A.doneFlag) return;
+  using C = ChT<Nq>;
+  constexpr int Nq2 = C::Nq2, Np = C::Np, LD = C::LD, SS = C::SS, ESS = C::ESS, EPB = C::EPB;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  dfloat* s_g = reinterpret_cast<dfloat*>(smem_raw);                    // [S][EPB][NG][Np]
+  dfloat* s_u = s_g + S * C::StageDoubles;
+  dfloat* s_r = s_u + EPB * ESS;
+  dfloat* s_s = s_r + EPB * ESS;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_s + EPB * ESS);       // [S]
+
+  const int t = threadIdx.x;
+  const bool valid = t < C::Work;
+  const int es = valid ? t / Nq2 : 0;
+  const int ij = valid ? t - es * Nq2 : 0;
+  const int b = ij / Nq, a = ij - b * Nq;
+  const int nC = ij;                               // layout C: i = a, j = b (natural)
+  const int sC = es * ESS + b * LD + a;
+  // layout A: i-pencil (row); layout B: j-pencil (column)
+  const int kA = (Nq == 8) ? a : b, jA = (Nq == 8) ? b : a;
+  const int sA = es * ESS + kA * SS + jA * LD;
+  const int kB = (Nq == 8) ? (4 * (b & 1) + (b >> 1)) : b;
+  const int sB = es * ESS + kB * SS + a;
+
+  const bool screened = (A.lambda != 0.0);
+  const bool bulkW = screened && C::kBulkWJ;
+  const uint64_t polS = pol_evict_first(), polK = pol_evict_last();
+  const int chain = blockIdx.x * EPB + es;         // one chain per element slot
+  const bool chainOK = valid && chain < A.nChains;
+  const size_t p0 = (size_t)chain * A.L;
+  const int L = A.L;
+
+  if (t == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(smem_u32(&s_bar[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // element header of step n of this slot's chain (-1: nothing to do)
+  auto header = [&](int n) -> int { return (chainOK && n < L) ? __ldg(A.hdr + p0 + n) : -1; };
+  // thread 0 arms stage (n % S) and issues the copies of step n for every slot of the block
+  auto issue = [&](int n) {
+    const uint32_t bar = smem_u32(&s_bar[n % S]);
+    uint32_t bytes = 0;
+    int e_slot[EPB];
+#pragma unroll
+    for (int x = 0; x < EPB; ++x) {
+      const int ch = blockIdx.x * EPB + x;
+      int h = -1;
+      if (ch < A.nChains && n < L) h = __ldg(A.hdr + (size_t)ch * L + n);
+      e_slot[x] = (h >= 0) ? (h >> 1) : -1;
+      if (h >= 0) bytes += (uint32_t)(8 * Np * (bulkW ? 7 : 6));
+    }
+    if (bytes == 0) return;
+    mbar_expect_tx(bar, bytes);
+#pragma unroll
+    for (int x = 0; x < EPB; ++x) {
+      if (e_slot[x] < 0) continue;
+      dfloat* dst = s_g + (n % S) * C::StageDoubles + x * C::NG * Np;
+      bulk_g2s(smem_u32(dst), A.ggeo + (size_t)e_slot[x] * 6 * Np, 8 * 6 * Np, bar, polS);
+      if (bulkW) bulk_g2s(smem_u32(dst + 6 * Np), A.wJ + (size_t)e_slot[x] * Np, 8 * Np, bar, polS);
+    }
+  };
+  if (t == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) issue(s);
+  }
+
+  // connectivity of step n: ids of this thread's k-pencil + store/reduce flags
+  auto load_ids = [&](int n, int h, dlong (&id)[Nq], unsigned& fl) {
+    if (h < 0) {
+#pragma unroll
+      for (int k = 0; k < Nq; ++k) id[k] = -1;
+      fl = 0;
+      return;
+    }
+    const size_t p = p0 + n;
+    fl = ld_stream_u16(A.flags + p * Nq2 + ij, polS);
+    if (h & 1) {
+      const dlong* g = A.G2L + (size_t)(h >> 1) * Np + nC;
+#pragma unroll
+      for (int k = 0; k < Nq; ++k) id[k] = ld_stream_i(g + k * Nq2, polS);
+    } else {
+      const int* c = A.cid + p * (2 * Nq2) + (a == 0 ? 0 : Nq2) + b;
+#pragma unroll
+      for (int k = 0; k < Nq; ++k) {
+        const int v = ld_stream_i(c + k * Nq, polS);
+        id[k] = (a == 0 || v < 0) ? v : v + (a - 1);
+      }
+    }
+  };
+  auto gather_q = [&](const dlong (&id)[Nq], dfloat (&u)[Nq]) {
+#pragma unroll
+    for (int k = 0; k < Nq; ++k) u[k] = (id[k] >= 0) ? ld_keep(A.q + id[k], polK) : 0.0;
+  };
+
+  // software pipeline: ids two steps ahead, q one step ahead, geometric factors S steps ahead (TMA)
+  int h_cur = header(0), h_nxt = header(1), h_nn = header(2);
+  dlong id_cur[Nq], id_nxt[Nq];
+  unsigned fl_cur, fl_nxt;
+  dfloat q_cur[Nq];
+  load_ids(0, h_cur, id_cur, fl_cur);
+  load_ids(1, h_nxt, id_nxt, fl_nxt);
+  gather_q(id_cur, q_cur);
+  dfloat dacc = 0.0;
+
+  // block-uniform trip count: the first slot owns the longest chain of the block (only the last chain is short)
+  const long long left = (long long)A.count - (long long)blockIdx.x * EPB * L;
+  const int nsteps = (int)(left < (long long)L ? (left < 0 ? 0 : left) : (long long)L);
+  for (int n = 0; n < nsteps; ++n) {
+    const bool active = h_cur >= 0;
+    const dfloat* __restrict__ sg = s_g + (n % S) * C::StageDoubles + es * C::NG * Np + nC;
+
+    // ---- prefetch: q of step n+1, ids of step n+2
+    dfloat q_nxt[Nq];
+    gather_q(id_nxt, q_nxt);
+    dlong id_nn[Nq];
+    unsigned fl_nn;
+    load_ids(n + 2, h_nn, id_nn, fl_nn);
+    const int h_nnn = header(n + 3);
+    dfloat r_w[Nq];
+    if (screened && !C::kBulkWJ) {
+#pragma unroll
+      for (int k = 0; k < Nq; ++k) r_w[k] = active ? __ldg(A.wJ + (size_t)(h_cur >> 1) * Np + nC + k * Nq2) : 0.0;
+    }
+
+    // ---- phase 0 (layout C): publish u, t-derivative in registers
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < Nq; ++k) s_u[sC + k * SS] = q_cur[k];
+    }
+    dfloat r_t[Nq];
+    eo_apply<Nq, false>(eo, q_cur, r_t);
+    __syncthreads();
+
+    // ---- phase 1: r-derivative on i-pencils (layout A), s-derivative on j-pencils (layout B)
+    if (valid) {
+      dfloat v[Nq], o[Nq];
+      load_row<Nq>(&s_u[sA], v);
+      eo_apply<Nq, false>(eo, v, o);
+      store_row<Nq>(&s_r[sA], o);
+#pragma unroll
+      for (int m = 0; m < Nq; ++m) v[m] = s_u[sB + m * LD];
+      eo_apply<Nq, false>(eo, v, o);
+#pragma unroll
+      for (int j = 0; j < Nq; ++j) s_s[sB + j * LD] = o[j];
+    }
+    __syncthreads();
+
+    // ---- phase 2 (layout C): geometric factors from the TMA-filled stage
+    mbar_wait(smem_u32(&s_bar[n % S]), (uint32_t)((n / S) & 1));
+    dfloat r_Aq[Nq];
+#pragma unroll
+    for (int k = 0; k < Nq; ++k) {
+      const dfloat qr = s_r[sC + k * SS], qs = s_s[sC + k * SS], qt = r_t[k];
+      dfloat G00 = 0, G01 = 0, G02 = 0, G11 = 0, G12 = 0, G22 = 0, GwJ = 0;
+      if (active) {
+        G00 = sg[0 * Np + k * Nq2]; G01 = sg[1 * Np + k * Nq2]; G02 = sg[2 * Np + k * Nq2];
+        G11 = sg[3 * Np + k * Nq2]; G12 = sg[4 * Np + k * Nq2]; G22 = sg[5 * Np + k * Nq2];
+        if (screened) GwJ = C::kBulkWJ ? sg[6 * Np + k * Nq2] : r_w[k];
+      }
+      if (valid) {
+        s_r[sC + k * SS] = G00 * qr + G01 * qs + G02 * qt;
+        s_s[sC + k * SS] = G01 * qr + G11 * qs + G12 * qt;
+      }
+      r_t[k] = G02 * qr + G12 * qs + G22 * qt;
+      r_Aq[k] = screened ? GwJ * A.lambda * q_cur[k] : 0.0;
+    }
+    {
+      dfloat o[Nq];
+      eo_apply<Nq, true>(eo, r_t, o);
+#pragma unroll
+      for (int k = 0; k < Nq; ++k) r_Aq[k] += o[k];
+    }
+    __syncthreads();  // the stage has been consumed by every thread; Gq* published
+    if (t == 0) issue(n + S);
+
+    // ---- phase 3: transposed derivatives, in place
+    if (valid) {
+      dfloat v[Nq], o[Nq];
+      load_row<Nq>(&s_r[sA], v);
+      eo_apply<Nq, true>(eo, v, o);
+      store_row<Nq>(&s_r[sA], o);
+#pragma unroll
+      for (int m = 0; m < Nq; ++m) v[m] = s_s[sB + m * LD];
+      eo_apply<Nq, true>(eo, v, o);
+#pragma unroll
+      for (int j = 0; j < Nq; ++j) s_s[sB + j * LD] = o[j];
+    }
+    __syncthreads();
+
+    // ---- phase 4 (layout C): collect, p.Ap partial, plain store (first touch of a private row) or reduction
+#pragma unroll
+    for (int k = 0; k < Nq; ++k) r_Aq[k] += s_r[sC + k * SS] + s_s[sC + k * SS];
+    if (kDot && active) {
+#pragma unroll
+      for (int k = 0; k < Nq; ++k) dacc += q_cur[k] * r_Aq[k];
+    }
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < Nq; ++k) {
+        if (id_cur[k] >= 0) {
+          if ((fl_cur >> k) & 1u) st_keep(A.Aq + id_cur[k], r_Aq[k], polK);
+          else red_keep(A.Aq + id_cur[k], r_Aq[k], polK);
+        }
+      }
+    }
+    // rotate the pipeline registers
+    h_cur = h_nxt; h_nxt = h_nn; h_nn = h_nnn;
+    fl_cur = fl_nxt; fl_nxt = fl_nn;
+#pragma unroll
+    for (int k = 0; k < Nq; ++k) { id_cur[k] = id_nxt[k]; id_nxt[k] = id_nn[k]; q_cur[k] = q_nxt[k]; }
+  }
+
+  if (kDot) {
+    dfloat d = dacc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_down_sync(0xffffffffu, d, o);
+    __shared__ dfloat s_dot[C::Threads / 32];
+    if ((t & 31) == 0) s_dot[t >> 5] = d;
+    __syncthreads();
+    if (t == 0) {
+      dfloat tot = 0.0;
+#pragma unroll
+      for (int w = 0; w < C::Threads / 32; ++w) tot += s_dot[w];
+      A.dotPartials[blockIdx.x] = tot;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ plan kernels
+// position p of the concatenated, chain-padded element sequence -> element (or -1)
+__global__ void __launch_bounds__(256) plan_touch_kernel(size_t nPos, int Np, const int* __restrict__ elem,
+                                                         const dlong* __restrict__ G2L, dlong NlocalT,
+                                                         int* __restrict__ firstPos, int* __restrict__ lastPos) {
+  const size_t total = nPos * (size_t)Np;
+  for (size_t x = (size_t)blockIdx.x * 256 + threadIdx.x; x < total; x += (size_t)gridDim.x * 256) {
+    const size_t p = x / Np;
+    const int e = elem[p];
+    if (e < 0) continue;
+    const dlong id = G2L[(size_t)e * Np + (x - p * Np)];
+    if (id < 0 || id >= NlocalT) continue;
+    atomicMin(&firstPos[id], (int)p);
+    atomicMax(&lastPos[id], (int)p);
+  }
+}
+__global__ void __launch_bounds__(256) plan_count_kernel(size_t nPos, int Np, const int* __restrict__ elem,
+                                                         const dlong* __restrict__ G2L, dlong NlocalT,
+                                                         const int* __restrict__ firstPos, int* __restrict__ cnt) {
+  const size_t total = nPos * (size_t)Np;
+  for (size_t x = (size_t)blockIdx.x * 256 + threadIdx.x; x < total; x += (size_t)gridDim.x * 256) {
+    const size_t p = x / Np;
+    const int e = elem[p];
+    if (e < 0) continue;
+    const dlong id = G2L[(size_t)e * Np + (x - p * Np)];
+    if (id < 0 || id >= NlocalT) continue;
+    if (firstPos[id] == (int)p) atomicAdd(&cnt[id], 1);
+  }
+}
+// one thread per 32 sectors: bit = 1 -> the sector (4 rows) must be zero-filled before the operator runs
+__global__ void __launch_bounds__(256) plan_sector_kernel(size_t nWords, dlong nRows, dlong NlocalT, int L,
+                                                          const int* __restrict__ firstPos,
+                                                          const int* __restrict__ lastPos, const int* __restrict__ cnt,
+                                                          uint32_t* __restrict__ zmask) {
+  const size_t w = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (w >= nWords) return;
+  uint32_t bits = 0;
+  for (int s = 0; s < 32; ++s) {
+    const size_t r0 = (w * 32 + s) * 4;
+    if (r0 >= (size_t)nRows) break;
+    bool clean = true;
+    for (int r = 0; r < 4; ++r) {
+      const size_t row = r0 + r;
+      if (row >= (size_t)nRows || row >= (size_t)NlocalT) { clean = false; break; }
+      const int f = firstPos[row], l = lastPos[row];
+      if (l < 0 || f / L != l / L || cnt[row] != 1) { clean = false; break; }
+    }
+    if (!clean) bits |= (1u << s);
+  }
+  zmask[w] = bits;
+}
+// one block per position: store/reduce flags, compressed ids, header
+__global__ void plan_element_kernel(int Nq, const int* __restrict__ elem, const dlong* __restrict__ G2L, dlong NlocalT,
+                                    const int* __restrict__ firstPos, const uint32_t* __restrict__ zmask,
+                                    int* __restrict__ hdr, int* __restrict__ cid, uint16_t* __restrict__ flags) {
+  const size_t p = blockIdx.x;
+  const int Nq2 = Nq * Nq, Np = Nq2 * Nq;
+  const int e = elem[p];
+  const int t = threadIdx.x;  // Nq2 threads
+  if (e < 0) {
+    if (t == 0) hdr[p] = -1;
+    if (t < Nq2) { flags[p * Nq2 + t] = 0; cid[p * 2 * Nq2 + t] = -1; cid[p * 2 * Nq2 + Nq2 + t] = -1; }
+    return;
+  }
+  const dlong* g = G2L + (size_t)e * Np;
+  int ok = 1;
+  if (t < Nq2) {
+    // as a column (j*Nq + i = t): flags over k
+    unsigned f = 0;
+    for (int k = 0; k < Nq; ++k) {
+      const dlong id = g[k * Nq2 + t];
+      if (id >= 0 && id < NlocalT && firstPos[id] == (int)p) {
+        const size_t sec = (size_t)id >> 2;
+        if (!((zmask[sec >> 5] >> (sec & 31)) & 1u)) f |= (1u << k);
+      }
+    }
+    flags[p * Nq2 + t] = (uint16_t)f;
+    // as a line (k*Nq + j = t): is it [x, b, b+1, ...] or [x, -1, -1, ...]?
+    const dlong* ln = g + (size_t)t * Nq;
+    const dlong id1 = ln[1];
+    for (int i = 2; i < Nq; ++i) {
+      const dlong want = (id1 < 0) ? -1 : id1 + (i - 1);
+      if (ln[i] != want) ok = 0;
+    }
+    cid[p * 2 * Nq2 + t] = ln[0];
+    cid[p * 2 * Nq2 + Nq2 + t] = id1;
+  }
+  ok = __syncthreads_and(ok);
+  if (t == 0) hdr[p] = (e << 1) | (ok ? 0 : 1);
+}
+__global__ void __launch_bounds__(256) plan_fill_elem_kernel(size_t nPos, int L, const dlong* __restrict__ list,
+                                                             dlong first, dlong count, int* __restrict__ elem) {
+  // positions of one segment: chains of L consecutive list entries, the last chain padded with -1
+  const size_t p = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (p >= nPos) return;
+  elem[p] = (p < (size_t)count) ? (list ? list[first + p] : (dlong)(first + p)) : -1;
+}
+__global__ void __launch_bounds__(256) plan_stats_kernel(size_t nWords, size_t nSectors, const uint32_t* __restrict__ zmask,
+                                                         unsigned long long* __restrict__ out) {
+  size_t w = (size_t)blockIdx.x * 256 + threadIdx.x;
+  unsigned c = 0;
+  if (w < nWords) {
+    uint32_t m = zmask[w];
+    if ((w + 1) * 32 > nSectors) m &= (nSectors - w * 32 >= 32) ? 0xffffffffu : ((1u << (nSectors - w * 32)) - 1u);
+    c = __popc(m);
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+__global__ void __launch_bounds__(256) plan_count_raw_kernel(size_t nPos, const int* __restrict__ hdr,
+                                                             unsigned long long* __restrict__ out) {
+  size_t p = (size_t)blockIdx.x * 256 + threadIdx.x;
+  unsigned c = (p < nPos && hdr[p] >= 0 && (hdr[p] & 1)) ? 1u : 0u;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
+// zero-fill of the sectors the plan marks (4 rows = 32 bytes each); one thread per sector
+__global__ void __launch_bounds__(256) zero_fill_kernel(size_t nSectors, dlong nRows, const uint32_t* __restrict__ zmask,
+                                                        dfloat* __restrict__ Aq, const int* __restrict__ doneFlag) {
+  if (doneFlag != nullptr && *doneFlag) return;
+  for (size_t s = (size_t)blockIdx.x * 256 + threadIdx.x; s < nSectors; s += (size_t)gridDim.x * 256) {
+    if (!((zmask[s >> 5] >> (s & 31)) & 1u)) continue;
+    const size_t r0 = s * 4;
+    if (r0 + 4 <= (size_t)nRows) {
+      double2* d = reinterpret_cast<double2*>(Aq + r0);
+      d[0] = make_double2(0.0, 0.0);
+      d[1] = make_double2(0.0, 0.0);
+    } else {
+      for (size_t r = r0; r < (size_t)nRows; ++r) Aq[r] = 0.0;
+    }
+  }
+}
+
+int grid_for(size_t n) { return (int)std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 32); }
+
+template <int Nq, int S, bool kDot>
+void launch_chain_t(const ChainArgs& A, const EoD& eo, cudaStream_t s) {
+  using C = ChT<Nq>;
+  constexpr size_t smem = chain_smem_bytes<Nq, S>();
+  // resident blocks by shared memory (227 KB per SM, 1 KB reserved per block)
+  constexpr int fit = (int)(232448 / (smem + 1024));
+  constexpr int cap = (512 + C::Threads - 1) / C::Threads;  // ~512 threads per SM keeps >= 128 registers per thread
+  constexpr int minb = fit < 1 ? 1 : (fit > cap ? cap : fit);
+  auto kern = ax_hex3d_chain_kernel<Nq, S, kDot, minb>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int grid = (A.nChains + C::EPB - 1) / C::EPB;
+  kern<<<grid, C::Threads, smem, s>>>(A, eo);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+template <int Nq>
+int launch_chain(const ChainArgs& A, const EoD& eo, int stages, cudaStream_t s) {
+  using C = ChT<Nq>;
+  if (A.dotPartials) {
+    if (stages == 3) launch_chain_t<Nq, 3, true>(A, eo, s); else launch_chain_t<Nq, 2, true>(A, eo, s);
+  } else {
+    if (stages == 3) launch_chain_t<Nq, 3, false>(A, eo, s); else launch_chain_t<Nq, 2, false>(A, eo, s);
+  }
+  return (A.nChains + C::EPB - 1) / C::EPB;
+}
+
+}  // namespace
+
+namespace libp_b200 {
+
+int ax_chain_blocks(int Nq, dlong count, int L) {
+  if (count <= 0) return 0;
+  const int chains = (int)((count + L - 1) / L);
+  static const int epb[10] = {1, 1, ChT<2>::EPB, ChT<3>::EPB, ChT<4>::EPB, ChT<5>::EPB, ChT<6>::EPB, ChT<7>::EPB,
+                              ChT<8>::EPB, ChT<9>::EPB};
+  return (chains + epb[Nq] - 1) / epb[Nq];
+}
+
+void AxChainPlan::build(int Nq_, const dfloat* D_host, dlong nRows_, dlong NlocalT, const dlong* G2L, int L_,
+                        const AxChainSegDesc (&sd)[3], cudaStream_t s) {
+  Nq = Nq_; L = L_; nRows = nRows_;
+  const int Nq2 = Nq * Nq, Np = Nq2 * Nq, H = Nq / 2, N = Nq - 1;
+  // even-odd factors of D (host, once)
+  EoD e{};
+  for (int i = 0; i < H; ++i)
+    for (int m = 0; m < H; ++m) {
+      e.De[i * H + m] = 0.5 * (D_host[i * Nq + m] + D_host[i * Nq + N - m]);
+      e.Do[i * H + m] = 0.5 * (D_host[i * Nq + m] - D_host[i * Nq + N - m]);
+    }
+  for (int i = 0; i < H; ++i) {
+    e.Dc[i] = (Nq & 1) ? D_host[i * Nq + H] : 0.0;
+    e.Dr[i] = (Nq & 1) ? D_host[H * Nq + i] : 0.0;
+  }
+  static_assert(sizeof(EoD) == sizeof(eo), "EoD storage");
+  std::memcpy(eo, &e, sizeof(EoD));
+
+  size_t nPos = 0;
+  for (int k = 0; k < 3; ++k) {
+    seg[k].first = nPos;
+    seg[k].count = sd[k].count;
+    seg[k].nChains = (int)((sd[k].count + L - 1) / L);
+    nPos += (size_t)seg[k].nChains * L;
+  }
+  nPosTotal = nPos;
+  LIBP_CHECK(nPos < (size_t)INT_MAX, "too many elements for the chain plan");
+  elem.alloc(nPos);
+  hdr.alloc(nPos);
+  cid.alloc(nPos * 2 * Nq2);
+  flags.alloc(nPos * Nq2);
+  nSectors = ((size_t)nRows + 3) / 4;
+  const size_t nWords = (nSectors + 31) / 32;
+  zmask.alloc(nWords);
+  for (int k = 0; k < 3; ++k) {
+    const size_t n = (size_t)seg[k].nChains * L;
+    if (n) plan_fill_elem_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(n, L, sd[k].list, sd[k].first, sd[k].count,
+                                                                       elem.p + seg[k].first);
+  }
+  CUDA_CHECK(cudaGetLastError());
+  dev_buf<int> firstPos, lastPos, cnt;
+  const size_t nr = (size_t)std::max<dlong>(nRows, 1);
+  firstPos.alloc(nr); lastPos.alloc(nr); cnt.alloc(nr);
+  CUDA_CHECK(cudaMemsetAsync(firstPos.p, 0x7f, sizeof(int) * nr, s));  // 0x7f7f7f7f: larger than any position
+  CUDA_CHECK(cudaMemsetAsync(lastPos.p, 0xff, sizeof(int) * nr, s));   // -1
+  CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, sizeof(int) * nr, s));
+  if (nPos) {
+    plan_touch_kernel<<<grid_for(nPos * Np), 256, 0, s>>>(nPos, Np, elem.p, G2L, NlocalT, firstPos.p, lastPos.p);
+    plan_count_kernel<<<grid_for(nPos * Np), 256, 0, s>>>(nPos, Np, elem.p, G2L, NlocalT, firstPos.p, cnt.p);
+  }
+  plan_sector_kernel<<<(int)((nWords + 255) / 256), 256, 0, s>>>(nWords, nRows, NlocalT, L, firstPos.p, lastPos.p, cnt.p,
+                                                                 zmask.p);
+  if (nPos) plan_element_kernel<<<(unsigned)nPos, ((Nq2 + 31) / 32) * 32, 0, s>>>(Nq, elem.p, G2L, NlocalT, firstPos.p,
+                                                                                   zmask.p, hdr.p, cid.p, flags.p);
+  CUDA_CHECK(cudaGetLastError());
+  // statistics (how much of the accumulator still needs the zero-fill; how many elements are uncompressed)
+  dev_buf<unsigned long long> st;
+  st.alloc(2);
+  CUDA_CHECK(cudaMemsetAsync(st.p, 0, 16, s));
+  plan_stats_kernel<<<(int)((nWords + 255) / 256), 256, 0, s>>>(nWords, nSectors, zmask.p, st.p);
+  if (nPos) plan_count_raw_kernel<<<(int)((nPos + 255) / 256), 256, 0, s>>>(nPos, hdr.p, st.p + 1);
+  unsigned long long h[2] = {0, 0};
+  CUDA_CHECK(cudaMemcpyAsync(h, st.p, 16, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  zeroSectors = (size_t)h[0];
+  rawElements = (size_t)h[1];
+  built = true;
+}
+
+void AxChainPlan::zero_fill(dfloat* Aq, const int* doneFlag, cudaStream_t s) const {
+  if (nSectors == 0) return;
+  zero_fill_kernel<<<grid_for(nSectors), 256, 0, s>>>(nSectors, nRows, zmask.p, Aq, doneFlag);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+int AxChainPlan::launch(int k, const dlong* G2L, const dfloat* wJ, const dfloat* ggeo, dfloat lambda, const dfloat* q,
+                        dfloat* Aq, dfloat* dotPartials, const int* doneFlag, cudaStream_t s) const {
+  const Seg& sg = seg[k];
+  if (sg.nChains == 0) return 0;
+  ChainArgs A;
+  A.hdr = hdr.p + sg.first;
+  A.cid = cid.p + sg.first * 2 * Nq * Nq;
+  A.flags = flags.p + sg.first * Nq * Nq;
+  A.G2L = G2L; A.wJ = wJ; A.ggeo = ggeo; A.q = q; A.Aq = Aq; A.dotPartials = dotPartials; A.doneFlag = doneFlag;
+  A.lambda = lambda; A.nChains = sg.nChains; A.L = L; A.count = sg.count;
+  EoD e;
+  std::memcpy(&e, eo, sizeof(EoD));
+  switch (Nq) {
+#define CASE(n) case n: return launch_chain<n>(A, e, stages, s);
+    CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9)
+#undef CASE
+  }
+  return 0;
+}
+
+}  // namespace libp_b200

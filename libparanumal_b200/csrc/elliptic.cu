@@ -14,6 +14,9 @@
 #ifndef LIBP_AX_ZERO_AHEAD_DEFAULT
 #define LIBP_AX_ZERO_AHEAD_DEFAULT false  // in-kernel zero-fill of the fused accumulator; see elliptic.hpp
 #endif
+#ifndef LIBP_AX_CHAIN_DEFAULT
+#define LIBP_AX_CHAIN_DEFAULT 16  // elements per chain of the element-chain kernel (0 = off); see elliptic.hpp
+#endif
 #ifndef LIBP_AX_CHUNK_DEFAULT
 #define LIBP_AX_CHUNK_DEFAULT 0  // elements per zero-fill piece of the fused operator (0 = off); see elliptic.hpp
 #endif
@@ -23,6 +26,7 @@ using namespace libp_b200;
 namespace {
 dlong g_default_chunk = LIBP_AX_CHUNK_DEFAULT;
 bool g_default_za = LIBP_AX_ZERO_AHEAD_DEFAULT;
+int g_default_chain = LIBP_AX_CHAIN_DEFAULT, g_default_chain_stages = 2;
 
 // largest local gathered id (< limit) touched by each piece of an element list
 __global__ void __launch_bounds__(256) piece_max_kernel(const dlong* __restrict__ list, const dlong* __restrict__ G2L,
@@ -125,6 +129,15 @@ int libp_elliptic_s::zero_ahead_errors() {
   return bad;
 }
 
+void libp_elliptic_s::build_chain_plan(cudaStream_t s) {
+  libp_ogs_s& ogs = *d.ogsMasked;
+  const dlong nL = d.NlocalGatherElements, nG = d.NglobalGatherElements, nL0 = nL / 2;
+  const AxChainSegDesc sd[3] = {{d.localGatherElementList, 0, nL0}, {d.globalGatherElementList, 0, nG},
+                                {d.localGatherElementList, nL0, nL - nL0}};
+  chainPlan.stages = chainStages;
+  chainPlan.build(d.Nq, hD, ogs.NlocalT + ogs.NhaloT, ogs.NlocalT, d.GlobalToLocal, chainL, sd, s);
+}
+
 void libp_elliptic_s::apply(dfloat* q, dfloat* Aq, bool want_dot, const int* doneFlag, cudaStream_t s, bool zeroed) {
   libp_ogs_s& ogs = *d.ogsMasked;
   const dlong nL = d.NlocalGatherElements, nG = d.NglobalGatherElements;
@@ -133,6 +146,26 @@ void libp_elliptic_s::apply(dfloat* q, dfloat* Aq, bool want_dot, const int* don
   dfloat* out = fused ? Aq : AqL.p;
   dfloat* dp = want_dot ? dotPartials.p : nullptr;
   int doff = 0;
+  if (chain_on(Aq)) {
+    // element-chain kernel: only the sectors that are not chain-private are zero-filled (`zeroed` callers did that
+    // themselves with chain_zero_mask(), or zero-filled everything)
+    if (!chainPlan.built) build_chain_plan(s);
+    if (tev) CUDA_CHECK(cudaEventRecord(tev[0], s));
+    if (!zeroed) chainPlan.zero_fill(Aq, doneFlag, s);
+    if (tev) CUDA_CHECK(cudaEventRecord(tev[1], s));
+    auto run = [&](int k) {
+      doff += chainPlan.launch(k, d.GlobalToLocal, d.wJ, d.ggeo, d.lambda, q, Aq, dp ? dp + doff : nullptr, doneFlag, s);
+    };
+    halo_start_f64(ogs, q, s);
+    run(0);
+    halo_finish_f64(ogs, q, s);
+    run(1);
+    halo_combine_start_f64(ogs, Aq, s);
+    run(2);
+    halo_combine_finish_f64(ogs, Aq, s);
+    nDotPartials = doff;
+    return;
+  }
   auto ax = [&](dlong n, const dlong* list, const ZeroAhead* za = nullptr) {
     if (n <= 0) return;
     int nb = ax_hex3d_launch(d.Nq, fused, true, symD, n, list, d.GlobalToLocal, d.wJ, d.ggeo, d.D, d.lambda, q, out,
@@ -189,8 +222,10 @@ void libp_elliptic_s::apply(dfloat* q, dfloat* Aq, bool want_dot, const int* don
     nDotPartials = doff;
     return;
   }
+  if (tev) CUDA_CHECK(cudaEventRecord(tev[0], s));
   if (fused && !zeroed)
     CUDA_CHECK(cudaMemsetAsync(Aq, 0, sizeof(dfloat) * (size_t)(ogs.NlocalT + ogs.NhaloT), s));
+  if (tev) CUDA_CHECK(cudaEventRecord(tev[1], s));
   halo_start_f64(ogs, q, s);
   ax(nL0, d.localGatherElementList);
   halo_finish_f64(ogs, q, s);
@@ -204,6 +239,7 @@ void libp_elliptic_s::apply(dfloat* q, dfloat* Aq, bool want_dot, const int* don
     ax(nL1, d.localGatherElementList ? d.localGatherElementList + nL0 : nullptr);
     ogs_gather_finish_f64(ogs, Aq, AqL.p, LIBP_ADD, LIBP_TRANS, s);
   }
+  if (tev) CUDA_CHECK(cudaEventRecord(tev[2], s));
   nDotPartials = doff;
 }
 
@@ -225,12 +261,15 @@ extern "C" int libp_elliptic_create(const libp_elliptic_desc_t* desc, libp_ellip
     double hD[81];
     CUDA_CHECK(cudaMemcpy(hD, desc->D, sizeof(double) * desc->Nq * desc->Nq, cudaMemcpyDeviceToHost));
     e->symD = ax_hex3d_D_is_centro_antisymmetric(desc->Nq, hD);
+    std::copy(hD, hD + desc->Nq * desc->Nq, e->hD);
   }
   e->Ndofs = desc->ogsMasked->Ngather;
   e->Nhalo = desc->ogsMasked->NhaloT - desc->ogsMasked->NhaloP;
   if (desc->mode == 0) e->AqL.alloc((size_t)desc->Nelements * e->Np);
   e->chunk = (desc->mode == 1) ? g_default_chunk : 0;
   e->za_on = g_default_za;
+  e->chainL = (desc->mode == 1) ? g_default_chain : 0;
+  e->chainStages = g_default_chain_stages;
   e->alloc_dot_partials();
   *op = e.release();
   LIBP_API_END
@@ -252,6 +291,38 @@ extern "C" int libp_elliptic_set_chunk(libp_elliptic_t op, libp_dlong chunkEleme
   op->plan_built = false;
   op->plan.clear();
   op->alloc_dot_partials();
+  LIBP_API_END
+}
+
+extern "C" int libp_elliptic_set_chain(libp_elliptic_t op, int chainElements, int stages) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(op && chainElements >= 0 && chainElements <= 4096 && (stages == 2 || stages == 3), "bad argument");
+  op->chainL = (op->d.mode == 1) ? chainElements : 0;
+  op->chainStages = stages;
+  op->chainPlan.built = false;
+  LIBP_API_END
+}
+
+extern "C" int libp_elliptic_set_default_chain(int chainElements, int stages) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(chainElements >= 0 && chainElements <= 4096 && (stages == 2 || stages == 3), "bad argument");
+  g_default_chain = chainElements;
+  g_default_chain_stages = stages;
+  LIBP_API_END
+}
+
+extern "C" int libp_elliptic_chain_stats(libp_elliptic_t op, libp_dfloat* Aq, long long* stats, void* stream) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(op && stats, "null argument");
+  for (int i = 0; i < 6; ++i) stats[i] = 0;
+  if (!op->chain_on(Aq)) return LIBP_SUCCESS;
+  if (!op->chainPlan.built) op->build_chain_plan(as_stream(stream));
+  stats[0] = op->chainPlan.L;
+  stats[1] = (long long)op->chainPlan.nSectors;
+  stats[2] = (long long)op->chainPlan.zeroSectors;
+  stats[3] = (long long)op->chainPlan.nPosTotal;
+  stats[4] = (long long)op->chainPlan.rawElements;
+  stats[5] = op->chainPlan.stages;
   LIBP_API_END
 }
 
@@ -353,6 +424,31 @@ extern "C" int libp_mass_matrix_apply_hex3d(libp_dlong Nelements, int Np, const 
   LIBP_CHECK(N == 0 || (wJ && q && Mq), "null device pointer");
   if (N) rhs_forcing_kernel<<<ew_grid(N), 256, 0, as_stream(stream)>>>(N, wJ, q, Mq);
   CUDA_CHECK(cudaGetLastError());
+  LIBP_API_END
+}
+
+extern "C" int libp_elliptic_operator_timed(libp_elliptic_t op, libp_dfloat* q, libp_dfloat* Aq, void* stream,
+                                            double* ms) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(op && q && Aq && ms, "null argument");
+  LIBP_CHECK(!op->chunked() && !op->zero_ahead(), "timed apply: not available with the chunk / zero-ahead knobs");
+  cudaEvent_t ev[3];
+  for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
+  op->tev = ev;
+  try {
+    op->apply(q, Aq, false, nullptr, as_stream(stream));
+  } catch (...) {
+    op->tev = nullptr;
+    for (auto& e : ev) cudaEventDestroy(e);
+    throw;
+  }
+  op->tev = nullptr;
+  CUDA_CHECK(cudaEventSynchronize(ev[2]));
+  float a = 0.f, b = 0.f;
+  CUDA_CHECK(cudaEventElapsedTime(&a, ev[0], ev[1]));
+  CUDA_CHECK(cudaEventElapsedTime(&b, ev[1], ev[2]));
+  ms[0] = a; ms[1] = b;
+  for (auto& e : ev) cudaEventDestroy(e);
   LIBP_API_END
 }
 

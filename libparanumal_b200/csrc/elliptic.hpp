@@ -2,6 +2,7 @@
 #pragma once
 #include <vector>
 
+#include "ax_chain.hpp"
 #include "common.hpp"
 #include "ogs.hpp"
 
@@ -59,6 +60,25 @@ struct libp_elliptic_s {
   bool zero_ahead() const { return d.mode == 1 && symD && za_on && chunk == 0; }
   void build_zero_ahead(cudaStream_t s);
   int zero_ahead_errors();
+  // ---- element-chain kernel (mode 1, GLL D; ax_chain.cu): TMA-staged geometric factors, owner-computes stores for
+  // chain-private rows, compressed connectivity.  chainL = elements per chain (0 = off -> ax_hex3d_t_kernel).
+  libp_b200::AxChainPlan chainPlan;
+  int chainL = 0, chainStages = 2;
+  double hD[81] = {0};
+  bool chain_capable() const { return d.mode == 1 && symD && chainL > 0 && chunk == 0 && !za_on; }
+  // the sector classification needs a 32-byte aligned accumulator, the bulk copies 16-byte aligned factors
+  bool chain_on(const dfloat* Aq) const {
+    return chain_capable() && (reinterpret_cast<uintptr_t>(Aq) & 31) == 0 &&
+           (reinterpret_cast<uintptr_t>(d.ggeo) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.wJ) & 15) == 0;
+  }
+  void build_chain_plan(cudaStream_t s);
+  cudaEvent_t* tev = nullptr;  // libp_elliptic_operator_timed: [before zero-fill, after zero-fill, end of apply]
+  // zero-fill mask for a caller that folds the zero-fill of Aq into its own pass (nullptr: zero everything)
+  const uint32_t* chain_zero_mask(const dfloat* Aq, cudaStream_t s) {
+    if (!chain_on(Aq)) return nullptr;
+    if (!chainPlan.built) build_chain_plan(s);
+    return chainPlan.zmask.p;
+  }
   // apply; when dot/doneFlag are given the p.Ap partials are produced and the kernels early-exit
   // zeroed: the caller already zero-filled Aq[0 : NlocalT+NhaloT] (PCG folds it into its p-update pass)
   void apply(dfloat* q, dfloat* Aq, bool want_dot, const int* doneFlag, cudaStream_t s, bool zeroed = false);

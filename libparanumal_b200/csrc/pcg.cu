@@ -125,15 +125,16 @@ __global__ void __launch_bounds__(kBlock) dot_kernel(dlong N, const PcgScalars* 
 }
 
 // p = z + beta p ; optionally zero-fill Ap (the accumulator of the fused Ax epilogue) in the same pass
+// zmask (element-chain operator, ax_chain.cu): one bit per 4-row sector, only flagged sectors need the zero-fill
 __global__ void __launch_bounds__(kBlock) pupdate_kernel(dlong N, dlong Nzero, const PcgScalars* __restrict__ sc,
                                                          const double* __restrict__ z, double* __restrict__ p,
-                                                         double* __restrict__ Ap) {
+                                                         double* __restrict__ Ap, const uint32_t* __restrict__ zmask) {
   if (sc->done) return;
   const double beta = sc->beta;
   const dlong M = N > Nzero ? N : Nzero;
   for (dlong n = blockIdx.x * kBlock + threadIdx.x; n < M; n += gridDim.x * kBlock) {
     if (n < N) p[n] = z[n] + beta * p[n];
-    if (n < Nzero) Ap[n] = 0.0;
+    if (n < Nzero && (zmask == nullptr || ((zmask[n >> 7] >> ((n >> 2) & 31)) & 1u))) Ap[n] = 0.0;
   }
 }
 
@@ -476,6 +477,8 @@ extern "C" int libp_pcg_solve(libp_pcg_t pcg, libp_elliptic_t A, libp_precon_t M
   // with the slab-wise plan the operator zero-fills its accumulator itself, piece by piece (elliptic.hpp)
   const dlong Nzero = (A->d.mode == 1 && !A->chunked() && !A->zero_ahead()) ? (dlong)(A->d.ogsMasked->NlocalT + A->d.ogsMasked->NhaloT) : 0;
 
+  const uint32_t* zmask = (Nzero > 0) ? A->chain_zero_mask(pcg->Ap.p, s) : nullptr;
+
   // z = M r ; r.z ; beta = 0 for the first iteration
   auto precon_and_rz = [&]() {
     if (precon == 1) precon_dot_kernel<1><<<nb, kBlock, 0, s>>>(N, sc, M->invDiag.p, r, pcg->z.p, parts);
@@ -491,7 +494,7 @@ extern "C" int libp_pcg_solve(libp_pcg_t pcg, libp_elliptic_t A, libp_precon_t M
   int queued = 0, iter = 0;
   while (true) {
     // p = z + beta p (and the zero-fill of Ap for the fused Ax epilogue)
-    pupdate_kernel<<<vgrid(std::max(N, Nzero)), kBlock, 0, s>>>(N, Nzero, sc, pcg->z.p, pcg->p.p, pcg->Ap.p);
+    pupdate_kernel<<<vgrid(std::max(N, Nzero)), kBlock, 0, s>>>(N, Nzero, sc, pcg->z.p, pcg->p.p, pcg->Ap.p, zmask);
     // Ap = A p with p.Ap partials from the Ax kernel ; alpha
     A->apply(pcg->p.p, pcg->Ap.p, true, done, s, /*zeroed=*/Nzero > 0);
     stage(1, A->dotPartials.p, A->nDotPartials, 0, 0, 0);

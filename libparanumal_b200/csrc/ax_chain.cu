@@ -153,13 +153,14 @@ struct ChT {
   static constexpr int NG = 7;  // components per stage: 6 geometric factors + wJ (only copied when lambda != 0)
   // wJ can only ride the bulk copy when its per-element block keeps 16-byte alignment
   static constexpr bool kBulkWJ = (Np % 2 == 0);
-  static constexpr int StageDoubles = EPB * NG * Np + ((EPB * NG * Np) & 1);  // keep stages 16-byte aligned
+  static constexpr int SlotDoubles = NG * Np + ((NG * Np) & 1);  // bulk-copy destinations must be 16-byte aligned
+  static constexpr int StageDoubles = EPB * SlotDoubles;
 };
 
 template <int Nq, int S>
 constexpr size_t chain_smem_bytes() {
   using C = ChT<Nq>;
-  return (size_t)8 * (S * C::StageDoubles + 3 * C::EPB * C::ESS) + 8 * S + 16;
+  return (size_t)8 * (S * C::StageDoubles + 3 * C::EPB * C::ESS) + 8 * S + 4 * C::EPB + 16;
 }
 
 struct ChainArgs {
@@ -190,6 +191,7 @@ ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
   dfloat* s_r = s_u + EPB * ESS;
   dfloat* s_s = s_r + EPB * ESS;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_s + EPB * ESS);       // [S]
+  int* s_hdr = reinterpret_cast<int*>(s_bar + S);                       // [EPB] header of the step to be issued next
 
   const int t = threadIdx.x;
   const bool valid = t < C::Work;
@@ -221,32 +223,33 @@ ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
 
   // element header of step n of this slot's chain (-1: nothing to do)
   auto header = [&](int n) -> int { return (chainOK && n < L) ? __ldg(A.hdr + p0 + n) : -1; };
-  // thread 0 arms stage (n % S) and issues the copies of step n for every slot of the block
+  // thread 0 arms stage (n % S) and issues the copies of step n for every slot of the block.  The headers come from
+  // shared memory (each slot's first thread publishes the one it prefetched), not from a dependent global load.
   auto issue = [&](int n) {
     const uint32_t bar = smem_u32(&s_bar[n % S]);
     uint32_t bytes = 0;
-    int e_slot[EPB];
 #pragma unroll
-    for (int x = 0; x < EPB; ++x) {
-      const int ch = blockIdx.x * EPB + x;
-      int h = -1;
-      if (ch < A.nChains && n < L) h = __ldg(A.hdr + (size_t)ch * L + n);
-      e_slot[x] = (h >= 0) ? (h >> 1) : -1;
-      if (h >= 0) bytes += (uint32_t)(8 * Np * (bulkW ? 7 : 6));
-    }
+    for (int x = 0; x < EPB; ++x)
+      if (s_hdr[x] >= 0) bytes += (uint32_t)(8 * Np * (bulkW ? 7 : 6));
     if (bytes == 0) return;
     mbar_expect_tx(bar, bytes);
 #pragma unroll
     for (int x = 0; x < EPB; ++x) {
-      if (e_slot[x] < 0) continue;
-      dfloat* dst = s_g + (n % S) * C::StageDoubles + x * C::NG * Np;
-      bulk_g2s(smem_u32(dst), A.ggeo + (size_t)e_slot[x] * 6 * Np, 8 * 6 * Np, bar, polS);
-      if (bulkW) bulk_g2s(smem_u32(dst + 6 * Np), A.wJ + (size_t)e_slot[x] * Np, 8 * Np, bar, polS);
+      const int h = s_hdr[x];
+      if (h < 0) continue;
+      dfloat* dst = s_g + (n % S) * C::StageDoubles + x * C::SlotDoubles;
+      bulk_g2s(smem_u32(dst), A.ggeo + (size_t)(h >> 1) * 6 * Np, 8 * 6 * Np, bar, polS);
+      if (bulkW) bulk_g2s(smem_u32(dst + 6 * Np), A.wJ + (size_t)(h >> 1) * Np, 8 * Np, bar, polS);
     }
   };
-  if (t == 0) {
-#pragma unroll
-    for (int s = 0; s < S; ++s) issue(s);
+  const bool slotLead = valid && ij == 0;
+  for (int s = 0; s < S; ++s) {  // prologue: the first S steps
+    if (t < EPB) s_hdr[t] = -1;
+    __syncthreads();
+    if (slotLead) s_hdr[es] = header(s);
+    __syncthreads();
+    if (t == 0) issue(s);
+    __syncthreads();
   }
 
   // connectivity of step n: ids of this thread's k-pencil + store/reduce flags
@@ -292,7 +295,7 @@ ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
   const int nsteps = (int)(left < (long long)L ? (left < 0 ? 0 : left) : (long long)L);
   for (int n = 0; n < nsteps; ++n) {
     const bool active = h_cur >= 0;
-    const dfloat* __restrict__ sg = s_g + (n % S) * C::StageDoubles + es * C::NG * Np + nC;
+    const dfloat* __restrict__ sg = s_g + (n % S) * C::StageDoubles + es * C::SlotDoubles + nC;
 
     // ---- prefetch: q of step n+1, ids of step n+2
     dfloat q_nxt[Nq];
@@ -301,6 +304,8 @@ ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
     unsigned fl_nn;
     load_ids(n + 2, h_nn, id_nn, fl_nn);
     const int h_nnn = header(n + 3);
+    // header of step n + S for the copy issued after phase 2 (S <= 2: already in registers)
+    if (slotLead) s_hdr[es] = (S == 1) ? h_nxt : (S == 2) ? h_nn : h_nnn;
     dfloat r_w[Nq];
     if (screened && !C::kBulkWJ) {
 #pragma unroll
@@ -570,9 +575,13 @@ template <int Nq>
 int launch_chain(const ChainArgs& A, const EoD& eo, int stages, cudaStream_t s) {
   using C = ChT<Nq>;
   if (A.dotPartials) {
-    if (stages == 3) launch_chain_t<Nq, 3, true>(A, eo, s); else launch_chain_t<Nq, 2, true>(A, eo, s);
+    if (stages == 3) launch_chain_t<Nq, 3, true>(A, eo, s);
+    else if (stages == 1) launch_chain_t<Nq, 1, true>(A, eo, s);
+    else launch_chain_t<Nq, 2, true>(A, eo, s);
   } else {
-    if (stages == 3) launch_chain_t<Nq, 3, false>(A, eo, s); else launch_chain_t<Nq, 2, false>(A, eo, s);
+    if (stages == 3) launch_chain_t<Nq, 3, false>(A, eo, s);
+    else if (stages == 1) launch_chain_t<Nq, 1, false>(A, eo, s);
+    else launch_chain_t<Nq, 2, false>(A, eo, s);
   }
   return (A.nChains + C::EPB - 1) / C::EPB;
 }

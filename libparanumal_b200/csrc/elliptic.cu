@@ -163,6 +163,7 @@ void libp_elliptic_s::apply(dfloat* q, dfloat* Aq, bool want_dot, const int* don
     halo_combine_start_f64(ogs, Aq, s);
     run(2);
     halo_combine_finish_f64(ogs, Aq, s);
+    if (tev) CUDA_CHECK(cudaEventRecord(tev[2], s));
     nDotPartials = doff;
     return;
   }
@@ -296,7 +297,7 @@ extern "C" int libp_elliptic_set_chunk(libp_elliptic_t op, libp_dlong chunkEleme
 
 extern "C" int libp_elliptic_set_chain(libp_elliptic_t op, int chainElements, int stages) {
   LIBP_API_BEGIN
-  LIBP_CHECK(op && chainElements >= 0 && chainElements <= 4096 && (stages == 2 || stages == 3), "bad argument");
+  LIBP_CHECK(op && chainElements >= 0 && chainElements <= 4096 && (stages >= 1 && stages <= 3), "bad argument");
   op->chainL = (op->d.mode == 1) ? chainElements : 0;
   op->chainStages = stages;
   op->chainPlan.built = false;
@@ -305,7 +306,7 @@ extern "C" int libp_elliptic_set_chain(libp_elliptic_t op, int chainElements, in
 
 extern "C" int libp_elliptic_set_default_chain(int chainElements, int stages) {
   LIBP_API_BEGIN
-  LIBP_CHECK(chainElements >= 0 && chainElements <= 4096 && (stages == 2 || stages == 3), "bad argument");
+  LIBP_CHECK(chainElements >= 0 && chainElements <= 4096 && (stages >= 1 && stages <= 3), "bad argument");
   g_default_chain = chainElements;
   g_default_chain_stages = stages;
   LIBP_API_END

@@ -118,6 +118,14 @@ __device__ __forceinline__ void red_keep(dfloat* p, dfloat v, uint64_t pol) {
   asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
 }
 
+// 8-byte asynchronous global -> shared copy (LDGSTS); src_bytes = 0 writes zeros (masked node)
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, uint32_t src_bytes, uint64_t pol) {
+  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2, %3;" ::"r"(dst), "l"(src), "r"(src_bytes),
+               "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <int Nq>
 __device__ __forceinline__ void load_row(const dfloat* __restrict__ row, dfloat (&v)[Nq]) {
 #pragma unroll
@@ -150,17 +158,19 @@ struct ChT {
                           : (Nq == 6) ? 38 : (Nq == 7) ? 70 : 90;
   static constexpr int ESS = (Nq == 8) ? 8 * 66 : (Nq == 2) ? 10 : (Nq == 3) ? 42 : (Nq == 4) ? 72 : (Nq == 5) ? 150
                            : (Nq == 6) ? 228 : (Nq == 7) ? 496 : Nq * SS;
-  static constexpr int NG = 7;  // components per stage: 6 geometric factors + wJ (only copied when lambda != 0)
   // wJ can only ride the bulk copy when its per-element block keeps 16-byte alignment
   static constexpr bool kBulkWJ = (Np % 2 == 0);
-  static constexpr int SlotDoubles = NG * Np + ((NG * Np) & 1);  // bulk-copy destinations must be 16-byte aligned
-  static constexpr int StageDoubles = EPB * SlotDoubles;
+  // components per stage: 6 geometric factors (+ wJ for the screened operator)
+  __host__ __device__ static constexpr int ng(bool scr) { return (scr && kBulkWJ) ? 7 : 6; }
+  // bulk-copy destinations must be 16-byte aligned
+  __host__ __device__ static constexpr int slot_doubles(bool scr) { return ng(scr) * Np + ((ng(scr) * Np) & 1); }
+  __host__ __device__ static constexpr int stage_doubles(bool scr) { return EPB * slot_doubles(scr); }
 };
 
-template <int Nq, int S>
+template <int Nq, int S, bool kScr>
 constexpr size_t chain_smem_bytes() {
   using C = ChT<Nq>;
-  return (size_t)8 * (S * C::StageDoubles + 3 * C::EPB * C::ESS) + 8 * S + 4 * C::EPB + 16;
+  return (size_t)8 * (S * C::stage_doubles(kScr) + 3 * C::EPB * C::ESS) + 8 * S + 4 * C::EPB + 16;
 }
 
 struct ChainArgs {
@@ -179,15 +189,16 @@ struct ChainArgs {
   dlong count;  // elements of the segment (the last chain may be shorter than L)
 };
 
-template <int Nq, int S, bool kDot, int kMinB>
+template <int Nq, int S, bool kDot, bool kScr, int kMinB>
 __global__ void __launch_bounds__(ChT<Nq>::Threads, kMinB)
 ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
   if (A.doneFlag != nullptr && *A.doneFlag) return;
   using C = ChT<Nq>;
   constexpr int Nq2 = C::Nq2, Np = C::Np, LD = C::LD, SS = C::SS, ESS = C::ESS, EPB = C::EPB;
+  constexpr int StageDoubles = C::stage_doubles(kScr), SlotDoubles = C::slot_doubles(kScr);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   dfloat* s_g = reinterpret_cast<dfloat*>(smem_raw);                    // [S][EPB][NG][Np]
-  dfloat* s_u = s_g + S * C::StageDoubles;
+  dfloat* s_u = s_g + S * StageDoubles;
   dfloat* s_r = s_u + EPB * ESS;
   dfloat* s_s = s_r + EPB * ESS;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_s + EPB * ESS);       // [S]
@@ -206,8 +217,8 @@ ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
   const int kB = (Nq == 8) ? (4 * (b & 1) + (b >> 1)) : b;
   const int sB = es * ESS + kB * SS + a;
 
-  const bool screened = (A.lambda != 0.0);
-  const bool bulkW = screened && C::kBulkWJ;
+  constexpr bool screened = kScr;  // lambda != 0
+  constexpr bool bulkW = screened && C::kBulkWJ;
   const uint64_t polS = pol_evict_first(), polK = pol_evict_last();
   const int chain = blockIdx.x * EPB + es;         // one chain per element slot
   const bool chainOK = valid && chain < A.nChains;
@@ -237,7 +248,7 @@ ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
     for (int x = 0; x < EPB; ++x) {
       const int h = s_hdr[x];
       if (h < 0) continue;
-      dfloat* dst = s_g + (n % S) * C::StageDoubles + x * C::SlotDoubles;
+      dfloat* dst = s_g + (n % S) * StageDoubles + x * SlotDoubles;
       bulk_g2s(smem_u32(dst), A.ggeo + (size_t)(h >> 1) * 6 * Np, 8 * 6 * Np, bar, polS);
       if (bulkW) bulk_g2s(smem_u32(dst + 6 * Np), A.wJ + (size_t)(h >> 1) * Np, 8 * Np, bar, polS);
     }
@@ -252,7 +263,9 @@ ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
     __syncthreads();
   }
 
-  // connectivity of step n: ids of this thread's k-pencil + store/reduce flags
+  // connectivity of step n: this thread's k-pencil of ids (still encoded) + store/reduce flags.  Nothing loaded here
+  // is looked at before the end of the iteration that issued it (decode_ids): an early use would stall the warp on
+  // the scoreboard it shares with the q gathers.
   auto load_ids = [&](int n, int h, dlong (&id)[Nq], unsigned& fl) {
     if (h < 0) {
 #pragma unroll
@@ -269,25 +282,39 @@ ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
     } else {
       const int* c = A.cid + p * (2 * Nq2) + (a == 0 ? 0 : Nq2) + b;
 #pragma unroll
-      for (int k = 0; k < Nq; ++k) {
-        const int v = ld_stream_i(c + k * Nq, polS);
-        id[k] = (a == 0 || v < 0) ? v : v + (a - 1);
-      }
+      for (int k = 0; k < Nq; ++k) id[k] = ld_stream_i(c + k * Nq, polS);
     }
   };
-  auto gather_q = [&](const dlong (&id)[Nq], dfloat (&u)[Nq]) {
+  auto decode_ids = [&](int h, dlong (&id)[Nq]) {
+    if (h >= 0 && !(h & 1) && a != 0) {
 #pragma unroll
-    for (int k = 0; k < Nq; ++k) u[k] = (id[k] >= 0) ? ld_keep(A.q + id[k], polK) : 0.0;
+      for (int k = 0; k < Nq; ++k) id[k] = (id[k] < 0) ? id[k] : id[k] + (a - 1);
+    }
+  };
+  // q of a step is gathered straight into s_u (layout C slots of this thread) by 8-byte asynchronous copies: no
+  // registers are held while the gathers are in flight
+  const uint32_t su_base = smem_u32(s_u + sC);
+  auto gather_q_async = [&](const dlong (&id)[Nq]) {
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < Nq; ++k) {
+        const bool on = id[k] >= 0;
+        cp_async8(su_base + 8u * (uint32_t)(k * SS), A.q + (on ? id[k] : 0), on ? 8u : 0u, polK);
+      }
+    }
+    cp_async_commit();
   };
 
-  // software pipeline: ids two steps ahead, q one step ahead, geometric factors S steps ahead (TMA)
+  // software pipeline: ids two steps ahead (registers), q one step ahead (cp.async into s_u after phase 1 of the
+  // previous step), geometric factors S steps ahead (TMA)
   int h_cur = header(0), h_nxt = header(1), h_nn = header(2);
   dlong id_cur[Nq], id_nxt[Nq];
   unsigned fl_cur, fl_nxt;
-  dfloat q_cur[Nq];
   load_ids(0, h_cur, id_cur, fl_cur);
   load_ids(1, h_nxt, id_nxt, fl_nxt);
-  gather_q(id_cur, q_cur);
+  decode_ids(h_cur, id_cur);
+  decode_ids(h_nxt, id_nxt);
+  gather_q_async(id_cur);
   dfloat dacc = 0.0;
 
   // block-uniform trip count: the first slot owns the longest chain of the block (only the last chain is short)
@@ -295,11 +322,9 @@ ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
   const int nsteps = (int)(left < (long long)L ? (left < 0 ? 0 : left) : (long long)L);
   for (int n = 0; n < nsteps; ++n) {
     const bool active = h_cur >= 0;
-    const dfloat* __restrict__ sg = s_g + (n % S) * C::StageDoubles + es * C::SlotDoubles + nC;
+    const dfloat* __restrict__ sg = s_g + (n % S) * StageDoubles + es * SlotDoubles + nC;
 
-    // ---- prefetch: q of step n+1, ids of step n+2
-    dfloat q_nxt[Nq];
-    gather_q(id_nxt, q_nxt);
+    // ---- prefetch: ids of step n+2 (not looked at before the end of this iteration)
     dlong id_nn[Nq];
     unsigned fl_nn;
     load_ids(n + 2, h_nn, id_nn, fl_nn);
@@ -312,11 +337,11 @@ ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
       for (int k = 0; k < Nq; ++k) r_w[k] = active ? __ldg(A.wJ + (size_t)(h_cur >> 1) * Np + nC + k * Nq2) : 0.0;
     }
 
-    // ---- phase 0 (layout C): publish u, t-derivative in registers
-    if (valid) {
+    // ---- phase 0 (layout C): u arrived in s_u (own slots), t-derivative in registers
+    cp_async_wait_all();
+    dfloat q_cur[Nq];
 #pragma unroll
-      for (int k = 0; k < Nq; ++k) s_u[sC + k * SS] = q_cur[k];
-    }
+    for (int k = 0; k < Nq; ++k) q_cur[k] = s_u[sC + k * SS];
     dfloat r_t[Nq];
     eo_apply<Nq, false>(eo, q_cur, r_t);
     __syncthreads();
@@ -334,6 +359,8 @@ ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
       for (int j = 0; j < Nq; ++j) s_s[sB + j * LD] = o[j];
     }
     __syncthreads();
+    // s_u is free: gather q of the next step into it while phases 2-4 run
+    gather_q_async(id_nxt);
 
     // ---- phase 2 (layout C): geometric factors from the TMA-filled stage
     mbar_wait(smem_u32(&s_bar[n % S]), (uint32_t)((n / S) & 1));
@@ -393,12 +420,16 @@ ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
         }
       }
     }
-    // rotate the pipeline registers
+    // rotate the pipeline registers (first use of this iteration's id loads)
+    decode_ids(h_nn, id_nn);
     h_cur = h_nxt; h_nxt = h_nn; h_nn = h_nnn;
     fl_cur = fl_nxt; fl_nxt = fl_nn;
 #pragma unroll
-    for (int k = 0; k < Nq; ++k) { id_cur[k] = id_nxt[k]; id_nxt[k] = id_nn[k]; q_cur[k] = q_nxt[k]; }
+    for (int k = 0; k < Nq; ++k) { id_cur[k] = id_nxt[k]; id_nxt[k] = id_nn[k]; }
+    // phase 4 reads of s_r / s_s must finish before the next phase 1 overwrites them: the barrier after the next
+    // phase 0 orders that
   }
+  cp_async_wait_all();
 
   if (kDot) {
     dfloat d = dacc;
@@ -552,15 +583,15 @@ __global__ void __launch_bounds__(256) zero_fill_kernel(size_t nSectors, dlong n
 
 int grid_for(size_t n) { return (int)std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 32); }
 
-template <int Nq, int S, bool kDot>
+template <int Nq, int S, bool kDot, bool kScr>
 void launch_chain_t(const ChainArgs& A, const EoD& eo, cudaStream_t s) {
   using C = ChT<Nq>;
-  constexpr size_t smem = chain_smem_bytes<Nq, S>();
+  constexpr size_t smem = chain_smem_bytes<Nq, S, kScr>();
   // resident blocks by shared memory (227 KB per SM, 1 KB reserved per block)
   constexpr int fit = (int)(232448 / (smem + 1024));
   constexpr int cap = (512 + C::Threads - 1) / C::Threads;  // ~512 threads per SM keeps >= 128 registers per thread
   constexpr int minb = fit < 1 ? 1 : (fit > cap ? cap : fit);
-  auto kern = ax_hex3d_chain_kernel<Nq, S, kDot, minb>;
+  auto kern = ax_hex3d_chain_kernel<Nq, S, kDot, kScr, minb>;
   static bool configured = false;
   if (!configured) {
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -571,17 +602,21 @@ void launch_chain_t(const ChainArgs& A, const EoD& eo, cudaStream_t s) {
   CUDA_CHECK(cudaGetLastError());
 }
 
+template <int Nq, bool kDot, bool kScr>
+void launch_chain_s(const ChainArgs& A, const EoD& eo, int stages, cudaStream_t s) {
+  if (stages == 3) launch_chain_t<Nq, 3, kDot, kScr>(A, eo, s);
+  else if (stages == 2) launch_chain_t<Nq, 2, kDot, kScr>(A, eo, s);
+  else launch_chain_t<Nq, 1, kDot, kScr>(A, eo, s);
+}
+
 template <int Nq>
 int launch_chain(const ChainArgs& A, const EoD& eo, int stages, cudaStream_t s) {
   using C = ChT<Nq>;
+  const bool scr = A.lambda != 0.0;
   if (A.dotPartials) {
-    if (stages == 3) launch_chain_t<Nq, 3, true>(A, eo, s);
-    else if (stages == 1) launch_chain_t<Nq, 1, true>(A, eo, s);
-    else launch_chain_t<Nq, 2, true>(A, eo, s);
+    if (scr) launch_chain_s<Nq, true, true>(A, eo, stages, s); else launch_chain_s<Nq, true, false>(A, eo, stages, s);
   } else {
-    if (stages == 3) launch_chain_t<Nq, 3, false>(A, eo, s);
-    else if (stages == 1) launch_chain_t<Nq, 1, false>(A, eo, s);
-    else launch_chain_t<Nq, 2, false>(A, eo, s);
+    if (scr) launch_chain_s<Nq, false, true>(A, eo, stages, s); else launch_chain_s<Nq, false, false>(A, eo, stages, s);
   }
   return (A.nChains + C::EPB - 1) / C::EPB;
 }

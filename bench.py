@@ -28,6 +28,35 @@ import time
 # 5x here.  Passive waiting is the setting that favours the CPU baseline; it must be in place before libgomp starts.
 os.environ.setdefault("OMP_WAIT_POLICY", "passive")
 
+
+def _physical_cores():
+    """physical cores this process may run on (the reference derives its OpenMP thread count from lscpu,
+    libs/core/platformDeviceConfig.cpp:103-153)"""
+    try:
+        allowed = os.sched_getaffinity(0)
+    except AttributeError:
+        allowed = set(range(os.cpu_count() or 1))
+    cores = set()
+    try:
+        for c in allowed:
+            base = f"/sys/devices/system/cpu/cpu{c}/topology/"
+            with open(base + "physical_package_id") as f:
+                pkg = f.read().strip()
+            with open(base + "core_id") as f:
+                cid = f.read().strip()
+            cores.add((pkg, cid))
+    except OSError:
+        return max(1, len(allowed))
+    return max(1, len(cores))
+
+
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arms (the reference arm, the cpu_baseline leg of a
+# single-GPU run) must use the host's cores, and libgomp reads the variable once, when it is first loaded.
+_WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+if "--impl" in sys.argv and "reference" in sys.argv or _WORLD == 1:
+    if os.environ.get("LIBP_BENCH_KEEP_OMP") != "1":
+        os.environ["OMP_NUM_THREADS"] = str(_physical_cores())
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -53,6 +82,10 @@ def parse():
     ap.add_argument("--no-pcg", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
+                    help="c2: BP5 operator + Jacobi-PCG on the 64^3 box (BASELINE configs[1], [2]); "
+                         "c4: MULTIGRID-PCG, Hex N=7, 96^3 box (configs[3], meant for --gpus 8)")
+    ap.add_argument("--solve-tol", type=float, default=1e-8)
     return ap.parse_args()
 
 
@@ -147,6 +180,13 @@ def cpu_ax_sample(N, n, steps, warmup, seconds=None):
     return o.Ngather / dt / 1e9, dt, threads, o.Ngather, steps, kind
 
 
+def bench_config(N, n, mode=1):
+    """identical on both arms (the driver compares them)"""
+    return {"workload": f"bp5_operator_hex_n{N}_e{n}", "N": N, "elements": [n, n, n], "lambda": 0.0,
+            "global_dofs": int((n * N - 1) ** 3), "mode": "fused-gather" if mode == 1 else "reference-flow",
+            "l2": "inputs (6.4 GB of geometric factors per apply) are far larger than the 126 MB L2; no flush needed"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -162,8 +202,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": gd, "unit": "GDOF/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"bp5_operator_hex_n{N}_e{args.elements}", "N": N,
-                       "elements": [args.elements] * 3, "lambda": 0.0, "cpu_sample_elements": [n] * 3},
+            "config": bench_config(N, args.elements, args.mode),
+            "cpu_sample_elements": [n] * 3, "cpu_flags": "g++ -O3 -march=x86-64-v3 -fopenmp (OCCA JIT of the reference's OKL)",
             "cpu_baseline": {"value": gd, "unit": "GDOF/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": gd, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -174,6 +214,15 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload == "c4":
+        # BASELINE configs[3]: MULTIGRID-PCG, Hex N=7, 96^3 box (run with --gpus 8); one "step" = one PCG iteration
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("mg_bench", os.path.join(ROOT, "tools", "mg_bench.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        n = args.elements if args.elements != 64 else 96
+        mod.main(["--degree", str(args.degree), "--elements", str(n), "--tol", str(args.solve_tol), "--bench-line"])
         return
 
     import torch
@@ -255,40 +304,36 @@ def main():
     del y, Ay
 
     # ------------------------------------------------------------------ dominant kernel vs HBM roofline
+    # Measured live, on the operator handle itself: libp_elliptic_operator_timed records CUDA events on the launching
+    # stream around the two parts of one apply (zero-fill of the accumulator | exchange + Ax launches + combine).
     m = p.mesh
     E, Np = m.Nelements, m.Np
     peak, peak_src = measured_peaks()
-    Aq2 = p.vec()
-    api.register_D(p.Nq, m.D)  # mesh.o_D is immutable: same even-odd kernel the operator handle launches
-    def kern():
-        api.ax_hex3d_gather(p.Nq, E, None, p.GlobalToLocal, m.wJ, m.ggeo, m.D, 0.0, q, Aq2)
-    for _ in range(3):
-        Aq2.zero_(); kern()
-    # the kernel accumulates into Aq2; zeroing is outside the kernel timing (events bracket kernels only)
-    kms = 0.0
     ksteps = min(steps, 50)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ksteps)]
-    torch.cuda.synchronize()
-    for a, b in ev:
-        Aq2.zero_()
-        a.record(); kern(); b.record()
-    torch.cuda.synchronize()
-    kms = sum(a.elapsed_time(b) for a, b in ev) / ksteps
-    api.unregister_D(m.D)
-    alg_bytes = 8.0 * 6 * E * Np + 16.0 * p.Ndofs  # geofactors + read q + write Aq (lambda = 0)
+    parts = [p.op.OperatorTimed(q, Aq) for _ in range(ksteps)]
+    zms = sum(x[0] for x in parts) / ksteps
+    kms = sum(x[1] for x in parts) / ksteps
+    alg_bytes = 8.0 * 6 * E * Np + 16.0 * p.Ndofs  # geofactors + read q + write Aq (lambda = 0), this rank
     achieved = alg_bytes / (kms * 1e-3) / 1e9
-    traffic = None
+    plan_stats = p.op.chain_stats(Aq)
+    chain_on = plan_stats["chain"] > 0
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "ax_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            key = "chain" if chain_on else "previous"
+            if N == 7 and n == 64 and world == 1 and key in tj:
+                traffic, traffic_src = tj[key]["dram_bytes_per_apply"], tj[key]["source"]
         except Exception:
             traffic = None
+    kname = (f"ax_hex3d_chain_kernel<Nq={p.Nq},stages={plan_stats['stages']}> x{plan_stats['chain']} elements per chain"
+             if chain_on else f"ax_hex3d_t_kernel<Nq={p.Nq},gather,fused,even-odd>")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "ax_hex3d_t_kernel<Nq=8,gather,fused,even-odd>", "kernel_ms": kms,
-                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "elements_per_launch": E}
-    del Aq2
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": kname, "kernel_ms": kms,
+                "zero_fill_ms": zms, "step_frac": (alg_bytes / (ms / steps * 1e-3) / 1e9) / peak,
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "elements_per_launch": E,
+                "launches_per_apply": (2 if world == 1 else 3)}
 
     # ------------------------------------------------------------------ e2e: host buffers through the C ABI
     # Each step copies that step's q from pinned host memory, applies the operator through the C ABI and
@@ -348,9 +393,9 @@ def main():
                "path": "pinned host q -> H2D -> libp_elliptic_operator -> D2H Aq (double-buffered over steps)"}
         del hq, hA, dq, dA
 
-    # launches inside the timed region per step: single rank = 2 Ax kernels (the two halves of the local
-    # element list; the zero-fill is a memset node); sharded = 3 Ax + halo extract + 2 combine/extract kernels
-    launches_per_step = 2 if world == 1 else 6
+    # launches inside the timed region per step: single rank = zero-fill kernel + 2 Ax kernels (the two halves of the
+    # local element list); sharded = zero-fill + 3 Ax + halo pack/send + wait/unpack + combine pack + combine unpack
+    launches_per_step = 3 if world == 1 else 8
 
     # ------------------------------------------------------------------ Jacobi-PCG on the screened problem
     pcg = None
@@ -379,7 +424,34 @@ def main():
         pms = float(pms.item())
         hist = solver.residual_history()
         it_bytes = (8.0 * 7 * p.mesh.Nelements * p.mesh.Np + 16.0 * p.Ndofs) + 88.0 * p.Ndofs
+        # solve-level end to end: gathered right-hand side in pinned HOST memory -> H2D -> libp_pcg_solve to
+        # args.solve_tol -> D2H of the solution (what a caller of elliptic_t::Solve sees, vectors resident in between)
+        solve_e2e = None
+        if not args.no_e2e:
+            h_r = r0.cpu().pin_memory()
+            h_x = torch.empty(p.Nall, dtype=torch.float64).pin_memory()
+            xs, rs_ = p.vec(), p.vec()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            rs_.copy_(h_r, non_blocking=True)
+            xs.zero_()
+            its = solver.Solve(p.op, M, xs, rs_, tol=args.solve_tol, maxit=5000)
+            h_x.copy_(xs, non_blocking=True)
+            e1.record()
+            barrier()
+            sms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+            sms = float(sms.item())
+            sh = solver.residual_history()
+            solve_e2e = {"value": p.NglobalDofs * its / (sms * 1e-3) / 1e9, "unit": "GDOF/s", "iterations": its,
+                         "seconds": sms * 1e-3, "tol": args.solve_tol, "h2d_bytes": int(8 * p.Nall),
+                         "d2h_bytes": int(8 * p.Nall), "residual_first_last": [float(sh[0]), float(sh[-1])],
+                         "path": "pinned host rhs -> H2D -> libp_pcg_solve (Jacobi) -> D2H x"}
+            del h_r, h_x, xs, rs_
         pcg = {"config": f"screened Poisson (lambda=1) Jacobi-PCG, Hex N={N}, {n}^3 box", "iterations": it,
+               "solve_e2e": solve_e2e,
                "ms_per_iteration": pms / max(it, 1), "value": p.NglobalDofs * it / (pms * 1e-3) / 1e9,
                "unit": "GDOF/s", "residual_first_last": [float(hist[0]), float(hist[-1])],
                "roofline_frac": (it_bytes / (pms / max(it, 1) * 1e-3) / 1e9) / peak,
@@ -401,10 +473,9 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "GDOF/s", "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"bp5_operator_hex_n{N}_e{n}", "N": N, "elements": [n, n, n], "lambda": 0.0,
-                           "global_dofs": int(Ng), "exchange": ("nvlink-peer-window" if p2p else "nccl") if world > 1 else "none", "mode": "fused-gather" if args.mode == 1 else "reference-flow",
-                           "l2": "inputs (6.4 GB of geometric factors per apply) are far larger than the 126 MB L2; no flush needed",
-                           "setup_seconds": round(t_setup, 1)},
+                "config": bench_config(N, n, args.mode),
+                "exchange": ("nvlink-peer-window" if p2p else "nccl") if world > 1 else "none",
+                "setup_seconds": round(t_setup, 1), "chain_plan": plan_stats,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * steps,
                 "roofline": roofline, "cpu_baseline": cpu, "pcg": pcg, "checks": checks}
         print(json.dumps(line))

@@ -384,7 +384,7 @@ class Elliptic:
         check(L.load().libp_elliptic_zero_ahead_errors(self._h, C.byref(e)))
         return e.value
 
-    def set_chain(self, chain_elements, stages=2):
+    def set_chain(self, chain_elements, stages=1):
         """element-chain kernel: elements per chain (0 = off), TMA stages; see libp_elliptic_set_chain"""
         check(L.load().libp_elliptic_set_chain(self._h, int(chain_elements), int(stages)))
 

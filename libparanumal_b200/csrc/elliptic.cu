@@ -15,7 +15,7 @@
 #define LIBP_AX_ZERO_AHEAD_DEFAULT false  // in-kernel zero-fill of the fused accumulator; see elliptic.hpp
 #endif
 #ifndef LIBP_AX_CHAIN_DEFAULT
-#define LIBP_AX_CHAIN_DEFAULT 16  // elements per chain of the element-chain kernel (0 = off); see elliptic.hpp
+#define LIBP_AX_CHAIN_DEFAULT 4  // elements per chain of the element-chain kernel (0 = off); see elliptic.hpp
 #endif
 #ifndef LIBP_AX_CHUNK_DEFAULT
 #define LIBP_AX_CHUNK_DEFAULT 0  // elements per zero-fill piece of the fused operator (0 = off); see elliptic.hpp
@@ -26,7 +26,7 @@ using namespace libp_b200;
 namespace {
 dlong g_default_chunk = LIBP_AX_CHUNK_DEFAULT;
 bool g_default_za = LIBP_AX_ZERO_AHEAD_DEFAULT;
-int g_default_chain = LIBP_AX_CHAIN_DEFAULT, g_default_chain_stages = 2;
+int g_default_chain = LIBP_AX_CHAIN_DEFAULT, g_default_chain_stages = 1;
 
 // largest local gathered id (< limit) touched by each piece of an element list
 __global__ void __launch_bounds__(256) piece_max_kernel(const dlong* __restrict__ list, const dlong* __restrict__ G2L,

@@ -29,3 +29,17 @@ def test_reference_arm_other_ranks_stay_silent():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "1", "--cpu-elements", "4"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_reference_arm_ignores_torchrun_thread_cap():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must still use the host's physical cores"""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", OMP_NUM_THREADS="1")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "1", "--cpu-elements", "4"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][0])
+    sys.path.insert(0, ROOT)
+    import importlib
+    cores = importlib.import_module("bench")._physical_cores()
+    assert d["cpu_baseline"]["cores"] == cores, (d["cpu_baseline"]["cores"], cores)
+    assert d["config"]["global_dofs"] == (64 * 7 - 1) ** 3

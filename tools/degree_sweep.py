@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--pcg-iters", type=int, default=30)
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the per-GPU box edge (smoke runs)")
+    ap.add_argument("--chains", default="", help="comma list of chain:stages configurations of the fused operator "
+                    "(0:1 = ax_hex3d_t_kernel); empty = library default")
     a = ap.parse_args()
     import torch.distributed as dist
     world, rank, lr = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -60,11 +62,16 @@ def main():
 
     for N in [int(x) for x in a.degrees.split(",")]:
         n = max(2, int(round(BOX[N] * a.scale)))
-        for lam in (0.0, 1.0):
-            p = EllipticProblem(N, n * sx, n * sy, n * sz, lam=lam, comm=comm, coords=(lam != 0.0))
+        for lam, cfg in [(l, c) for l in (0.0, 1.0) for c in (a.chains.split(",") if a.chains else [""])]:
+            if cfg == "" or cfg == (a.chains.split(",")[0] if a.chains else ""):
+                p = EllipticProblem(N, n * sx, n * sy, n * sz, lam=lam, comm=comm, coords=(lam != 0.0))
             E, Np = p.mesh.Nelements, p.mesh.Np
             out = {"N": N, "elements_per_gpu": [n, n, n], "n_gpus": world, "lambda": lam, "global_dofs": int(p.NglobalDofs),
                    "local_dofs": int(p.Ndofs)}
+            if cfg:
+                L_, S_ = (int(v) for v in cfg.split(":"))
+                p.op.set_chain(L_, S_)
+                out.update(chain=L_, stages=S_)
             ax_bytes = 8.0 * (6 + (lam != 0.0)) * E * Np + 16.0 * p.Ndofs
             if lam == 0.0:
                 q, Aq = p.vec(), p.vec()
@@ -89,9 +96,10 @@ def main():
                 del M, r0, solver, x, r
             if rank == 0:
                 print(json.dumps(out), flush=True)
-            p.op.Free()
-            del p
-            torch.cuda.empty_cache()
+            if cfg == "" or cfg == a.chains.split(",")[-1]:
+                p.op.Free()
+                del p
+                torch.cuda.empty_cache()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

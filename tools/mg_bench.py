@@ -26,7 +26,7 @@ from libparanumal_b200.api import Comm  # noqa: E402
 from libparanumal_b200.problem import EllipticProblem, MultigridHierarchy  # noqa: E402
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--degree", type=int, default=7)
     ap.add_argument("--elements", type=int, default=64)
@@ -34,7 +34,8 @@ def main():
     ap.add_argument("--smoother", default="CHEBYSHEV")
     ap.add_argument("--repeat", type=int, default=3)
     ap.add_argument("--no-jacobi", action="store_true")
-    args = ap.parse_args()
+    ap.add_argument("--bench-line", action="store_true", help="print bench.py's contract line (bench.py --workload c4)")
+    args = ap.parse_args(argv)
     world, rank, lr = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
     api.init(lr)
     gloo = None
@@ -104,6 +105,15 @@ def main():
         itj, msj = timed_solve(sj, p.jacobi(), xj, r0)
         out["jacobi_pcg"] = {"iterations": itj, "solve_ms": msj, "gdofs": p.NglobalDofs * itj / (msj * 1e-3) / 1e9,
                              "speedup_time_to_solution": msj / ms}
+    if args.bench_line:
+        out = {"metric": "GDOF/s (FP64) hex N=7 Ax & PCG solve at 1/2/4/8 B200; % HBM roofline",
+               "value": out["gdofs"], "unit": "GDOF/s", "n_gpus": world, "steps": it, "warmup": args.repeat - 1,
+               "ms_per_step": ms / max(it, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic",
+               "config": {"workload": out["workload"], "N": args.degree, "elements": [args.elements] * 3, "lambda": 1.0,
+                          "global_dofs": int(p.NglobalDofs), "preconditioner": "MULTIGRID (p-MG Chebyshev + AMG + exact coarse)",
+                          "step": "one PCG iteration of the solve to tol"},
+               "roofline": None, "cpu_baseline": None, "e2e": None, "gpu_launches": None, "c4": out}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -15,7 +15,7 @@
 #define LIBP_AX_ZERO_AHEAD_DEFAULT false  // in-kernel zero-fill of the fused accumulator; see elliptic.hpp
 #endif
 #ifndef LIBP_AX_CHAIN_DEFAULT
-#define LIBP_AX_CHAIN_DEFAULT 4  // elements per chain of the element-chain kernel (0 = off); see elliptic.hpp
+#define LIBP_AX_CHAIN_DEFAULT -1  // elements per chain of the element-chain kernel (0 = off, -1 = per order); see elliptic.hpp
 #endif
 #ifndef LIBP_AX_CHUNK_DEFAULT
 #define LIBP_AX_CHUNK_DEFAULT 0  // elements per zero-fill piece of the fused operator (0 = off); see elliptic.hpp
@@ -269,7 +269,9 @@ extern "C" int libp_elliptic_create(const libp_elliptic_desc_t* desc, libp_ellip
   if (desc->mode == 0) e->AqL.alloc((size_t)desc->Nelements * e->Np);
   e->chunk = (desc->mode == 1) ? g_default_chunk : 0;
   e->za_on = g_default_za;
-  e->chainL = (desc->mode == 1) ? g_default_chain : 0;
+  // measured on B200 (profiles/r2_d_degree_sweep_chains.jsonl, r2_c_chain_tune_*): 8 elements per chain up to N = 6,
+  // 4 from N = 7 (short chains keep the tail of a launch short; longer ones make more sectors chain-private)
+  e->chainL = (desc->mode == 1) ? (g_default_chain >= 0 ? g_default_chain : (desc->Nq >= 8 ? 4 : 8)) : 0;
   e->chainStages = g_default_chain_stages;
   e->alloc_dot_partials();
   *op = e.release();
@@ -306,7 +308,7 @@ extern "C" int libp_elliptic_set_chain(libp_elliptic_t op, int chainElements, in
 
 extern "C" int libp_elliptic_set_default_chain(int chainElements, int stages) {
   LIBP_API_BEGIN
-  LIBP_CHECK(chainElements >= 0 && chainElements <= 4096 && (stages >= 1 && stages <= 3), "bad argument");
+  LIBP_CHECK(chainElements >= -1 && chainElements <= 4096 && (stages >= 1 && stages <= 3), "bad argument");
   g_default_chain = chainElements;
   g_default_chain_stages = stages;
   LIBP_API_END

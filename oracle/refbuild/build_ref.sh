@@ -35,13 +35,16 @@ if [ ! -f "$W/occa/lib/libocca.so" ]; then
      OCCA_CUDA_ENABLED=0 OCCA_OPENCL_ENABLED=0 OCCA_HIP_ENABLED=0 OCCA_DPCPP_ENABLED=0 OCCA_METAL_ENABLED=0 \
      > "$W/occa_build.log" 2>&1
 fi
+# 1b. the MPI stand-in (single rank: memcpy collectives; MPISTUB_SIZE > 1: one process per rank, see mpistub.c)
+gcc -O2 -fPIC -c "$HERE/mpistub/mpistub.c" -I"$HERE/mpistub" -o "$W/mpistub.o"
+ar rcs "$W/libmpistub.a" "$W/mpistub.o"
 # 2. libParanumal libs + elliptic (std::sort semantics: no -DGLIBCXX_PARALLEL)
 INC="-I$HERE/mpistub -include $W/lapack_rename.h -I$W/include -I$W/occa/include"
 make -C "$W" -j"$J" elliptic LIBP_CC=gcc LIBP_CXX=g++ LIBP_LD=g++ \
   LIBP_INCLUDES="$INC" \
   LIBP_CXXFLAGS="-fopenmp -O3 -Wall -Wno-unused-function -std=c++17 -mavx2 -march=native" \
   LIBP_CFLAGS="-fopenmp -O3 -Wall -Wno-unused-function -mavx2 -march=native" \
-  LIBP_BLAS_DIR="$BL" LIBP_BLAS_LIB="-L$BL -l:$BLSO" > "$W/libp_build.log" 2>&1
+  LIBP_BLAS_DIR="$BL" LIBP_BLAS_LIB="-L$BL -l:$BLSO $W/libmpistub.a" > "$W/libp_build.log" 2>&1
 make -C "$W/solvers/elliptic" lib LIBP_DIR="$W" LIBP_CC=gcc LIBP_CXX=g++ LIBP_LD=g++ \
   LIBP_INCLUDES="$INC" \
   LIBP_CXXFLAGS="-fopenmp -O3 -Wall -Wno-unused-function -std=c++17 -mavx2 -march=native" \
@@ -55,7 +58,7 @@ g++ -fopenmp -O2 -std=c++17 -march=native -Wno-unused-function \
   -o "$OUT/dump_driver" "$HERE/dump_driver.cpp" \
   "$W/solvers/elliptic/libelliptic.a" \
   -L"$W/libs" -lparAlmond -llinearSolver -lmesh -lparAdogs -logs -llinAlg -lcore \
-  -Wl,-rpath,"$BL" -L"$BL" -l:"$BLSO" -Wl,-rpath,"$W/occa/lib" -L"$W/occa/lib" -locca
+  "$W/libmpistub.a" -Wl,-rpath,"$BL" -L"$BL" -l:"$BLSO" -Wl,-rpath,"$W/occa/lib" -L"$W/occa/lib" -locca
 echo "dump driver built: $OUT/dump_driver"
 # 4. multigrid dump driver (our own code, oracle/refbuild/dump_mg_driver.cpp)
 g++ -fopenmp -O2 -std=c++17 -march=native -Wno-unused-function \
@@ -64,5 +67,5 @@ g++ -fopenmp -O2 -std=c++17 -march=native -Wno-unused-function \
   -o "$OUT/dump_mg_driver" "$HERE/dump_mg_driver.cpp" \
   "$W/solvers/elliptic/libelliptic.a" \
   -L"$W/libs" -lparAlmond -llinearSolver -lmesh -lparAdogs -logs -llinAlg -lcore \
-  -Wl,-rpath,"$BL" -L"$BL" -l:"$BLSO" -Wl,-rpath,"$W/occa/lib" -L"$W/occa/lib" -locca
+  "$W/libmpistub.a" -Wl,-rpath,"$BL" -L"$BL" -l:"$BLSO" -Wl,-rpath,"$W/occa/lib" -L"$W/occa/lib" -locca
 echo "mg dump driver built: $OUT/dump_mg_driver"

@@ -105,6 +105,12 @@ int libp_comm_nccl_init(libp_comm_t comm, const void* uid128);
  * called (or fails on any rank: LIBP_ERROR on every rank) the NCCL path is used.                          */
 int libp_comm_p2p_init(libp_comm_t comm, size_t window_bytes);
 int libp_comm_p2p_enabled(libp_comm_t comm, int* enabled);
+/* Every in-kernel wait on a peer's flag is bounded (LIBP_P2P_TIMEOUT_MS, default 30000): when one times out - a peer
+ * threw between collectives, or ranks diverged in the exchanges they issue - the kernels stop waiting and raise an
+ * error word instead of hanging the GPU.  libp_comm_p2p_status reads it (non-zero: results computed through this
+ * communicator since are invalid; libp_pcg_solve checks it itself); libp_comm_p2p_reset clears it. */
+int libp_comm_p2p_status(libp_comm_t comm, int* timed_out);
+int libp_comm_p2p_reset(libp_comm_t comm);
 
 /* ------------------------------------------------------------------ ogs
  * ogs::ogs_t::Setup (include/ogs.hpp:216-226; libs/ogs/ogsSetup.cpp:43-190).

@@ -74,6 +74,8 @@ SIGNATURES = {
     "libp_comm_nccl_init": (i32, [vp, vp]),
     "libp_comm_p2p_init": (i32, [vp, C.c_size_t]),
     "libp_comm_p2p_enabled": (i32, [vp, vp]),
+    "libp_comm_p2p_status": (i32, [vp, P(i32)]),
+    "libp_comm_p2p_reset": (i32, [vp]),
     "libp_ogs_setup": (i32, [i32, vp, vp, i32, i32, i32, P(vp)]),
     "libp_ogs_free": (i32, [vp]),
     "libp_ogs_info": (i32, [vp, P(OgsInfo)]),

@@ -206,6 +206,12 @@ class Comm:
         check(L.load().libp_comm_p2p_enabled(self._h, C.byref(e)))
         return bool(e.value)
 
+    def p2p_timed_out(self):
+        """True when an in-kernel wait on a peer exceeded its bound (libp_comm_p2p_status)"""
+        e = C.c_int(0)
+        check(L.load().libp_comm_p2p_status(self._h, C.byref(e)))
+        return bool(e.value)
+
     @property
     def handle(self):
         return self._h

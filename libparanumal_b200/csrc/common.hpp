@@ -100,6 +100,8 @@ struct WinAR {
   int rank = 0, size = 1;
   char* const* peer_win = nullptr;   // device table
   unsigned long long* seq = nullptr; // device counter (shared by every user of the communicator)
+  int* err = nullptr;                // device error word of the communicator (a bounded wait timed out)
+  long long timeout = 0;             // SM cycles a wait may last
 };
 
 }  // namespace libp_b200
@@ -120,6 +122,11 @@ struct libp_comm_s {
   std::vector<char*> peer_win;                  // peer_win[r] = rank r's window in my address space (self included)
   libp_b200::dev_buf<char*> d_peer_win;         // the same table on the device
   unsigned long long* d_ar_seq = nullptr;       // device counter of window all-reduces
+  // every in-kernel wait on a peer's flag is bounded: on a time-out the kernel sets this word and stops waiting
+  // (results of the communicator are then invalid; libp_comm_p2p_status reports it, solves check it)
+  int* d_p2p_err = nullptr;
+  long long p2p_timeout_cycles = 0;
+  int p2p_error() const;                        // current value of the error word (synchronises the device)
   size_t win_alloc(size_t bytes);               // offset of a new 256-byte aligned region of my window
   // host collectives with size==1 shortcuts
   void alltoall(const void* send, void* recv, size_t bytes_per_rank) const;

@@ -172,6 +172,30 @@ void exchange_start(libp_ogs_s& o, T* buf, int K, int trans, cudaStream_t s) {
     extract_kernel<T><<<grid_for((size_t)ex.Nsend() * K), kBlock, 0, cs>>>(ex.Nsend(), K, ex.d_sendIds.p, buf, sendBuf);
     CUDA_CHECK(cudaGetLastError());
   }
+  if (c.nccl == nullptr) {
+    // no device transport for generic types / ops (a communicator without NCCL, e.g. several ranks sharing one
+    // GPU): stage the exchange through the host collectives.  Setup-time traffic only; the hot path (FP64, k = 1)
+    // uses the peer window.
+    LIBP_CHECK(c.has_host, "exchange needs NCCL or host collectives");
+    const size_t eb = (size_t)K * sizeof(T);
+    std::vector<char> hs((size_t)ex.Nsend() * eb), hr((size_t)ex.Nrecv() * eb);
+    if (!hs.empty()) CUDA_CHECK(cudaMemcpyAsync(hs.data(), sendBuf, hs.size(), cudaMemcpyDeviceToHost, cs));
+    CUDA_CHECK(cudaStreamSynchronize(cs));
+    std::vector<int64_t> sc((size_t)c.size, 0), so((size_t)c.size, 0), rc((size_t)c.size, 0), ro((size_t)c.size, 0);
+    for (size_t r = 0; r < ex.sendRanks.size(); ++r) {
+      sc[(size_t)ex.sendRanks[r]] = (int64_t)ex.sendCounts[r] * (int64_t)eb;
+      so[(size_t)ex.sendRanks[r]] = (int64_t)ex.sendOffsets[r] * (int64_t)eb;
+    }
+    for (size_t r = 0; r < ex.recvRanks.size(); ++r) {
+      rc[(size_t)ex.recvRanks[r]] = (int64_t)ex.recvCounts[r] * (int64_t)eb;
+      ro[(size_t)ex.recvRanks[r]] = (int64_t)ex.recvOffsets[r] * (int64_t)eb;
+    }
+    c.alltoallv(hs.data(), sc.data(), so.data(), hr.data(), rc.data(), ro.data());
+    if (!hr.empty()) CUDA_CHECK(cudaMemcpyAsync(buf + (size_t)Nhalo * K, hr.data(), hr.size(), cudaMemcpyHostToDevice, cs));
+    CUDA_CHECK(cudaStreamSynchronize(cs));
+    CUDA_CHECK(cudaEventRecord(o.ev_done, cs));
+    return;
+  }
   c.group_start();
   for (size_t r = 0; r < ex.recvRanks.size(); ++r)
     c.recv(buf + (size_t)Nhalo * K + (size_t)ex.recvOffsets[r] * K, (size_t)ex.recvCounts[r] * K * sizeof(T),
@@ -290,13 +314,15 @@ struct P2PPackArgs {
   unsigned long long* d_seq;
   unsigned int* d_done;
   int rank, size;
+  int* err;
+  long long timeout;
 };
 __global__ void __launch_bounds__(kBlock) p2p_pack_send_kernel(P2PPackArgs a) {
   const unsigned long long seq = *a.d_seq + 1;
   const int par = (int)(seq & 1);
   // the buffer of this parity was last used by exchange seq-2: wait until every destination consumed it
   if (seq > 2 && threadIdx.x < a.nSendRanks)
-    while (ld_acquire_sys(&a.acks[par * a.size + a.sendRanks[threadIdx.x]]) < seq - 2) { }
+    wait_ge_sys(&a.acks[par * a.size + a.sendRanks[threadIdx.x]], seq - 2, a.err, a.timeout);
   __syncthreads();
   double* const* dst = a.dst[par];
   for (dlong n = blockIdx.x * kBlock + threadIdx.x; n < a.Nsend; n += gridDim.x * kBlock)
@@ -331,13 +357,15 @@ struct P2PUnpackArgs {
   const unsigned long long* d_seq;
   unsigned int* d_done;
   int rank, size;
+  int* err;
+  long long timeout;
 };
 template <bool kTrans>
 __global__ void __launch_bounds__(kBlock) p2p_wait_unpack_kernel(P2PUnpackArgs a) {
   const unsigned long long seq = *a.d_seq;  // already advanced by this exchange's pack kernel
   const int par = (int)(seq & 1);
   if (threadIdx.x < a.nRecvRanks)
-    while (ld_acquire_sys(&a.flags[par * a.size + a.recvRanks[threadIdx.x]]) < seq) { }
+    wait_ge_sys(&a.flags[par * a.size + a.recvRanks[threadIdx.x]], seq, a.err, a.timeout);
   __syncthreads();
   const double* recv = a.recv + (size_t)par * a.cap;
   for (dlong row = a.rowBegin + blockIdx.x * kBlock + threadIdx.x; row < a.rowEnd; row += gridDim.x * kBlock) {
@@ -383,6 +411,8 @@ void p2p_start(libp_ogs_s& o, double* v, int flavour, cudaStream_t s) {
   a.d_done = x.d_done;
   a.rank = c.rank;
   a.size = c.size;
+  a.err = c.d_p2p_err;
+  a.timeout = c.p2p_timeout_cycles;
   int g = (int)std::min<size_t>(((size_t)std::max<dlong>(a.Nsend, 1) + kBlock - 1) / kBlock, 64);
   p2p_pack_send_kernel<<<g, kBlock, 0, cs>>>(a);
   CUDA_CHECK(cudaGetLastError());
@@ -411,6 +441,8 @@ void p2p_finish(libp_ogs_s& o, double* v, int flavour, cudaStream_t s) {
   a.d_done = x.d_done + 1;
   a.rank = c.rank;
   a.size = c.size;
+  a.err = c.d_p2p_err;
+  a.timeout = c.p2p_timeout_cycles;
   const dlong nrows = std::max<dlong>(a.rowEnd - a.rowBegin, 1);
   int g = (int)std::min<size_t>(((size_t)nrows + kBlock - 1) / kBlock, 64);
   if (flavour == 0) p2p_wait_unpack_kernel<false><<<g, kBlock, 0, s>>>(a);

@@ -22,6 +22,26 @@ __device__ __forceinline__ void st_peer(double* p, double v) {
   asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
+// Bounded wait for *p >= target.  Returns false (and raises the communicator's error word) when it lasted longer than
+// `timeout` SM cycles or another wait already failed: a peer that threw between collectives, or a protocol bug, then
+// shows up as an error instead of a hung GPU.
+__device__ __forceinline__ bool wait_ge_sys(const unsigned long long* p, unsigned long long target, int* err,
+                                            long long timeout) {
+  if (ld_acquire_sys(p) >= target) return true;
+  const long long t0 = clock64();
+  unsigned it = 0;
+  while (ld_acquire_sys(p) < target) {
+    if ((++it & 0xff) == 0) {
+      if (err != nullptr && *reinterpret_cast<volatile int*>(err) != 0) return false;
+      if (timeout > 0 && clock64() - t0 > timeout) {
+        if (err != nullptr) atomicExch(err, 1);
+        return false;
+      }
+    }
+  }
+  return true;
+}
+
 // All-reduce (sum) of n <= kWinMaxVals doubles held in shared memory `vals`, by ONE thread block per rank.
 // Every rank stores its values into every peer's mailbox, publishes the sequence number, waits for all peers'
 // flags and sums in rank order - every rank gets the bit-identical result.  Two mailbox parities suffice: a rank
@@ -41,7 +61,7 @@ __device__ __forceinline__ void win_allreduce_sum(const WinAR& w, double* vals, 
   }
   WinHeader* me = reinterpret_cast<WinHeader*>(w.peer_win[w.rank]);
   if (t < w.size) {
-    while (ld_acquire_sys(&me->mflag[par][t]) < seq) { }
+    wait_ge_sys(&me->mflag[par][t], seq, w.err, w.timeout);
   }
   __syncthreads();
   if (t < n) {

@@ -457,7 +457,10 @@ extern "C" int libp_pcg_solve(libp_pcg_t pcg, libp_elliptic_t A, libp_precon_t M
   // communicator has one, otherwise local sums -> NCCL all-reduce -> scalar kernel
   const bool win = multi && comm->p2p;
   WinAR w{};
-  if (win) { w.rank = comm->rank; w.size = comm->size; w.peer_win = comm->d_peer_win.p; w.seq = comm->d_ar_seq; }
+  if (win) {
+    w.rank = comm->rank; w.size = comm->size; w.peer_win = comm->d_peer_win.p; w.seq = comm->d_ar_seq;
+    w.err = comm->d_p2p_err; w.timeout = comm->p2p_timeout_cycles;
+  }
   auto stage = [&](int st, const double* partials, int n0, int n1, int n2, int with_beta) {
     double* hist = pcg->d_hist.p;
     const int mh = maxit + 2;
@@ -524,6 +527,7 @@ extern "C" int libp_pcg_solve(libp_pcg_t pcg, libp_elliptic_t A, libp_precon_t M
       if (pcg->h_sc->done) break;
     }
   }
+  LIBP_CHECK(!(win && comm->p2p_error()), "a peer-window wait timed out (a peer rank failed or diverged)");
   const int it = pcg->h_sc->iter;
   std::vector<double> hh((size_t)it + 1);
   CUDA_CHECK(cudaMemcpy(hh.data(), pcg->d_hist.p, sizeof(double) * ((size_t)it + 1), cudaMemcpyDeviceToHost));

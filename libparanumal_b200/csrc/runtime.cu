@@ -107,6 +107,7 @@ extern "C" int libp_comm_free(libp_comm_t comm) {
         if (r != comm->rank && comm->peer_win[r]) cudaIpcCloseMemHandle(comm->peer_win[r]);
       cudaFree(comm->win);
       cudaFree(comm->d_ar_seq);
+      if (comm->d_p2p_err) cudaFree(comm->d_p2p_err);
     }
     delete comm;
   }
@@ -205,8 +206,40 @@ extern "C" int libp_comm_p2p_init(libp_comm_t comm, size_t window_bytes) {
   comm->d_peer_win.upload(comm->peer_win);
   CUDA_CHECK(cudaMalloc(&comm->d_ar_seq, sizeof(unsigned long long)));
   CUDA_CHECK(cudaMemset(comm->d_ar_seq, 0, sizeof(unsigned long long)));
+  CUDA_CHECK(cudaMalloc(&comm->d_p2p_err, sizeof(int)));
+  CUDA_CHECK(cudaMemset(comm->d_p2p_err, 0, sizeof(int)));
+  {
+    // bound of every in-kernel wait on a peer (LIBP_P2P_TIMEOUT_MS, default 30 s), in SM cycles
+    const char* e = getenv("LIBP_P2P_TIMEOUT_MS");
+    const long long ms = (e && atoll(e) > 0) ? atoll(e) : 30000;
+    int khz = 0, dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+    comm->p2p_timeout_cycles = ms * (long long)(khz > 0 ? khz : 1500000);
+  }
   CUDA_CHECK(cudaDeviceSynchronize());
   comm->p2p = true;
+  LIBP_API_END
+}
+
+int libp_comm_s::p2p_error() const {
+  if (!d_p2p_err) return 0;
+  int e = 0;
+  CUDA_CHECK(cudaMemcpy(&e, d_p2p_err, sizeof(int), cudaMemcpyDeviceToHost));
+  return e;
+}
+
+extern "C" int libp_comm_p2p_status(libp_comm_t comm, int* timed_out) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(comm && timed_out, "null argument");
+  *timed_out = comm->p2p_error();
+  LIBP_API_END
+}
+
+extern "C" int libp_comm_p2p_reset(libp_comm_t comm) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(comm, "null comm");
+  if (comm->d_p2p_err) CUDA_CHECK(cudaMemset(comm->d_p2p_err, 0, sizeof(int)));
   LIBP_API_END
 }
 
@@ -244,6 +277,16 @@ void libp_comm_s::allreduce_f64(double* inout, int n, int op) const {
 }
 void libp_comm_s::allreduce_dev(double* buf, int n, int op, cudaStream_t s) const {
   if (size == 1) return;
+  if (!nccl && has_host && host.allreduce_f64 && op != LIBP_MUL) {
+    // no NCCL (e.g. several ranks on one GPU): stage the few doubles through the host collectives
+    std::vector<double> h((size_t)n);
+    CUDA_CHECK(cudaMemcpyAsync(h.data(), buf, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    allreduce_f64(h.data(), n, op);
+    CUDA_CHECK(cudaMemcpyAsync(buf, h.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    return;
+  }
   LIBP_CHECK(nccl, "communicator has size>1 but NCCL was not initialised (libp_comm_nccl_init)");
   int nop = op == LIBP_ADD ? ncclSum_ : op == LIBP_MUL ? ncclProd_ : op == LIBP_MAX ? ncclMax_ : ncclMin_;
   nccl_check(::nccl().AllReduce(buf, buf, (size_t)n, ncclFloat64_, nop, nccl, s), "AllReduce");

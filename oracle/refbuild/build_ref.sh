@@ -69,3 +69,12 @@ g++ -fopenmp -O2 -std=c++17 -march=native -Wno-unused-function \
   -L"$W/libs" -lparAlmond -llinearSolver -lmesh -lparAdogs -logs -llinAlg -lcore \
   "$W/libmpistub.a" -Wl,-rpath,"$BL" -L"$BL" -l:"$BLSO" -Wl,-rpath,"$W/occa/lib" -L"$W/occa/lib" -locca
 echo "mg dump driver built: $OUT/dump_mg_driver"
+# 5. multi-rank dump driver (our own code, oracle/refbuild/dump_mr_driver.cpp; run under mpirun_stub.sh)
+g++ -fopenmp -O2 -std=c++17 -march=native -Wno-unused-function \
+  -DLIBP_DIR="\"$W\"" \
+  -I"$HERE/mpistub" -include "$W/lapack_rename.h" -I"$W/include" -I"$W/occa/include" -I"$W/solvers/elliptic" \
+  -o "$OUT/dump_mr_driver" "$HERE/dump_mr_driver.cpp" \
+  "$W/solvers/elliptic/libelliptic.a" \
+  -L"$W/libs" -lparAlmond -llinearSolver -lmesh -lparAdogs -logs -llinAlg -lcore \
+  "$W/libmpistub.a" -Wl,-rpath,"$BL" -L"$BL" -l:"$BLSO" -Wl,-rpath,"$W/occa/lib" -L"$W/occa/lib" -locca
+echo "multi-rank dump driver built: $OUT/dump_mr_driver"

@@ -32,7 +32,8 @@ def _worker(rank, size, port, N, n, flag, outq):
         from libparanumal_b200.api import Comm, Ogs
         from libparanumal_b200.box_mesh import BoxMesh
         ctypes.CDLL("libc.so.6").srand(1)  # every MPI rank of the reference is a fresh process
-        mesh = BoxMesh(N, n, n, n, rank, size, flag, geometry=False)
+        box = (n, n, n) if np.isscalar(n) else tuple(n)
+        mesh = BoxMesh(N, box[0], box[1], box[2], rank, size, flag, geometry=False)
         _, ids = mesh.masked_global_ids()
         ids = ids.numpy().copy()
         comm = Comm(rank, size)
@@ -92,6 +93,48 @@ def test_multirank_ogs_setup_matches_oracle(size, N, n, flag):
     # global invariants: every unmasked global node owned exactly once
     nglobal = len(np.unique(np.abs(np.concatenate(ids))[np.concatenate(ids) != 0]))
     assert ref[0].NgatherGlobal == nglobal
+
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MR_NAMES = ["mr_n3_e4x4x4_p2", "mr_n3_e4x4x4_p4", "mr_n3_e4x4x4_p8", "mr_n2_e5x4x3_p2", "mr_n2_e5x4x3_p4", "mr_n2_e5x4x3_p8",
+            "mr_n7_e2x2x2_p8", "mr_n7_e4x2x2_p2", "mr_n2_e4x4x4_periodic_p4"]
+
+
+@pytest.mark.parametrize("name", MR_NAMES)
+def test_multirank_ogs_setup_matches_multirank_reference(name):
+    """The C-ABI host setup on P processes (gloo host collectives standing in for MPI) against dumps of the UNMODIFIED
+    reference run on P ranks (tests/golden/mr_*.npz, oracle/refbuild/make_golden_mr.py): box decomposition, owner
+    choice, counters, gatherLocal / gatherHalo / postmpi maps, pairwise send lists, neighbour ranks, counts and
+    offsets, GlobalToLocal, element lists - all bit-exact (libs/ogs/ogsSetup.cpp:69-886, ogsPairwise.cpp:194-415)."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    N, box, flag, size = int(g["config_N"]), [int(x) for x in g["config_box"]], int(g["config_flag"]), int(g["config_P"])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, size, port, N, box, flag, q)) for r in range(size)]
+    for p in procs:
+        p.start()
+    results = {}
+    for _ in range(size):
+        r = q.get(timeout=180)
+        results[r["rank"]] = r
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(size):
+        got, k = results[r], f"r{r}_"
+        assert got["counts"] == [int(x) for x in g[k + "ogs_counts"][:7]]
+        assert np.array_equal(got["ids"], g[k + "maskedGlobalIds"])
+        assert np.array_equal(got["g2l"], g[k + "GlobalToLocal"])
+        for key, ref in (("local", "gatherLocal"), ("halo", "gatherHalo"), ("postmpi", "pw_postmpi")):
+            for nm in ("rowStartsN", "rowStartsT", "colIdsN", "colIdsT"):
+                assert np.array_equal(got[key][nm], g[k + ref + "_" + nm]), (r, key, nm)
+        for key, f in (("exN", "N"), ("exT", "T")):
+            assert np.array_equal(got[key]["sendIds"], g[k + "pw_sendIds" + f])
+            for nm in ("sendRanks", "sendCounts", "recvRanks", "recvCounts", "sendOffsets", "recvOffsets"):
+                assert np.array_equal(got[key][nm], g[k + "pw_" + nm + f]), (r, key, nm)
+        assert np.array_equal(got["lists"][0], g[k + "localGatherElementList"])
+        assert np.array_equal(got["lists"][1], g[k + "globalGatherElementList"])
 
 
 def _csr_worker(rank, size, port, outq):

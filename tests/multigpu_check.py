@@ -125,6 +125,19 @@ def main():
     commN = Comm(rank, world, gloo); commN.init_nccl()
     commP = Comm(rank, world, gloo); commP.init_nccl()
     assert commP.init_p2p(required=True) and commP.p2p and not commN.p2p
+    # (0) against the UNMODIFIED reference run on the same number of ranks (tests/golden/mr_*.npz): maps bit-exact,
+    # Operator(q) <= 1e-12 on the reference's arrays, halo exchange exact, PCG iterations / history / solution -
+    # through NCCL and through the peer window
+    import glob
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from mr_gpu_worker import run_rank
+    for f in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", f"mr_*_p{world}.npz"))):
+        name = os.path.basename(f)[:-4]
+        for cname, comm in (("nccl", commN), ("p2p", commP)):
+            res = run_rank(rank, world, name, lr, comm=comm, group=gloo)
+            if rank == 0:
+                print(f"multigpu vs multi-rank reference ok: {name} [{cname}] {res}", flush=True)
+        dist.barrier()
     for N, n, lam, flag in [(3, 6, 1.0, 1), (7, 4, 0.0, 1), (2, 5, 0.5, -1), (7, 6, 1.0, 1)]:
         probs = {}
         for name, comm in (("nccl", commN), ("p2p", commP)):

@@ -333,7 +333,7 @@ def main():
                 "traffic": traffic, "traffic_source": traffic_src, "kernel": kname, "kernel_ms": kms,
                 "zero_fill_ms": zms, "step_frac": (alg_bytes / (ms / steps * 1e-3) / 1e9) / peak,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "elements_per_launch": E,
-                "launches_per_apply": (2 if world == 1 else 3)}
+                "launches_per_apply": (1 if world == 1 else 2)}
 
     # ------------------------------------------------------------------ e2e: host buffers through the C ABI
     # Each step copies that step's q from pinned host memory, applies the operator through the C ABI and
@@ -393,9 +393,9 @@ def main():
                "path": "pinned host q -> H2D -> libp_elliptic_operator -> D2H Aq (double-buffered over steps)"}
         del hq, hA, dq, dA
 
-    # launches inside the timed region per step: single rank = zero-fill kernel + 2 Ax kernels (the two halves of the
-    # local element list); sharded = zero-fill + 3 Ax + halo pack/send + wait/unpack + combine pack + combine unpack
-    launches_per_step = 3 if world == 1 else 8
+    # launches inside the timed region per step: single rank = zero-fill kernel + 1 Ax kernel;
+    # sharded = zero-fill + 2 Ax (local | boundary elements) + halo pack/send + wait/unpack + combine pack + combine unpack
+    launches_per_step = 2 if world == 1 else 7
 
     # ------------------------------------------------------------------ Jacobi-PCG on the screened problem
     pcg = None

@@ -37,32 +37,42 @@ namespace {
 #define LIBP_AX_HINT true
 #endif
 constexpr int kMaxNq = 9;
-__constant__ double c_D[kMaxNq * kMaxNq];  // D[i*Nq+m] = phi'_m(r_i), loaded per launch (D2D async)
+constexpr int kMaxH = kMaxNq / 2;
+}  // namespace
+namespace libp_b200 {
+// Derivative matrix and its even-odd factors, passed to the kernels BY VALUE as a __grid_constant__ parameter (the
+// parameter bank serves compile-time indexed DFMA operands exactly like __constant__ memory did, without any
+// process-global state: handles of different orders / streams / threads cannot disturb each other).
+//   D[i*Nq+m] = phi'_m(r_i)
 // Even-odd factors of a centro-antisymmetric D (GLL: D[N-i][N-m] = -D[i][m]), H = Nq/2:
-//   c_De[i*H+m] = (D[i][m] + D[i][N-m])/2,  c_Do[i*H+m] = (D[i][m] - D[i][N-m])/2      (i,m < H)
-//   c_Dc[i] = D[i][c], c_Dr[m] = D[c][m] for the centre node c = H of odd Nq.
+//   De[i*H+m] = (D[i][m] + D[i][N-m])/2,  Do[i*H+m] = (D[i][m] - D[i][N-m])/2      (i,m < H)
+//   Dc[i] = D[i][c], Dr[m] = D[c][m] for the centre node c = H of odd Nq.
 // They halve the constants a thread keeps in (uniform) registers and cut a pencil contraction from
 // Nq^2 DFMAs to Nq^2/2 DFMAs + 2*Nq DADDs.  The same factors serve D^T ((D^T)e = Do^T, (D^T)o = De^T).
-constexpr int kMaxH = kMaxNq / 2;
-__constant__ double c_De[kMaxH * kMaxH], c_Do[kMaxH * kMaxH], c_Dc[kMaxH], c_Dr[kMaxH];
-
-__global__ void even_odd_factors_kernel(int Nq, const double* __restrict__ D, double* __restrict__ out) {
-  const int H = Nq / 2, N = Nq - 1, t = threadIdx.x;
-  double* De = out; double* Do = out + kMaxH * kMaxH; double* Dc = Do + kMaxH * kMaxH; double* Dr = Dc + kMaxH;
-  if (t < H * H) {
-    const int i = t / H, m = t - i * H;
-    De[t] = 0.5 * (D[i * Nq + m] + D[i * Nq + N - m]);
-    Do[t] = 0.5 * (D[i * Nq + m] - D[i * Nq + N - m]);
-  }
-  if (t < H) {
-    Dc[t] = (Nq & 1) ? D[t * Nq + H] : 0.0;
-    Dr[t] = (Nq & 1) ? D[H * Nq + t] : 0.0;
+void AxD::set(int Nq, const double* Dh) {
+  const int H = Nq / 2, N = Nq - 1;
+  for (int n = 0; n < Nq * Nq; ++n) D[n] = Dh[n];
+  for (int i = 0; i < H; ++i)
+    for (int m = 0; m < H; ++m) {
+      De[i * H + m] = 0.5 * (Dh[i * Nq + m] + Dh[i * Nq + N - m]);
+      Do[i * H + m] = 0.5 * (Dh[i * Nq + m] - Dh[i * Nq + N - m]);
+    }
+  for (int i = 0; i < H; ++i) {
+    Dc[i] = (Nq & 1) ? Dh[i * Nq + H] : 0.0;
+    Dr[i] = (Nq & 1) ? Dh[H * Nq + i] : 0.0;
   }
 }
+}  // namespace libp_b200
+namespace {
+#define c_D dc.D
+#define c_De dc.De
+#define c_Do dc.Do
+#define c_Dc dc.Dc
+#define c_Dr dc.Dr
 
 // o = D v (kT = false) or o = D^T v (kT = true) on a register pencil.
 template <int Nq, bool kSym, bool kT>
-__device__ __forceinline__ void pencil_apply(const dfloat (&v)[Nq], dfloat (&o)[Nq]) {
+__device__ __forceinline__ void pencil_apply(const AxD& dc, const dfloat (&v)[Nq], dfloat (&o)[Nq]) {
   if (!kSym) {
 #pragma unroll
     for (int i = 0; i < Nq; ++i) {
@@ -116,7 +126,7 @@ __global__ void __launch_bounds__(AxCfg<Nq>::Threads)
 ax_hex3d_kernel(const dlong Nelements, const dlong* __restrict__ elementList, const dlong* __restrict__ G2L,
                 const dfloat* __restrict__ wJ, const dfloat* __restrict__ ggeo, const dfloat lambda,
                 const dfloat* __restrict__ q, dfloat* __restrict__ Aq, dfloat* __restrict__ dotPartials,
-                const int* __restrict__ doneFlag) {
+                const int* __restrict__ doneFlag, const __grid_constant__ AxD dc) {
   if (doneFlag != nullptr && *doneFlag) return;  // converged solver: the iteration body is a no-op
   using C = AxCfg<Nq>;
   constexpr int Nq2 = C::Nq2, Np = C::Np, LD = C::LD;
@@ -385,7 +395,7 @@ __global__ void __launch_bounds__(AxT<Nq>::Threads, (Nq == 8) ? kMinB : AxT<Nq>:
 ax_hex3d_t_kernel(const dlong Nelements, const dlong* __restrict__ elementList, const dlong* __restrict__ G2L,
                   const dfloat* __restrict__ wJ, const dfloat* __restrict__ ggeo, const dfloat lambda,
                   const dfloat* __restrict__ q, dfloat* __restrict__ Aq, dfloat* __restrict__ dotPartials,
-                  const int* __restrict__ doneFlag, const ZeroAhead za = ZeroAhead()) {
+                  const int* __restrict__ doneFlag, const __grid_constant__ AxD dc, const ZeroAhead za = ZeroAhead()) {
   if (doneFlag != nullptr && *doneFlag) return;
   using C = AxT<Nq>;
   // zero-ahead relies on blocks being dispatched in blockIdx order (so that the producers a block waits for are
@@ -460,18 +470,18 @@ ax_hex3d_t_kernel(const dlong Nelements, const dlong* __restrict__ elementList, 
     for (int k = 0; k < Nq; ++k) s_u[sC + k * SS] = r_q[k];
   }
   dfloat r_t[Nq];  // qt, later Gqt
-  pencil_apply<Nq, kSym, false>(r_q, r_t);
+  pencil_apply<Nq, kSym, false>(dc, r_q, r_t);
   __syncthreads();
 
   // ---- phase 1: r-derivative on i-pencils (layout A), s-derivative on j-pencils (layout B)
   if (valid) {
     dfloat v[Nq], o[Nq];
     load_row<Nq>(&s_u[sA], v);
-    pencil_apply<Nq, kSym, false>(v, o);
+    pencil_apply<Nq, kSym, false>(dc, v, o);
     store_row<Nq>(&s_r[sA], o);
 #pragma unroll
     for (int m = 0; m < Nq; ++m) v[m] = s_u[sB + m * LD];
-    pencil_apply<Nq, kSym, false>(v, o);
+    pencil_apply<Nq, kSym, false>(dc, v, o);
 #pragma unroll
     for (int j = 0; j < Nq; ++j) s_s[sB + j * LD] = o[j];
   }
@@ -498,7 +508,7 @@ ax_hex3d_t_kernel(const dlong Nelements, const dlong* __restrict__ elementList, 
   }
   {
     dfloat o[Nq];
-    pencil_apply<Nq, kSym, true>(r_t, o);
+    pencil_apply<Nq, kSym, true>(dc, r_t, o);
 #pragma unroll
     for (int k = 0; k < Nq; ++k) r_Aq[k] += o[k];
   }
@@ -508,11 +518,11 @@ ax_hex3d_t_kernel(const dlong Nelements, const dlong* __restrict__ elementList, 
   if (valid) {
     dfloat v[Nq], o[Nq];
     load_row<Nq>(&s_r[sA], v);
-    pencil_apply<Nq, kSym, true>(v, o);
+    pencil_apply<Nq, kSym, true>(dc, v, o);
     store_row<Nq>(&s_r[sA], o);
 #pragma unroll
     for (int m = 0; m < Nq; ++m) v[m] = s_s[sB + m * LD];
-    pencil_apply<Nq, kSym, true>(v, o);
+    pencil_apply<Nq, kSym, true>(dc, v, o);
 #pragma unroll
     for (int j = 0; j < Nq; ++j) s_s[sB + j * LD] = o[j];
   }
@@ -577,17 +587,17 @@ int g_pf = 2, g_hint = 1, g_minb = 6;  // tuning state of variant 1 (libp_ax_hex
 template <int Nq, bool G, bool F, bool DOT, bool SYM>
 void launch_t(int grid, dlong Nelements, const dlong* elementList, const dlong* G2L, const dfloat* wJ,
               const dfloat* ggeo, dfloat lambda, const dfloat* q, dfloat* Aq, dfloat* dotPartials,
-              const int* doneFlag, const ZeroAhead* za, cudaStream_t s) {
+              const int* doneFlag, const ZeroAhead* za, cudaStream_t s, const AxD& dc) {
   if constexpr (G && F && SYM) {
     if (za != nullptr) {
       ax_hex3d_t_kernel<Nq, G, F, DOT, AxT<Nq>::PF, LIBP_AX_HINT, LIBP_AX_MINB, SYM, true>
-          <<<grid, AxT<Nq>::Threads, 0, s>>>(Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag, *za);
+          <<<grid, AxT<Nq>::Threads, 0, s>>>(Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag, dc, *za);
       return;
     }
   }
 #define GOT(PF, H, MB)                                                                                        \
   ax_hex3d_t_kernel<Nq, G, F, DOT, PF, H, MB, SYM><<<grid, AxT<Nq>::Threads, 0, s>>>(                         \
-      Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag)
+      Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag, dc)
 #ifdef LIBP_AX_TUNE_GRID
   if constexpr (Nq == 8 && G && F && SYM && !DOT) {
 #define ROW(PF, H)                                        \
@@ -609,11 +619,11 @@ void launch_t(int grid, dlong Nelements, const dlong* elementList, const dlong* 
 template <int Nq>
 int launch(bool gather, bool fused, bool sym, dlong Nelements, const dlong* elementList, const dlong* G2L,
            const dfloat* wJ, const dfloat* ggeo, dfloat lambda, const dfloat* q, dfloat* Aq, dfloat* dotPartials,
-           const int* doneFlag, const ZeroAhead* za, cudaStream_t s) {
+           const int* doneFlag, const ZeroAhead* za, cudaStream_t s, const AxD& dc) {
   using C = AxCfg<Nq>;
   const int epb = (g_variant == 1) ? AxT<Nq>::EPB : C::EPB;
   const int grid = (int)((Nelements + epb - 1) / epb);
-#define ARGS grid, Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag, za, s
+#define ARGS grid, Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag, za, s, dc
 #define GO(G, F, DOT)                                                                                         \
   do {                                                                                                        \
     if (g_variant == 1) {                                                                                     \
@@ -621,7 +631,7 @@ int launch(bool gather, bool fused, bool sym, dlong Nelements, const dlong* elem
       else launch_t<Nq, G, F, DOT, false>(ARGS);                                                              \
     } else {                                                                                                  \
       ax_hex3d_kernel<Nq, G, F, DOT><<<grid, C::Threads, 0, s>>>(Nelements, elementList, G2L, wJ, ggeo, lambda, \
-                                                                 q, Aq, dotPartials, doneFlag);               \
+                                                                 q, Aq, dotPartials, doneFlag, dc);           \
     }                                                                                                         \
   } while (0)
   if (dotPartials) {
@@ -639,46 +649,24 @@ int launch(bool gather, bool fused, bool sym, dlong Nelements, const dlong* elem
   return grid;
 }
 
-const dfloat* g_cD_owner = nullptr;  // device pointer whose contents currently sit in c_D (+ even-odd factors)
-int g_cD_nq = 0;
-bool g_cD_sym = false;
-dfloat* g_eo_scratch = nullptr;  // device staging of the even-odd factors
-
 }  // namespace
 
 namespace libp_b200 {
 
-// trusted_D: the caller guarantees D is immutable (operator handles), so the constant bank is only
-// reloaded when a different D pointer / order is used.  sym: D was verified centro-antisymmetric
+// dc: host copy of D (+ even-odd factors), passed to the kernel by value.  sym: D was verified centro-antisymmetric
 // (libp_elliptic_create does that once), which enables the even-odd contractions.
 // Returns the number of blocks launched (= number of dotPartials written when dotPartials != nullptr).
-int ax_hex3d_launch(int Nq, bool fused, bool trusted_D, bool sym, dlong Nelements, const dlong* elementList,
-                    const dlong* G2L, const dfloat* wJ, const dfloat* ggeo, const dfloat* D, dfloat lambda,
+int ax_hex3d_launch(int Nq, bool fused, const AxD& dc, bool sym, dlong Nelements, const dlong* elementList,
+                    const dlong* G2L, const dfloat* wJ, const dfloat* ggeo, dfloat lambda,
                     const dfloat* q, dfloat* Aq, dfloat* dotPartials, const int* doneFlag, cudaStream_t s,
                     const ZeroAhead* za) {
   LIBP_CHECK(Nq >= 2 && Nq <= kMaxNq, "Nq must be in [2, 9]");
   LIBP_CHECK(za == nullptr || (fused && sym && g_variant == 1), "zero-ahead needs the fused even-odd kernel");
   LIBP_CHECK(!fused || G2L != nullptr, "fused gather needs GlobalToLocal");
   if (Nelements <= 0) return 0;
-  if (!(trusted_D && g_cD_owner == D && g_cD_nq == Nq && (g_cD_sym || !sym))) {
-    CUDA_CHECK(cudaMemcpyToSymbolAsync(c_D, D, sizeof(dfloat) * Nq * Nq, 0, cudaMemcpyDeviceToDevice, s));
-    if (sym) {
-      constexpr int HH = kMaxH * kMaxH;
-      if (!g_eo_scratch) CUDA_CHECK(cudaMalloc(&g_eo_scratch, sizeof(dfloat) * (2 * HH + 2 * kMaxH)));
-      even_odd_factors_kernel<<<1, 32, 0, s>>>(Nq, D, g_eo_scratch);
-      CUDA_CHECK(cudaGetLastError());
-      CUDA_CHECK(cudaMemcpyToSymbolAsync(c_De, g_eo_scratch, sizeof(dfloat) * HH, 0, cudaMemcpyDeviceToDevice, s));
-      CUDA_CHECK(cudaMemcpyToSymbolAsync(c_Do, g_eo_scratch + HH, sizeof(dfloat) * HH, 0, cudaMemcpyDeviceToDevice, s));
-      CUDA_CHECK(cudaMemcpyToSymbolAsync(c_Dc, g_eo_scratch + 2 * HH, sizeof(dfloat) * kMaxH, 0, cudaMemcpyDeviceToDevice, s));
-      CUDA_CHECK(cudaMemcpyToSymbolAsync(c_Dr, g_eo_scratch + 2 * HH + kMaxH, sizeof(dfloat) * kMaxH, 0, cudaMemcpyDeviceToDevice, s));
-    }
-    g_cD_owner = trusted_D ? D : nullptr;
-    g_cD_nq = Nq;
-    g_cD_sym = sym;
-  }
   const bool gather = G2L != nullptr;
   switch (Nq) {
-#define CASE(n) case n: return launch<n>(gather, fused, sym, Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag, za, s);
+#define CASE(n) case n: return launch<n>(gather, fused, sym, Nelements, elementList, G2L, wJ, ggeo, lambda, q, Aq, dotPartials, doneFlag, za, s, dc);
     CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9)
 #undef CASE
   }
@@ -714,15 +702,22 @@ int ax_hex3d_blocks(int Nq, dlong Nelements) {
 }  // namespace libp_b200
 
 // Registry of derivative matrices the caller promised to keep immutable (libp_ax_hex3d_register_D):
-// device pointer -> (Nq, centro-antisymmetric?).  Registered matrices skip the per-call constant-bank
-// reload and, when they are GLL matrices, run the even-odd kernels.
+// device pointer -> host copy of D with its even-odd factors and whether it is centro-antisymmetric.  Registered
+// matrices skip the per-call device-to-host read of D and, when they are GLL matrices, run the even-odd kernels.
 namespace {
-struct RegisteredD { const dfloat* ptr; int Nq; bool sym; };
+struct RegisteredD { const dfloat* ptr; int Nq; bool sym; AxD dc; };
 std::vector<RegisteredD> g_registry;
 const RegisteredD* find_registered(const dfloat* D, int Nq) {
   for (const auto& r : g_registry)
     if (r.ptr == D && r.Nq == Nq) return &r;
   return nullptr;
+}
+// raw entry points with an unregistered D: read it back (stream-ordered, then synchronise) - correct but slow
+void fetch_D(int Nq, const dfloat* D, cudaStream_t s, AxD& dc) {
+  double hD[kMaxNq * kMaxNq];
+  CUDA_CHECK(cudaMemcpyAsync(hD, D, sizeof(double) * Nq * Nq, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  dc.set(Nq, hD);
 }
 }  // namespace
 
@@ -731,10 +726,11 @@ extern "C" int libp_ax_hex3d_register_D(int Nq, const libp_dfloat* D) {
   LIBP_CHECK(Nq >= 2 && Nq <= kMaxNq && D, "bad argument");
   double hD[kMaxNq * kMaxNq];
   CUDA_CHECK(cudaMemcpy(hD, D, sizeof(double) * Nq * Nq, cudaMemcpyDeviceToHost));
-  const bool sym = ax_hex3d_D_is_centro_antisymmetric(Nq, hD);
-  for (auto& r : g_registry)
-    if (r.ptr == D) { r.Nq = Nq; r.sym = sym; if (g_cD_owner == D) g_cD_owner = nullptr; return LIBP_SUCCESS; }
-  g_registry.push_back({D, Nq, sym});
+  RegisteredD r{D, Nq, ax_hex3d_D_is_centro_antisymmetric(Nq, hD), AxD()};
+  r.dc.set(Nq, hD);
+  for (auto& e : g_registry)
+    if (e.ptr == D) { e = r; return LIBP_SUCCESS; }
+  g_registry.push_back(r);
   LIBP_API_END
 }
 
@@ -742,7 +738,6 @@ extern "C" int libp_ax_hex3d_unregister_D(const libp_dfloat* D) {
   LIBP_API_BEGIN
   for (size_t i = 0; i < g_registry.size(); ++i)
     if (g_registry[i].ptr == D) { g_registry.erase(g_registry.begin() + i); break; }
-  if (g_cD_owner == D) g_cD_owner = nullptr;
   LIBP_API_END
 }
 
@@ -770,8 +765,11 @@ extern "C" int libp_ax_hex3d(int Nq, libp_dlong Nelements, const libp_dlong* ele
                              void* stream) {
   LIBP_API_BEGIN
   LIBP_CHECK(Nelements == 0 || (wJ && ggeo && D && q && AqL), "null device pointer");
+  if (Nelements == 0) return LIBP_SUCCESS;
   const RegisteredD* r = find_registered(D, Nq);
-  ax_hex3d_launch(Nq, false, r != nullptr, r && r->sym, Nelements, elementList, GlobalToLocal, wJ, ggeo, D, lambda, q,
+  AxD tmp;
+  if (!r) fetch_D(Nq, D, as_stream(stream), tmp);
+  ax_hex3d_launch(Nq, false, r ? r->dc : tmp, r && r->sym, Nelements, elementList, GlobalToLocal, wJ, ggeo, lambda, q,
                   AqL, nullptr, nullptr, as_stream(stream), nullptr);
   LIBP_API_END
 }
@@ -782,8 +780,11 @@ extern "C" int libp_ax_hex3d_gather(int Nq, libp_dlong Nelements, const libp_dlo
                                     void* stream) {
   LIBP_API_BEGIN
   LIBP_CHECK(Nelements == 0 || (GlobalToLocal && wJ && ggeo && D && q && Aq), "null device pointer");
+  if (Nelements == 0) return LIBP_SUCCESS;
   const RegisteredD* r = find_registered(D, Nq);
-  ax_hex3d_launch(Nq, true, r != nullptr, r && r->sym, Nelements, elementList, GlobalToLocal, wJ, ggeo, D, lambda, q,
+  AxD tmp;
+  if (!r) fetch_D(Nq, D, as_stream(stream), tmp);
+  ax_hex3d_launch(Nq, true, r ? r->dc : tmp, r && r->sym, Nelements, elementList, GlobalToLocal, wJ, ggeo, lambda, q,
                   Aq, nullptr, nullptr, as_stream(stream), nullptr);
   LIBP_API_END
 }

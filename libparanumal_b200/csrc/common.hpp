@@ -80,6 +80,13 @@ struct dev_buf {
 
 int sm_count();
 
+// Derivative matrix + even-odd factors handed to the Ax kernels by value (see ax_hex3d.cu)
+struct AxD {
+  double D[81];
+  double De[16], Do[16], Dc[4], Dr[4];
+  void set(int Nq, const double* D_host);
+};
+
 // Zero-ahead arguments of the fused Ax kernel (protocol: ax_hex3d.cu, kZA)
 struct ZeroAhead {
   int* ctr = nullptr;           // device: [0] ticket, [1] complete leading groups, [2] error, [3] pad, [4+g] done[g]

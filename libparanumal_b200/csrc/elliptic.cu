@@ -131,11 +131,19 @@ int libp_elliptic_s::zero_ahead_errors() {
 
 void libp_elliptic_s::build_chain_plan(cudaStream_t s) {
   libp_ogs_s& ogs = *d.ogsMasked;
-  const dlong nL = d.NlocalGatherElements, nG = d.NglobalGatherElements, nL0 = nL / 2;
-  const AxChainSegDesc sd[3] = {{d.localGatherElementList, 0, nL0}, {d.globalGatherElementList, 0, nG},
-                                {d.localGatherElementList, nL0, nL - nL0}};
+  // two launch segments: every local element (touches no rank-shared row) | the elements on rank boundaries.  The
+  // reference cuts the local list in halves around the global one to overlap MPI on ONE stream
+  // (ellipticOperator.cpp:40-104); here the global segment and both exchanges run on a side stream beside the local one.
+  const AxChainSegDesc sd[3] = {{d.localGatherElementList, 0, d.NlocalGatherElements},
+                                {d.globalGatherElementList, 0, d.NglobalGatherElements}, {nullptr, 0, 0}};
   chainPlan.stages = chainStages;
   chainPlan.build(d.Nq, hD, ogs.NlocalT + ogs.NhaloT, ogs.NlocalT, d.GlobalToLocal, chainL, sd, s);
+}
+
+libp_elliptic_s::~libp_elliptic_s() {
+  if (side) cudaStreamDestroy(side);
+  if (e_fork) cudaEventDestroy(e_fork);
+  if (e_join) cudaEventDestroy(e_join);
 }
 
 void libp_elliptic_s::apply(dfloat* q, dfloat* Aq, bool want_dot, const int* doneFlag, cudaStream_t s, bool zeroed) {
@@ -153,23 +161,39 @@ void libp_elliptic_s::apply(dfloat* q, dfloat* Aq, bool want_dot, const int* don
     if (tev) CUDA_CHECK(cudaEventRecord(tev[0], s));
     if (!zeroed) chainPlan.zero_fill(Aq, doneFlag, s);
     if (tev) CUDA_CHECK(cudaEventRecord(tev[1], s));
-    auto run = [&](int k) {
-      doff += chainPlan.launch(k, d.GlobalToLocal, d.wJ, d.ggeo, d.lambda, q, Aq, dp ? dp + doff : nullptr, doneFlag, s);
+    const int nb0 = ax_chain_blocks(d.Nq, nL, chainPlan.L);
+    auto run = [&](int k, int off, cudaStream_t st) {
+      return chainPlan.launch(k, d.GlobalToLocal, d.wJ, d.ggeo, d.lambda, q, Aq, dp ? dp + off : nullptr, doneFlag, st);
     };
-    halo_start_f64(ogs, q, s);
-    run(0);
-    halo_finish_f64(ogs, q, s);
-    run(1);
-    halo_combine_start_f64(ogs, Aq, s);
-    run(2);
-    halo_combine_finish_f64(ogs, Aq, s);
+    int nb1 = 0;
+    if (ogs.comm->size > 1) {
+      // side stream: halo of q -> boundary elements -> cross-rank combine, concurrent with the local elements
+      if (!side) {
+        int least = 0, greatest = 0;
+        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, greatest));
+        CUDA_CHECK(cudaEventCreateWithFlags(&e_fork, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&e_join, cudaEventDisableTiming));
+      }
+      CUDA_CHECK(cudaEventRecord(e_fork, s));
+      CUDA_CHECK(cudaStreamWaitEvent(side, e_fork, 0));
+      halo_start_f64(ogs, q, side);
+      halo_finish_f64(ogs, q, side);
+      nb1 = run(1, nb0, side);
+      halo_combine_start_f64(ogs, Aq, side);
+      halo_combine_finish_f64(ogs, Aq, side);
+      CUDA_CHECK(cudaEventRecord(e_join, side));
+    }
+    const int got0 = run(0, 0, s);
+    (void)got0;
+    if (ogs.comm->size > 1) CUDA_CHECK(cudaStreamWaitEvent(s, e_join, 0));
     if (tev) CUDA_CHECK(cudaEventRecord(tev[2], s));
-    nDotPartials = doff;
+    nDotPartials = nb0 + nb1;
     return;
   }
   auto ax = [&](dlong n, const dlong* list, const ZeroAhead* za = nullptr) {
     if (n <= 0) return;
-    int nb = ax_hex3d_launch(d.Nq, fused, true, symD, n, list, d.GlobalToLocal, d.wJ, d.ggeo, d.D, d.lambda, q, out,
+    int nb = ax_hex3d_launch(d.Nq, fused, axD, symD, n, list, d.GlobalToLocal, d.wJ, d.ggeo, d.lambda, q, out,
                              dp ? dp + doff : nullptr, doneFlag, s, za);
     doff += nb;
   };
@@ -263,6 +287,7 @@ extern "C" int libp_elliptic_create(const libp_elliptic_desc_t* desc, libp_ellip
     CUDA_CHECK(cudaMemcpy(hD, desc->D, sizeof(double) * desc->Nq * desc->Nq, cudaMemcpyDeviceToHost));
     e->symD = ax_hex3d_D_is_centro_antisymmetric(desc->Nq, hD);
     std::copy(hD, hD + desc->Nq * desc->Nq, e->hD);
+    e->axD.set(desc->Nq, hD);
   }
   e->Ndofs = desc->ogsMasked->Ngather;
   e->Nhalo = desc->ogsMasked->NhaloT - desc->ogsMasked->NhaloP;
@@ -401,12 +426,19 @@ extern "C" int libp_elliptic_rhs_bc_hex3d(int Nq, libp_dlong Nelements, const li
   LIBP_CHECK(N == 0 || (wJ && ggeo && D && uD && rhs), "null device pointer");
   if (N == 0) return LIBP_SUCCESS;
   cudaStream_t s = as_stream(stream);
-  dev_buf<dfloat> AuD;  // setup-time scratch
-  AuD.alloc(N);
-  ax_hex3d_launch(Nq, false, false, false, Nelements, nullptr, nullptr, wJ, ggeo, D, lambda, uD, AuD.p, nullptr, nullptr, s);
-  rhs_bc_kernel<<<ew_grid(N), 256, 0, s>>>(N, AuD.p, ndq, rhs);
+  // scratch for A u_D: stream-ordered allocation, released in stream order (no synchronisation with the host)
+  dfloat* AuD = nullptr;
+  CUDA_CHECK(cudaMallocAsync(&AuD, sizeof(dfloat) * N, s));
+  double hD[81];
+  CUDA_CHECK(cudaMemcpyAsync(hD, D, sizeof(double) * Nq * Nq, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));  // D is a setup-time input read back once per call
+  AxD dc;
+  dc.set(Nq, hD);
+  ax_hex3d_launch(Nq, false, dc, ax_hex3d_D_is_centro_antisymmetric(Nq, hD), Nelements, nullptr, nullptr, wJ, ggeo, lambda,
+                  uD, AuD, nullptr, nullptr, s);
+  rhs_bc_kernel<<<ew_grid(N), 256, 0, s>>>(N, AuD, ndq, rhs);
   CUDA_CHECK(cudaGetLastError());
-  CUDA_CHECK(cudaStreamSynchronize(s));  // AuD is released on return
+  CUDA_CHECK(cudaFreeAsync(AuD, s));
   LIBP_API_END
 }
 

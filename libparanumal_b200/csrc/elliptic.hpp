@@ -7,8 +7,8 @@
 #include "ogs.hpp"
 
 namespace libp_b200 {
-int ax_hex3d_launch(int Nq, bool fused, bool trusted_D, bool sym, dlong Nelements, const dlong* elementList,
-                    const dlong* G2L, const dfloat* wJ, const dfloat* ggeo, const dfloat* D, dfloat lambda,
+int ax_hex3d_launch(int Nq, bool fused, const AxD& dc, bool sym, dlong Nelements, const dlong* elementList,
+                    const dlong* G2L, const dfloat* wJ, const dfloat* ggeo, dfloat lambda,
                     const dfloat* q, dfloat* Aq, dfloat* dotPartials, const int* doneFlag, cudaStream_t s,
                     const ZeroAhead* za = nullptr);
 int ax_hex3d_zero_ahead_epb(int Nq);
@@ -65,6 +65,7 @@ struct libp_elliptic_s {
   libp_b200::AxChainPlan chainPlan;
   int chainL = 0, chainStages = 2;
   double hD[81] = {0};
+  libp_b200::AxD axD;          // host copy of D + even-odd factors (kernel parameter of ax_hex3d_t_kernel)
   bool chain_capable() const { return d.mode == 1 && symD && chainL > 0 && chunk == 0 && !za_on; }
   // the sector classification needs a 32-byte aligned accumulator, the bulk copies 16-byte aligned factors
   bool chain_on(const dfloat* Aq) const {
@@ -72,6 +73,10 @@ struct libp_elliptic_s {
            (reinterpret_cast<uintptr_t>(d.ggeo) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.wJ) & 15) == 0;
   }
   void build_chain_plan(cudaStream_t s);
+  // multi-rank: the boundary elements and both exchanges run on this high-priority side stream
+  cudaStream_t side = nullptr;
+  cudaEvent_t e_fork = nullptr, e_join = nullptr;
+  ~libp_elliptic_s();
   cudaEvent_t* tev = nullptr;  // libp_elliptic_operator_timed: [before zero-fill, after zero-fill, end of apply]
   // zero-fill mask for a caller that folds the zero-fill of Aq into its own pass (nullptr: zero everything)
   const uint32_t* chain_zero_mask(const dfloat* Aq, cudaStream_t s) {

@@ -6,6 +6,9 @@
 // block count and a fixed tree inside each block, so results are run-to-run deterministic; the
 // cross-rank step is a device-side NCCL all-reduce of the scalar (no pinned-host MPI staging).
 // beta == 0 variants never read y (callers pass uninitialised outputs).
+#include <memory>
+#include <unordered_map>
+
 #include "linalg.hpp"
 
 using namespace libp_b200;
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(kRedMaxBlocks) red2_kernel(int nparts, const d
 
 template <int kind, int mode>
 void reduce_dev(dlong N, const double* w, const double* x, const double* y, double* d_out, cudaStream_t s) {
-  RedScratch& rs = red_scratch();
+  RedScratch& rs = red_scratch(s);
   rs.ensure();
   const int nb = red_blocks(N);
   red1_kernel<kind, mode><<<nb, kRedBlock, 0, s>>>(N, w, x, y, rs.partials.p);
@@ -145,7 +148,7 @@ void reduce_dev(dlong N, const double* w, const double* x, const double* y, doub
 
 template <int kind, int mode>
 double reduce_host(dlong N, const double* w, const double* x, const double* y, libp_comm_t comm, cudaStream_t s) {
-  RedScratch& rs = red_scratch();
+  RedScratch& rs = red_scratch(s);
   rs.ensure();
   reduce_dev<kind, mode>(N, w, x, y, rs.result.p, s);
   if (comm && comm->size > 1) comm->allreduce_dev(rs.result.p, 1, kind == kSum ? LIBP_ADD : kind == kMin ? LIBP_MIN : LIBP_MAX, s);
@@ -167,9 +170,13 @@ void RedScratch::ensure() {
 RedScratch::~RedScratch() {
   if (h_result) cudaFreeHost(h_result);
 }
-RedScratch& red_scratch() {
-  static RedScratch rs;
-  return rs;
+// one scratch per (host thread, stream): reductions issued concurrently from different streams or threads never share
+// partial sums or landing slots
+RedScratch& red_scratch(cudaStream_t s) {
+  thread_local std::unordered_map<cudaStream_t, std::unique_ptr<RedScratch>> table;
+  std::unique_ptr<RedScratch>& p = table[s];
+  if (!p) p.reset(new RedScratch());
+  return *p;
 }
 void dot_to_device(dlong N, const double* x, const double* y, const double* w, double* d_out, cudaStream_t s) {
   if (w) reduce_dev<kSum, 2>(N, w, x, y, d_out, s);

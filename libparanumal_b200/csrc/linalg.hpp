@@ -23,7 +23,7 @@ struct RedScratch {
   void ensure();
   ~RedScratch();
 };
-RedScratch& red_scratch();
+RedScratch& red_scratch(cudaStream_t s);
 
 // result[slot] = sum_i x[i]*y[i] (y==nullptr -> x[i]); deterministic two-level reduction, stays on device
 void dot_to_device(dlong N, const double* x, const double* y, const double* w, double* d_out, cudaStream_t s);

@@ -9,8 +9,11 @@
 //                         vector updates are fused with their dot products
 //                              x += alpha p ; r -= alpha Ap ; r.r ; z = D^-1 r ; r.z     (one pass)
 //                              p  = z + beta p                                            (one pass)
-//                         p.Ap is produced by the Ax kernel itself (element-local u.A_e u), reductions
-//                         are deterministic two-level sums + NCCL all-reduce, and the host only reads
+//                         p.Ap is produced by the Ax kernel itself (element-local u.A_e u), the SCALAR
+//                         reductions are deterministic two-level sums + NCCL all-reduce (the vectors are not:
+//                         in operator mode 1 Ap is accumulated with unordered FP64 red.add, so iterates and
+//                         iteration counts are reproducible to rounding only; mode 0 keeps the reference's
+//                         left-to-right row sums and is bit-reproducible), and the host only reads
 //                         the iteration counter back every `check_every` iterations (a converged solve
 //                         turns the remaining queued kernels into no-ops through a device flag).
 #include <cmath>
@@ -298,7 +301,14 @@ struct libp_pcg_s {
   PcgScalars* h_sc = nullptr;  // pinned
   std::vector<double> hist;
   int check_every = 8;
-  ~libp_pcg_s() { if (h_sc) cudaFreeHost(h_sc); }
+  // one PCG iteration (p update, operator with its exchanges on the side streams, the stage kernels, x/r update)
+  // captured once per solve into a CUDA graph and replayed: one launch per iteration instead of ~12
+  int use_graph = 1;
+  cudaGraphExec_t iter_graph = nullptr;
+  ~libp_pcg_s() {
+    if (h_sc) cudaFreeHost(h_sc);
+    if (iter_graph) cudaGraphExecDestroy(iter_graph);
+  }
 };
 
 extern "C" int libp_pcg_create(libp_dlong N, libp_dlong Nhalo, int flexible, int stopping, libp_comm_t comm,
@@ -317,6 +327,8 @@ extern "C" int libp_pcg_create(libp_dlong N, libp_dlong Nhalo, int flexible, int
   CUDA_CHECK(cudaMallocHost(&s->h_sc, sizeof(PcgScalars)));
   const char* ce = getenv("LIBP_PCG_CHECK_EVERY");
   if (ce && atoi(ce) > 0) s->check_every = atoi(ce);
+  const char* ge = getenv("LIBP_PCG_GRAPH");
+  if (ge) s->use_graph = atoi(ge) != 0;
   *pcg = s.release();
   LIBP_API_END
 }
@@ -495,7 +507,9 @@ extern "C" int libp_pcg_solve(libp_pcg_t pcg, libp_elliptic_t A, libp_precon_t M
   };
   precon_and_rz();
   int queued = 0, iter = 0;
-  while (true) {
+  // the part of an iteration that needs no host decision (everything for the diagonal preconditioners; up to the
+  // convergence test for a general one)
+  auto body = [&]() {
     // p = z + beta p (and the zero-fill of Ap for the fused Ax epilogue)
     pupdate_kernel<<<vgrid(std::max(N, Nzero)), kBlock, 0, s>>>(N, Nzero, sc, pcg->z.p, pcg->p.p, pcg->Ap.p, zmask);
     // Ap = A p with p.Ap partials from the Ax kernel ; alpha
@@ -511,20 +525,51 @@ extern "C" int libp_pcg_solve(libp_pcg_t pcg, libp_elliptic_t A, libp_precon_t M
     } else {
       update_kernel<0, false><<<nb, kBlock, 0, s>>>(N, sc, pcg->p.p, pcg->Ap.p, nullptr, x, r, nullptr, parts, nb);
     }
-    if (precon != 0) {
-      stage(2, parts, nb, nb, flex ? nb : 0, 1);
-    } else {
-      stage(2, parts, nb, 0, 0, 0);
-      precon_and_rz();  // general preconditioner: separate apply, then r.z (z.Ap) and beta
-    }
     CUDA_CHECK(cudaGetLastError());
+    if (precon != 0) stage(2, parts, nb, nb, flex ? nb : 0, 1);
+    else stage(2, parts, nb, 0, 0, 0);
+  };
+  // Graph of one iteration.  Only where every kernel of the body is ours (single rank, or the peer-window transport:
+  // no NCCL calls inside the capture); the first iteration runs eagerly (it builds lazily created plans / streams).
+  bool graph_ok = pcg->use_graph && (!multi || win) && maxit > 2;
+  if (pcg->iter_graph) { cudaGraphExecDestroy(pcg->iter_graph); pcg->iter_graph = nullptr; }
+  while (true) {
+    if (graph_ok && iter >= 1 && pcg->iter_graph == nullptr) {
+      cudaGraph_t g = nullptr;
+      cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+      if (e == cudaSuccess) {
+        bool thrown = false;
+        try { body(); } catch (...) { thrown = true; }
+        e = cudaStreamEndCapture(s, &g);
+        if (e == cudaSuccess && !thrown && g) e = cudaGraphInstantiate(&pcg->iter_graph, g, 0);
+        else if (e == cudaSuccess) e = cudaErrorUnknown;
+        if (g) cudaGraphDestroy(g);
+      }
+      if (e != cudaSuccess) {  // not capturable here: run eagerly
+        cudaGetLastError();
+        pcg->iter_graph = nullptr;
+        graph_ok = false;
+      }
+    }
+    if (pcg->iter_graph) CUDA_CHECK(cudaGraphLaunch(pcg->iter_graph, s));
+    else body();
     queued++;
     iter++;
-    if (queued >= pcg->check_every || iter >= maxit) {
+    if (precon != 0) {
+      if (queued >= pcg->check_every || iter >= maxit) {
+        CUDA_CHECK(cudaMemcpyAsync(pcg->h_sc, sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        queued = 0;
+        if (pcg->h_sc->done) break;
+      }
+    } else {
+      // general preconditioner (a multigrid V-cycle, exchanges included): like the reference
+      // (linearSolverPCG.cpp:104-110) test convergence BEFORE applying it - one small read-back per iteration,
+      // negligible beside a V-cycle, and no preconditioner work after the converged iteration
       CUDA_CHECK(cudaMemcpyAsync(pcg->h_sc, sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, s));
       CUDA_CHECK(cudaStreamSynchronize(s));
-      queued = 0;
       if (pcg->h_sc->done) break;
+      precon_and_rz();  // separate apply, then r.z (z.Ap) and beta
     }
   }
   LIBP_CHECK(!(win && comm->p2p_error()), "a peer-window wait timed out (a peer rank failed or diverged)");

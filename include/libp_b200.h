@@ -51,6 +51,7 @@ typedef struct libp_ogs_s* libp_ogs_t;
 typedef struct libp_elliptic_s* libp_elliptic_t;
 typedef struct libp_pcg_s* libp_pcg_t;
 typedef struct libp_nbpcg_s* libp_nbpcg_t;
+typedef struct libp_nbfpcg_s* libp_nbfpcg_t;
 typedef struct libp_precon_s* libp_precon_t;
 typedef struct libp_mglevel_s* libp_mglevel_t;
 typedef struct libp_csr_s* libp_csr_t;
@@ -245,6 +246,35 @@ int libp_elliptic_operator(libp_elliptic_t op, libp_dfloat* q, libp_dfloat* Aq, 
  * of bench.py): ms[0] = zero-fill of the accumulator, ms[1] = halo exchange + Ax launches + combine.  Synchronises. */
 int libp_elliptic_operator_timed(libp_elliptic_t op, libp_dfloat* q, libp_dfloat* Aq, void* stream, double* ms);
 
+/* ------------------------------------------------------------------ device-side setup
+ * What the reference computes on the host before the first solve, computed in HBM directly.
+ * libp_mesh_physical_nodes_hex3d: libs/mesh/meshPhysicalNodesHex3D.cpp - trilinear nodes x, y, z [Nelements*Np] from the
+ *   element vertices EX, EY, EZ [Nelements*8] (vertex order of the reference) and the GLL nodes gllz [Nq].
+ * libp_mesh_geometric_factors_hex3d: libs/mesh/meshGeometricFactorsHex3D.cpp:94-174 - ggeo [Nelements][6][Np]
+ *   (G00,G01,G02,G11,G12,G22), wJ [Nelements*Np] and, when vgeo != NULL, vgeo [Nelements][12][Np]
+ *   (rx..tz, J, JW, 1/JW) from the nodal coordinates and D; a non-positive Jacobian is an error, as in the reference.
+ * libp_elliptic_build_diagonal_hex3d: BuildOperatorDiagonalContinuousHex3D
+ *   (solvers/elliptic/src/ellipticBuildOperatorDiagonal.cpp:998-1057) - element-local diagonal [Nelements*Np]
+ *   (masked nodes 1), allNeumannBoost = allNeumannPenalty * allNeumannScale^2 (0 unless all-Neumann); the caller
+ *   gathers it (ogs Add, Trans).
+ * libp_ax_trilinear_hex3d: ellipticPartialAxTrilinearHex3D (solvers/elliptic/okl/ellipticAxHex3D.okl:440-627,
+ *   ELEMENT MAP = TRILINEAR, selected at ellipticSetup.cpp:131) - element-local A_e q with the geometric factors
+ *   recomputed at every node from EXYZ [Nelements][3][8] and gllzw = [GLL nodes | GLL weights] (2*Nq);
+ *   GlobalToLocal != NULL reads q through the connectivity (-1 -> 0) like ellipticPartialAx*, else q is element-local. */
+int libp_mesh_physical_nodes_hex3d(int Nq, libp_dlong Nelements, const libp_dfloat* EX, const libp_dfloat* EY,
+                                   const libp_dfloat* EZ, const libp_dfloat* gllz, libp_dfloat* x, libp_dfloat* y,
+                                   libp_dfloat* z, void* stream);
+int libp_mesh_geometric_factors_hex3d(int Nq, libp_dlong Nelements, const libp_dfloat* x, const libp_dfloat* y,
+                                      const libp_dfloat* z, const libp_dfloat* D, const libp_dfloat* gllw,
+                                      libp_dfloat* ggeo, libp_dfloat* wJ, libp_dfloat* vgeo, void* stream);
+int libp_elliptic_build_diagonal_hex3d(int Nq, libp_dlong Nelements, const libp_dfloat* ggeo, const libp_dfloat* wJ,
+                                       const libp_dfloat* D, const int* mapB, libp_dfloat lambda,
+                                       libp_dfloat allNeumannBoost, libp_dfloat* diagL, void* stream);
+int libp_ax_trilinear_hex3d(int Nq, libp_dlong Nelements, const libp_dlong* elementList,
+                            const libp_dlong* GlobalToLocal, const libp_dfloat* EXYZ, const libp_dfloat* gllzw,
+                            const libp_dfloat* D, libp_dfloat lambda, const libp_dfloat* q, libp_dfloat* AqL,
+                            void* stream);
+
 /* ------------------------------------------------------------------ elliptic_t::Run pre/post steps (Hex3D, C0)
  * solvers/elliptic/src/ellipticRun.cpp:139-246.  The reference JIT-inlines the user's data file (forcing and
  * boundary functions, e.g. data/ellipticSine3D.h) into these kernels; across a C ABI they arrive evaluated at the
@@ -434,6 +464,19 @@ int libp_nbpcg_solve_cb(libp_nbpcg_t solver, libp_operator_fn A, void* Actx, lib
 int libp_nbpcg_solve(libp_nbpcg_t solver, libp_elliptic_t A, libp_precon_t M, libp_dfloat* x, libp_dfloat* r,
                      libp_dfloat tol, int maxit, int verbose, void* stream, int* iters);
 int libp_nbpcg_residual_history(libp_nbpcg_t solver, const libp_dfloat** hist, int* n);
+
+/* ------------------------------------------------------------------ LinearSolver::nbfpcg (LINEAR SOLVER = NBFPCG)
+ * libs/linearSolver/linearSolverNBFPCG.cpp:71-246: non-blocking FLEXIBLE PCG (one fused update per iteration posts
+ * u.r, u.s, u.w, r.r; the next preconditioner and operator applies are queued before the host waits for them).
+ * Same calling convention as nbpcg; returns the reference's iteration counter. */
+int libp_nbfpcg_create(libp_dlong N, libp_dlong Nhalo, libp_comm_t comm, libp_nbfpcg_t* solver);
+int libp_nbfpcg_free(libp_nbfpcg_t solver);
+int libp_nbfpcg_solve_cb(libp_nbfpcg_t solver, libp_operator_fn A, void* Actx, libp_operator_fn M, void* Mctx,
+                         libp_dfloat* x, libp_dfloat* r, libp_dfloat tol, int maxit, int verbose, void* stream,
+                         int* iters);
+int libp_nbfpcg_solve(libp_nbfpcg_t solver, libp_elliptic_t A, libp_precon_t M, libp_dfloat* x, libp_dfloat* r,
+                      libp_dfloat tol, int maxit, int verbose, void* stream, int* iters);
+int libp_nbfpcg_residual_history(libp_nbfpcg_t solver, const libp_dfloat** hist, int* n);
 
 #ifdef __cplusplus
 }

@@ -100,6 +100,10 @@ SIGNATURES = {
     "libp_ax_hex3d_register_D": (i32, [i32, vp]),
     "libp_ax_hex3d_unregister_D": (i32, [vp]),
     "libp_ax_hex3d_tune": (i32, [i32, i32, i32]),
+    "libp_mesh_physical_nodes_hex3d": (i32, [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "libp_mesh_geometric_factors_hex3d": (i32, [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "libp_elliptic_build_diagonal_hex3d": (i32, [i32, i32, vp, vp, vp, vp, f64, f64, vp, vp]),
+    "libp_ax_trilinear_hex3d": (i32, [i32, i32, vp, vp, vp, vp, vp, f64, vp, vp, vp]),
     "libp_elliptic_create": (i32, [P(EllipticDesc), P(vp)]),
     "libp_elliptic_rhs_forcing_hex3d": (i32, [i32, i32, vp, vp, vp, vp]),
     "libp_elliptic_rhs_bc_hex3d": (i32, [i32, i32, vp, vp, vp, f64, vp, vp, vp, vp]),
@@ -177,6 +181,11 @@ SIGNATURES = {
     "libp_nbpcg_solve_cb": (i32, [vp, OPERATOR_FN, vp, OPERATOR_FN, vp, vp, vp, f64, i32, i32, vp, P(i32)]),
     "libp_nbpcg_solve": (i32, [vp, vp, vp, vp, vp, f64, i32, i32, vp, P(i32)]),
     "libp_nbpcg_residual_history": (i32, [vp, P(vp), P(i32)]),
+    "libp_nbfpcg_create": (i32, [i32, i32, vp, P(vp)]),
+    "libp_nbfpcg_free": (i32, [vp]),
+    "libp_nbfpcg_solve_cb": (i32, [vp, OPERATOR_FN, vp, OPERATOR_FN, vp, vp, vp, f64, i32, i32, vp, P(i32)]),
+    "libp_nbfpcg_solve": (i32, [vp, vp, vp, vp, vp, f64, i32, i32, vp, P(i32)]),
+    "libp_nbfpcg_residual_history": (i32, [vp, P(vp), P(i32)]),
 }
 
 _lib = None

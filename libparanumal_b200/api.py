@@ -356,6 +356,28 @@ def ax_hex3d_gather(Nq, Nelements, elementList, GlobalToLocal, wJ, ggeo, D, lam,
                                         _ptr(D), float(lam), _ptr(q), _ptr(Aq), _stream()))
 
 
+def mesh_physical_nodes_hex3d(Nq, Nelements, EX, EY, EZ, gllz, x, y, z):
+    check(L.load().libp_mesh_physical_nodes_hex3d(Nq, Nelements, _ptr(EX), _ptr(EY), _ptr(EZ), _ptr(gllz), _ptr(x), _ptr(y),
+                                                  _ptr(z), _stream()))
+
+
+def mesh_geometric_factors_hex3d(Nq, Nelements, x, y, z, D, gllw, ggeo, wJ, vgeo=None):
+    check(L.load().libp_mesh_geometric_factors_hex3d(Nq, Nelements, _ptr(x), _ptr(y), _ptr(z), _ptr(D), _ptr(gllw),
+                                                     _ptr(ggeo), _ptr(wJ), _ptr(vgeo) if vgeo is not None else None,
+                                                     _stream()))
+
+
+def elliptic_build_diagonal_hex3d(Nq, Nelements, ggeo, wJ, D, mapB, lam, boost, diagL):
+    check(L.load().libp_elliptic_build_diagonal_hex3d(Nq, Nelements, _ptr(ggeo), _ptr(wJ), _ptr(D), _ptr(mapB), float(lam),
+                                                      float(boost), _ptr(diagL), _stream()))
+
+
+def ax_trilinear_hex3d(Nq, Nelements, elementList, GlobalToLocal, EXYZ, gllzw, D, lam, q, AqL):
+    check(L.load().libp_ax_trilinear_hex3d(Nq, Nelements, _ptr(elementList) if elementList is not None else None,
+                                           _ptr(GlobalToLocal) if GlobalToLocal is not None else None, _ptr(EXYZ),
+                                           _ptr(gllzw), _ptr(D), float(lam), _ptr(q), _ptr(AqL), _stream()))
+
+
 class Elliptic:
     """The C0 branch of elliptic_t::Operator as an operator_t."""
 
@@ -700,4 +722,30 @@ class NbPcg:
     def Free(self):
         if self._h:
             L.load().libp_nbpcg_free(self._h)
+            self._h = C.c_void_p()
+
+
+class NbFPcg:
+    """LinearSolver::nbfpcg (libs/linearSolver/linearSolverNBFPCG.cpp): non-blocking flexible PCG, native handles."""
+
+    def __init__(self, N, Nhalo, comm=None):
+        self._h = C.c_void_p()
+        check(L.load().libp_nbfpcg_create(int(N), int(Nhalo), comm.handle if comm is not None else None, C.byref(self._h)))
+
+    def Solve(self, A: Elliptic, M: Precon, o_x, o_r, tol=1e-8, maxit=5000, verbose=0):
+        it = C.c_int()
+        check(L.load().libp_nbfpcg_solve(self._h, A.handle, M.handle, _ptr(o_x), _ptr(o_r), float(tol), int(maxit),
+                                         int(verbose), _stream(), C.byref(it)))
+        return it.value
+
+    def residual_history(self):
+        p, n = C.c_void_p(), C.c_int()
+        check(L.load().libp_nbfpcg_residual_history(self._h, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), (n.value,)).copy()
+
+    def Free(self):
+        if self._h:
+            L.load().libp_nbfpcg_free(self._h)
             self._h = C.c_void_p()

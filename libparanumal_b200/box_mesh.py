@@ -209,8 +209,52 @@ class BoxMesh:
         if geometry:
             self._geometry(coords)
 
+    def element_vertices(self, e0=0, e1=None):
+        """EX, EY, EZ [n, 8] of elements e0..e1 (vertex order of the reference: libs/mesh/meshSetupBoxHex3D.cpp)"""
+        nx, ny, nz = self.nloc
+        ox, oy, oz = self.off
+        DIMX, DIMY, DIMZ = self.dims
+        dx, dy, dz = DIMX / self.NX, DIMY / self.NY, DIMZ / self.NZ
+        X0, Y0, Z0 = -DIMX / 2.0 + ox * dx, -DIMY / 2.0 + oy * dy, -DIMZ / 2.0 + oz * dz
+        e = torch.arange(e0, self.Nelements if e1 is None else e1, device=self.device)
+        x0 = X0 + dx * (e % nx).double()
+        y0 = Y0 + dy * ((e // nx) % ny).double()
+        z0 = Z0 + dz * (e // (nx * ny)).double()
+        ex = torch.stack([x0, x0 + dx, x0 + dx, x0, x0, x0 + dx, x0 + dx, x0], dim=1)
+        ey = torch.stack([y0, y0, y0 + dy, y0 + dy, y0, y0, y0 + dy, y0 + dy], dim=1)
+        ez = torch.stack([z0, z0, z0, z0, z0 + dz, z0 + dz, z0 + dz, z0 + dz], dim=1)
+        return ex.contiguous(), ey.contiguous(), ez.contiguous()
+
+    def _geometry_device(self, keep_coords, chunk=32768):
+        """physical nodes + geometric factors by the library's device kernels (libp_mesh_physical_nodes_hex3d,
+        libp_mesh_geometric_factors_hex3d), chunked over elements so that the temporaries x, y, z stay small"""
+        from . import api
+        Nq, Np, E, dev = self.Nq, self.Np, self.Nelements, self.device
+        gz = torch.from_numpy(self.gllz).to(dev)
+        gw = torch.from_numpy(self.gllw).to(dev)
+        self.ggeo = torch.empty((E, 6, Np), dtype=torch.float64, device=dev)
+        self.wJ = torch.empty((E, Np), dtype=torch.float64, device=dev)
+        if keep_coords:
+            self.x = torch.empty((E, Np), dtype=torch.float64, device=dev)
+            self.y = torch.empty_like(self.x)
+            self.z = torch.empty_like(self.x)
+        else:
+            n = min(chunk, max(E, 1))
+            tx, ty, tz = (torch.empty((n, Np), dtype=torch.float64, device=dev) for _ in range(3))
+        for e0 in range(0, E, chunk):
+            e1 = min(E, e0 + chunk)
+            ex, ey, ez = self.element_vertices(e0, e1)
+            if keep_coords:
+                x, y, z = self.x[e0:e1], self.y[e0:e1], self.z[e0:e1]
+            else:
+                x, y, z = tx[: e1 - e0], ty[: e1 - e0], tz[: e1 - e0]
+            api.mesh_physical_nodes_hex3d(Nq, e1 - e0, ex, ey, ez, gz, x, y, z)
+            api.mesh_geometric_factors_hex3d(Nq, e1 - e0, x, y, z, self.D, gw, self.ggeo[e0:e1], self.wJ[e0:e1])
+
     # physical nodes + geometric factors, chunked over elements to bound temporaries
     def _geometry(self, keep_coords, chunk=16384):
+        if self.device.type == "cuda":
+            return self._geometry_device(keep_coords)
         N, Nq, Np, E = self.N, self.Nq, self.Np, self.Nelements
         nx, ny, nz = self.nloc
         ox, oy, oz = self.off

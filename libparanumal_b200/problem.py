@@ -61,25 +61,16 @@ class EllipticProblem:
 
     # ---- setup-time pieces (torch, not the hot path) ---------------------------------------------
     def diagonal_local(self):
-        """BuildOperatorDiagonalContinuousHex3D: element-local diagonal [E*Np]."""
-        m, Nq = self.mesh, self.Nq
-        E = m.Nelements
-        G = m.ggeo.reshape(E, 6, Nq, Nq, Nq)
-        D = m.D.reshape(Nq, Nq)
-        dd = torch.diagonal(D)
-        di, dj, dk = dd[None, None, None, :], dd[None, None, :, None], dd[None, :, None, None]
-        A = 2 * G[:, 1] * di * dj + 2 * G[:, 2] * di * dk + 2 * G[:, 4] * dj * dk
-        D2 = D * D
-        A = A + torch.einsum("ezyk,kx->ezyx", G[:, 0], D2)
-        A = A + torch.einsum("ezkx,ky->ezyx", G[:, 3], D2)
-        A = A + torch.einsum("ekyx,kz->ezyx", G[:, 5], D2)
-        A = A + m.wJ.reshape(E, Nq, Nq, Nq) * self.lam
-        A = A.reshape(-1).clone()
-        masked = self.mapB == 1
+        """BuildOperatorDiagonalContinuousHex3D: element-local diagonal [E*Np] (device kernel
+        libp_elliptic_build_diagonal_hex3d)."""
+        from .api import elliptic_build_diagonal_hex3d
+        m = self.mesh
+        boost = 0.0
         if self.allNeumann:
             scale = 1.0 / math.sqrt(float(self.NglobalDofs))
-            A[~masked] += 1.0 * scale * scale
-        A[masked] = 1.0
+            boost = 1.0 * scale * scale  # allNeumannPenalty * allNeumannScale^2
+        A = torch.empty(m.Nelements * m.Np, dtype=torch.float64, device=self.device)
+        elliptic_build_diagonal_hex3d(self.Nq, m.Nelements, m.ggeo, m.wJ, m.D, self.mapB.contiguous(), self.lam, boost, A)
         return A
 
     def inv_diagonal(self):

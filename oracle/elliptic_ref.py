@@ -75,6 +75,48 @@ def ax_hex3d(Nq, wJ, ggeo, D, lam, q, G2L=None, element_list=None, out=None, Nel
     return out
 
 
+def trilinear_factors(Nq, EXYZ, gllz, gllw):
+    """Geometric factors of trilinear elements evaluated at the GLL nodes, as ellipticPartialAxTrilinearHex3D computes
+    them on the fly (solvers/elliptic/okl/ellipticAxHex3D.okl:527-566; delayed J scaling: G = (W/J) * cofactor
+    products, GwJ = W*J).  EXYZ [E][3][8] vertex coordinates.  Returns ggeo [E,6,Np], wJ [E,Np]."""
+    E = np.asarray(EXYZ).size // 24
+    v = np.asarray(EXYZ, dtype=np.float64).reshape(E, 3, 8)
+    z, w = np.asarray(gllz, dtype=np.float64), np.asarray(gllw, dtype=np.float64)
+    rn = z[None, None, None, :] * np.ones((1, Nq, Nq, 1))
+    sn = z[None, None, :, None] * np.ones((1, Nq, 1, Nq))
+    tn = z[None, :, None, None] * np.ones((1, 1, Nq, Nq))
+    c = lambda d, a: v[:, d, a][:, None, None, None]
+
+    def jac(d):
+        fr = 0.125 * ((1 - tn) * (1 - sn) * (c(d, 1) - c(d, 0)) + (1 - tn) * (1 + sn) * (c(d, 2) - c(d, 3))
+                      + (1 + tn) * (1 - sn) * (c(d, 5) - c(d, 4)) + (1 + tn) * (1 + sn) * (c(d, 6) - c(d, 7)))
+        fs = 0.125 * ((1 - tn) * (1 - rn) * (c(d, 3) - c(d, 0)) + (1 - tn) * (1 + rn) * (c(d, 2) - c(d, 1))
+                      + (1 + tn) * (1 - rn) * (c(d, 7) - c(d, 4)) + (1 + tn) * (1 + rn) * (c(d, 6) - c(d, 5)))
+        ft = 0.125 * ((1 - rn) * (1 - sn) * (c(d, 4) - c(d, 0)) + (1 + rn) * (1 - sn) * (c(d, 5) - c(d, 1))
+                      + (1 + rn) * (1 + sn) * (c(d, 6) - c(d, 2)) + (1 - rn) * (1 + sn) * (c(d, 7) - c(d, 3)))
+        return fr, fs, ft
+    xr, xs, xt = jac(0)
+    yr, ys, yt = jac(1)
+    zr, zs, zt = jac(2)
+    J = xr * (ys * zt - zs * yt) - yr * (xs * zt - zs * xt) + zr * (xs * yt - ys * xt)
+    rx, ry, rz = (ys * zt - zs * yt), -(xs * zt - zs * xt), (xs * yt - ys * xt)
+    sx, sy, sz = -(yr * zt - zr * yt), (xr * zt - zr * xt), -(xr * yt - yr * xt)
+    tx, ty, tz = (yr * zs - zr * ys), -(xr * zs - zr * xs), (xr * ys - yr * xs)
+    W = w[None, None, None, :] * w[None, None, :, None] * w[None, :, None, None]
+    sc = W / J
+    G = np.stack([sc * (rx * rx + ry * ry + rz * rz), sc * (rx * sx + ry * sy + rz * sz), sc * (rx * tx + ry * ty + rz * tz),
+                  sc * (sx * sx + sy * sy + sz * sz), sc * (sx * tx + sy * ty + sz * tz), sc * (tx * tx + ty * ty + tz * tz)],
+                 axis=1)
+    return G.reshape(E, 6, Nq ** 3), (W * J).reshape(E, Nq ** 3)
+
+
+def ax_trilinear_hex3d(Nq, EXYZ, gllz, gllw, D, lam, q, G2L=None, element_list=None):
+    """ellipticPartialAxTrilinearHex3D (solvers/elliptic/okl/ellipticAxHex3D.okl:440-627): the same tensor-product
+    apply as ellipticPartialAxHex3D with the factors of trilinear_factors()."""
+    ggeo, wJ = trilinear_factors(Nq, EXYZ, gllz, gllw)
+    return ax_hex3d(Nq, wJ, ggeo, D, lam, q, G2L=G2L, element_list=element_list)
+
+
 def gather_add(rowStarts, colIds, v, nrows=None):
     rowStarts = _c(rowStarts, np.int32)
     colIds = _c(colIds, np.int32)

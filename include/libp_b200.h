@@ -52,6 +52,7 @@ typedef struct libp_elliptic_s* libp_elliptic_t;
 typedef struct libp_pcg_s* libp_pcg_t;
 typedef struct libp_nbpcg_s* libp_nbpcg_t;
 typedef struct libp_nbfpcg_s* libp_nbfpcg_t;
+typedef struct libp_ig_s* libp_ig_t;
 typedef struct libp_precon_s* libp_precon_t;
 typedef struct libp_mglevel_s* libp_mglevel_t;
 typedef struct libp_csr_s* libp_csr_t;
@@ -477,6 +478,21 @@ int libp_nbfpcg_solve_cb(libp_nbfpcg_t solver, libp_operator_fn A, void* Actx, l
 int libp_nbfpcg_solve(libp_nbfpcg_t solver, libp_elliptic_t A, libp_precon_t M, libp_dfloat* x, libp_dfloat* r,
                       libp_dfloat tol, int maxit, int verbose, void* stream, int* iters);
 int libp_nbfpcg_residual_history(libp_nbfpcg_t solver, const libp_dfloat** hist, int* n);
+
+/* ------------------------------------------------------------------ initial-guess strategies of linearSolver_t
+ * libs/linearSolver/initialGuess.cpp, include/initialGuess.hpp; linearSolver_t::Solve brackets every solve with
+ * FormInitialGuess / Update (libs/linearSolver/linearSolver.cpp:31-44).  strategy = INITIAL GUESS STRATEGY:
+ * 0 NONE, 1 ZERO, 2 CLASSIC (Fischer projection), 3 QR (rolling-QR projection), 4 EXTRAP.
+ * maxDim = INITIAL GUESS HISTORY SPACE DIMENSION, extrapDegree = INITIAL GUESS EXTRAP DEGREE,
+ * cpqr = INITIAL GUESS EXTRAP COEFFS METHOD (0 MINNORM, 1 CPQR).  Vectors have N (+ Nhalo for the operator) entries.
+ * libp_ig_extrap_coeffs = Extrap::extrapCoeffs (coefficients c[0:M] for degree m). */
+int libp_ig_create(int strategy, libp_dlong N, libp_dlong Nhalo, int maxDim, int extrapDegree, int cpqr,
+                   libp_comm_t comm, libp_ig_t* ig);
+int libp_ig_free(libp_ig_t ig);
+int libp_ig_dimension(libp_ig_t ig, int* curDim);
+int libp_ig_form_initial_guess(libp_ig_t ig, libp_dfloat* x, const libp_dfloat* rhs, void* stream);
+int libp_ig_update(libp_ig_t ig, libp_operator_fn A, void* Actx, libp_dfloat* x, const libp_dfloat* rhs, void* stream);
+int libp_ig_extrap_coeffs(int m, int M, int cpqr, double* c);
 
 #ifdef __cplusplus
 }

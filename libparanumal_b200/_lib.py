@@ -181,6 +181,12 @@ SIGNATURES = {
     "libp_nbpcg_solve_cb": (i32, [vp, OPERATOR_FN, vp, OPERATOR_FN, vp, vp, vp, f64, i32, i32, vp, P(i32)]),
     "libp_nbpcg_solve": (i32, [vp, vp, vp, vp, vp, f64, i32, i32, vp, P(i32)]),
     "libp_nbpcg_residual_history": (i32, [vp, P(vp), P(i32)]),
+    "libp_ig_create": (i32, [i32, i32, i32, i32, i32, i32, vp, P(vp)]),
+    "libp_ig_free": (i32, [vp]),
+    "libp_ig_dimension": (i32, [vp, P(i32)]),
+    "libp_ig_form_initial_guess": (i32, [vp, vp, vp, vp]),
+    "libp_ig_update": (i32, [vp, OPERATOR_FN, vp, vp, vp, vp]),
+    "libp_ig_extrap_coeffs": (i32, [i32, i32, i32, P(f64)]),
     "libp_nbfpcg_create": (i32, [i32, i32, vp, P(vp)]),
     "libp_nbfpcg_free": (i32, [vp]),
     "libp_nbfpcg_solve_cb": (i32, [vp, OPERATOR_FN, vp, OPERATOR_FN, vp, vp, vp, f64, i32, i32, vp, P(i32)]),

@@ -749,3 +749,56 @@ class NbFPcg:
         if self._h:
             L.load().libp_nbfpcg_free(self._h)
             self._h = C.c_void_p()
+
+
+class InitialGuess:
+    """InitialGuess strategies of linearSolver_t (libs/linearSolver/initialGuess.cpp): NONE, ZERO, CLASSIC, QR, EXTRAP.
+    linearSolver_t::Solve calls FormInitialGuess before and Update after every solve (linearSolver.cpp:31-44)."""
+
+    KINDS = {"NONE": 0, "ZERO": 1, "CLASSIC": 2, "QR": 3, "EXTRAP": 4}
+
+    def __init__(self, strategy, N, Nhalo=0, history=0, extrap_degree=0, coeffs_method="MINNORM", comm=None):
+        self._h = C.c_void_p()
+        self._cb = None
+        check(L.load().libp_ig_create(self.KINDS[strategy], int(N), int(Nhalo), int(history), int(extrap_degree),
+                                      1 if coeffs_method == "CPQR" else 0, comm.handle if comm is not None else None,
+                                      C.byref(self._h)))
+
+    def FormInitialGuess(self, o_x, o_rhs):
+        check(L.load().libp_ig_form_initial_guess(self._h, _ptr(o_x), _ptr(o_rhs), _stream()))
+
+    def Update(self, A, o_x, o_rhs):
+        """A: Elliptic handle, or a python callable (pin, pout) working on raw device pointers"""
+        if isinstance(A, Elliptic):
+            def fn(pin, pout, h=A.handle):
+                check(L.load().libp_elliptic_operator(h, pin, pout, _stream()))
+        else:
+            fn = A
+
+        def cb(ctx, pin, pout, stream):
+            try:
+                fn(pin, pout)
+                return 0
+            except Exception as e:  # pragma: no cover
+                print("operator callback failed:", e)
+                return -1
+        self._cb = L.OPERATOR_FN(cb)
+        check(L.load().libp_ig_update(self._h, self._cb, None, _ptr(o_x), _ptr(o_rhs), _stream()))
+
+    @property
+    def dimension(self):
+        d = C.c_int()
+        check(L.load().libp_ig_dimension(self._h, C.byref(d)))
+        return d.value
+
+    def Free(self):
+        if self._h:
+            L.load().libp_ig_free(self._h)
+            self._h = C.c_void_p()
+
+
+def extrap_coeffs(m, M, coeffs_method="MINNORM"):
+    """Extrap::extrapCoeffs (initialGuess.cpp:440-466)"""
+    c = (C.c_double * M)()
+    check(L.load().libp_ig_extrap_coeffs(int(m), int(M), 1 if coeffs_method == "CPQR" else 0, c))
+    return np.array(c[:])

@@ -78,3 +78,11 @@ g++ -fopenmp -O2 -std=c++17 -march=native -Wno-unused-function \
   -L"$W/libs" -lparAlmond -llinearSolver -lmesh -lparAdogs -logs -llinAlg -lcore \
   "$W/libmpistub.a" -Wl,-rpath,"$BL" -L"$BL" -l:"$BLSO" -Wl,-rpath,"$W/occa/lib" -L"$W/occa/lib" -locca
 echo "multi-rank dump driver built: $OUT/dump_mr_driver"
+# 6. initial-guess dump driver (our own code, oracle/refbuild/dump_ig_driver.cpp)
+g++ -fopenmp -O2 -std=c++17 -march=native -Wno-unused-function \
+  -DLIBP_DIR="\"$W\"" \
+  -I"$HERE/mpistub" -include "$W/lapack_rename.h" -I"$W/include" -I"$W/occa/include" \
+  -o "$OUT/dump_ig_driver" "$HERE/dump_ig_driver.cpp" \
+  -L"$W/libs" -llinearSolver -lmesh -lparAdogs -logs -llinAlg -lcore \
+  "$W/libmpistub.a" -Wl,-rpath,"$BL" -L"$BL" -l:"$BLSO" -Wl,-rpath,"$W/occa/lib" -L"$W/occa/lib" -locca
+echo "initial-guess dump driver built: $OUT/dump_ig_driver"

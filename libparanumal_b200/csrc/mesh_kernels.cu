@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(Nq * Nq) ax_trilinear_kernel(dlong Nelements, 
   const dlong e = elementList ? elementList[blockIdx.x] : (dlong)blockIdx.x;
   s_D[j][i] = D[j * Nq + i];
   if (t < 2 * Nq) s_zw[t / Nq][t % Nq] = gllzw[t];
-  if (t < 24) s_v[t / 8][t % 8] = EXYZ[(size_t)e * 24 + t];
+  for (int n = t; n < 24; n += Nq2) s_v[n / 8][n % 8] = EXYZ[(size_t)e * 24 + n];
   dfloat r_q[Nq], r_Aq[Nq];
   dlong r_id[Nq];
   const size_t base = (size_t)e * Np + t;

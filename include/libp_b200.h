@@ -428,6 +428,13 @@ int libp_multigrid_add_mglevel(libp_multigrid_t mg, libp_mglevel_t level);
 int libp_multigrid_add_amglevel(libp_multigrid_t mg, libp_amglevel_t level);
 int libp_multigrid_set_coarse(libp_multigrid_t mg, libp_coarse_t coarse);
 int libp_multigrid_vcycle(libp_multigrid_t mg, const libp_dfloat* rhs, libp_dfloat* x, void* stream);
+/* PARALMOND CYCLE: kcycle = 0 VCYCLE (parAlmondVcycle.cpp:34-60), 1 KCYCLE (multigrid_t::kcycle,
+ * libs/parAlmond/parAlmondKcycle.cpp:34-249: two inner Krylov steps on the first NUMKCYCLES = 3 coarse levels with
+ * KCYCLETOL = 0.2, fused reductions of okl/kcycleCombinedOp.okl / vectorAddInnerProd.okl); nonsym = 1 selects the
+ * GMRES-type inner products (PARALMOND CYCLE = NONSYM).  libp_multigrid_cycle runs the selected cycle; the
+ * preconditioner made by libp_precon_multigrid_create uses it too. */
+int libp_multigrid_set_cycle(libp_multigrid_t mg, int kcycle, int nonsym);
+int libp_multigrid_cycle(libp_multigrid_t mg, const libp_dfloat* rhs, libp_dfloat* x, void* stream);
 int libp_multigrid_free(libp_multigrid_t mg);
 /* MultiGridPrecon (solvers/elliptic/src/ellipticPreconMultiGrid.cpp:29-37): one V-cycle (+ZeroMean when allNeumann) */
 int libp_precon_multigrid_create(libp_multigrid_t mg, int allNeumann, libp_hlong NglobalDofs, libp_comm_t comm,

@@ -169,6 +169,8 @@ SIGNATURES = {
     "libp_multigrid_add_amglevel": (i32, [vp, vp]),
     "libp_multigrid_set_coarse": (i32, [vp, vp]),
     "libp_multigrid_vcycle": (i32, [vp, vp, vp, vp]),
+    "libp_multigrid_set_cycle": (i32, [vp, i32, i32]),
+    "libp_multigrid_cycle": (i32, [vp, vp, vp, vp]),
     "libp_multigrid_free": (i32, [vp]),
     "libp_precon_multigrid_create": (i32, [vp, i32, i64, vp, P(vp)]),
     "libp_pcg_create": (i32, [i32, i32, i32, i32, vp, P(vp)]),

@@ -649,7 +649,14 @@ class Multigrid:
         self.keep.append(coarse)
         check(L.load().libp_multigrid_set_coarse(self._h, coarse.handle))
 
+    def SetCycle(self, cycle="VCYCLE"):
+        """PARALMOND CYCLE: VCYCLE | KCYCLE | NONSYM (K-cycle with the GMRES-type inner products)"""
+        check(L.load().libp_multigrid_set_cycle(self._h, 0 if cycle == "VCYCLE" else 1, 1 if cycle == "NONSYM" else 0))
+
     def Operator(self, o_rhs, o_x):
+        check(L.load().libp_multigrid_cycle(self._h, _ptr(o_rhs), _ptr(o_x), _stream()))
+
+    def Vcycle(self, o_rhs, o_x):
         check(L.load().libp_multigrid_vcycle(self._h, _ptr(o_rhs), _ptr(o_x), _stream()))
 
 

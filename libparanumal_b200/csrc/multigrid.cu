@@ -25,6 +25,9 @@ using namespace libp_b200;
 namespace {
 
 constexpr int kBlock = 256;
+constexpr int kNumKcycles = 3;       // NUMKCYCLES (include/parAlmond/parAlmondDefines.hpp:35)
+constexpr double kKcycleTol = 0.2;   // KCYCLETOL (:36)
+constexpr int kKcBlocks = 512;       // partial sums per K-cycle reduction
 
 inline int vgrid(size_t n, int per = 1) {
   size_t b = (n + (size_t)kBlock * per - 1) / ((size_t)kBlock * per);
@@ -358,8 +361,21 @@ struct libp_multigrid_s {
   std::vector<std::unique_ptr<dev_buf<double>>> rhs, x;  // per level (index 0 unused: caller's vectors)
   dev_buf<double> scratch;                               // residual of the current level
   dlong coarseN = 0;
+  // ---- K-cycle (PARALMOND CYCLE = KCYCLE, libs/parAlmond/parAlmondKcycle.cpp): two inner Krylov steps on the first
+  // NUMKCYCLES coarse levels, V-cycle below
+  int ctype = 0;   // 0 VCYCLE, 1 KCYCLE
+  int ktype = 0;   // 0 PCG, 1 GMRES (PARALMOND CYCLE = NONSYM)
+  std::vector<std::unique_ptr<dev_buf<double>>> ck, vk, wk;  // levels 1..NUMKCYCLES
+  dev_buf<double> kparts, kdots;
+  double* h_kdots = nullptr;  // pinned
+  ~libp_multigrid_s() { if (h_kdots) cudaFreeHost(h_kdots); }
   void prepare();
   void vcycle(int k, const double* rhs_k, double* x_k, cudaStream_t s);
+  void kcycle(int k, double* rhs_k, double* x_k, cudaStream_t s);
+  void cycle(const double* rhs, double* x, cudaStream_t s);
+  void level_op(int k, double* x, double* Ax, cudaStream_t s);
+  void kdots3(int mode, dlong N, const double* a, const double* b, const double* c, const double* d, double alpha,
+              double beta, double* y, double* out, int nout, cudaStream_t s);
 };
 
 // ===================================================================== MGLevel
@@ -838,6 +854,152 @@ void libp_multigrid_s::prepare() {
   }
   scratch.alloc((size_t)maxCols);
   CUDA_CHECK(cudaMemset(scratch.p, 0, sizeof(double) * (size_t)maxCols));
+  ck.clear(); vk.clear(); wk.clear();
+  if (ctype == 1) {  // multigrid_t::AllocateLevelWorkSpace (parAlmondMultigrid.cpp:104-121)
+    for (size_t k = 0; k <= levels.size(); ++k) {
+      ck.emplace_back(new dev_buf<double>()); vk.emplace_back(new dev_buf<double>()); wk.emplace_back(new dev_buf<double>());
+      if (k > 0 && k < (size_t)kNumKcycles + 1 && k < levels.size()) {
+        const size_t n = (size_t)std::max<dlong>(levels[k].Ncols, 1);
+        for (dev_buf<double>* b : {ck[k].get(), vk[k].get(), wk[k].get()}) {
+          b->alloc(n);
+          CUDA_CHECK(cudaMemset(b->p, 0, sizeof(double) * n));
+        }
+      }
+    }
+    if (!kparts.p) {
+      kparts.alloc((size_t)3 * kKcBlocks);
+      kdots.alloc(4);
+      CUDA_CHECK(cudaMallocHost(&h_kdots, sizeof(double) * 4));
+    }
+  }
+}
+
+// ---- K-cycle reductions: mode 1 kcycleCombinedOp1 (a.b, a.c, b.b); mode 2 kcycleCombinedOp2 (a.b, a.c, a.d);
+// mode 3 vectorAddInnerProd (y = beta y + alpha a ; y.y)   (libs/parAlmond/okl/kcycleCombinedOp.okl, vectorAddInnerProd.okl)
+template <int kMode>
+__global__ void __launch_bounds__(kBlock) kcycle_dots_kernel(dlong N, const double* __restrict__ a, const double* __restrict__ b,
+                                                             const double* __restrict__ c, const double* __restrict__ d,
+                                                             double alpha, double beta, double* __restrict__ y,
+                                                             double* __restrict__ partials, int stride) {
+  __shared__ double s_red[3][kBlock / 32];
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+  for (dlong n = blockIdx.x * kBlock + threadIdx.x; n < N; n += gridDim.x * kBlock) {
+    if (kMode == 1) { const double an = a[n], bn = b[n]; v0 += an * bn; v1 += an * c[n]; v2 += bn * bn; }
+    else if (kMode == 2) { const double an = a[n]; v0 += an * b[n]; v1 += an * c[n]; v2 += an * d[n]; }
+    else { const double yn = beta * y[n] + alpha * a[n]; y[n] = yn; v0 += yn * yn; }
+  }
+  double v[3] = {v0, v1, v2};
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    double t = v[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) s_red[q][threadIdx.x >> 5] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int w = 0; w < kBlock / 32; ++w) t += s_red[threadIdx.x][w];
+    partials[threadIdx.x * stride + blockIdx.x] = t;
+  }
+}
+__global__ void kcycle_finish_kernel(const double* __restrict__ partials, int nb, int stride, int nq, double* __restrict__ out) {
+  const int q = threadIdx.x;
+  if (q < nq) {
+    double t = 0.0;
+    for (int b = 0; b < nb; ++b) t += partials[q * stride + b];
+    out[q] = t;
+  }
+}
+
+void libp_multigrid_s::kdots3(int mode, dlong N, const double* a, const double* b, const double* c, const double* d,
+                              double alpha, double beta, double* y, double* out, int nout, cudaStream_t s) {
+  const int nb = (int)std::max<long>(1, std::min<long>(((long)N + kBlock - 1) / kBlock, kKcBlocks));
+  if (mode == 1) kcycle_dots_kernel<1><<<nb, kBlock, 0, s>>>(N, a, b, c, d, alpha, beta, y, kparts.p, kKcBlocks);
+  else if (mode == 2) kcycle_dots_kernel<2><<<nb, kBlock, 0, s>>>(N, a, b, c, d, alpha, beta, y, kparts.p, kKcBlocks);
+  else kcycle_dots_kernel<3><<<nb, kBlock, 0, s>>>(N, a, b, c, d, alpha, beta, y, kparts.p, kKcBlocks);
+  kcycle_finish_kernel<<<1, 32, 0, s>>>(kparts.p, nb, kKcBlocks, nout, kdots.p);
+  CUDA_CHECK(cudaGetLastError());
+  if (comm && comm->size > 1) comm->allreduce_sum_dev(kdots.p, nout, s);
+  CUDA_CHECK(cudaMemcpyAsync(h_kdots, kdots.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));  // the K-cycle branches on these scalars (parAlmondKcycle.cpp:77)
+  for (int q = 0; q < nout; ++q) out[q] = h_kdots[q];
+}
+
+// level.Operator of level k (matrix-free: the elliptic operator of that degree; CSR: SpMV)
+void libp_multigrid_s::level_op(int k, double* xin, double* Ax, cudaStream_t s) {
+  Level& L = levels[k];
+  if (L.kind == 0) L.mg->op(xin, Ax, s);
+  else L.amg->A->run<0>(1.0, 0.0, nullptr, xin, nullptr, Ax, s);
+}
+
+// multigrid_t::kcycle (libs/parAlmond/parAlmondKcycle.cpp:34-97) with kcycleOp1 / kcycleOp2 (:100-155)
+void libp_multigrid_s::kcycle(int k, double* rhs_k, double* x_k, cudaStream_t s) {
+  if (k == (int)levels.size()) {
+    LIBP_CHECK(coarse != nullptr, "multigrid has no coarse solver");
+    coarse->solve(rhs_k, x_k, s);
+    return;
+  }
+  Level& L = levels[k];
+  double* rhsC = rhs[k + 1]->p;
+  double* xC = x[k + 1]->p;
+  double* res = scratch.p;
+  if (L.kind == 0) {
+    L.mg->smooth(rhs_k, x_k, true, s);
+    L.mg->residual(rhs_k, x_k, res, s);
+    L.mg->coarsen(res, rhsC, s);
+  } else {
+    libp_amglevel_s& A = *L.amg;
+    A.smooth(rhs_k, x_k, true, s);
+    A.A->run<0>(-1.0, 1.0, nullptr, x_k, rhs_k, res, s);
+    LIBP_CHECK(A.R && A.P, "CSR level without transfer operators above the coarse solver");
+    A.R->run<0>(1.0, 0.0, nullptr, res, nullptr, rhsC, s);
+  }
+  if (k + 1 > kNumKcycles || k + 1 >= (int)levels.size()) {
+    // below the K-cycle levels (or the coarse solver is next: base level): plain recursion
+    if (k + 1 >= (int)levels.size()) kcycle(k + 1, rhsC, xC, s);
+    else vcycle(k + 1, rhsC, xC, s);
+  } else {
+    const dlong mC = levels[k + 1].Nrows;
+    kcycle(k + 1, rhsC, xC, s);  // first inner Krylov iteration
+    double* CK = ck[k + 1]->p; double* VK = vk[k + 1]->p; double* WK = wk[k + 1]->p;
+    // kcycleOp1: ck = xC ; vk = A ck ; alpha1 = ck.rhsC, rho1 = ck.vk, |rhsC| ; rhsC -= (alpha1/rho1) vk ; |rhsC|
+    CUDA_CHECK(cudaMemcpyAsync(CK, xC, sizeof(double) * (size_t)mC, cudaMemcpyDeviceToDevice, s));
+    level_op(k + 1, CK, VK, s);
+    double d3[3];
+    kdots3(1, mC, ktype == 0 ? CK : VK, rhsC, VK, nullptr, 0, 0, nullptr, d3, 3, s);
+    const double alpha1 = d3[0], rho1 = d3[1], norm_rhs = std::sqrt(d3[2]);
+    double nn;
+    kdots3(3, mC, VK, nullptr, nullptr, nullptr, -alpha1 / rho1, 1.0, rhsC, &nn, 1, s);
+    const double norm_rhstilde = std::sqrt(nn);
+    if (norm_rhstilde < kKcycleTol * norm_rhs) {
+      LIBP_CHECK(libp_linalg_scale(mC, alpha1 / rho1, xC, s) == LIBP_SUCCESS, libp_last_error());
+    } else {
+      kcycle(k + 1, rhsC, xC, s);  // second inner Krylov iteration
+      if (std::abs(rho1) > 1e-20) {  // kcycleOp2
+        level_op(k + 1, xC, WK, s);
+        kdots3(2, mC, ktype == 0 ? xC : WK, VK, WK, rhsC, 0, 0, nullptr, d3, 3, s);
+        const double gamma = d3[0], beta = d3[1], alpha2 = d3[2];
+        const double rho2 = beta - gamma * gamma / rho1;
+        if (std::abs(rho2) > 1e-20) {
+          const double a = alpha1 / rho1 - gamma * alpha2 / (rho1 * rho2), b = alpha2 / rho2;
+          LIBP_CHECK(libp_linalg_axpy(mC, a, CK, b, xC, s) == LIBP_SUCCESS, libp_last_error());
+        }
+      }
+    }
+  }
+  if (L.kind == 0) {
+    L.mg->prolongate(xC, x_k, s);
+    L.mg->smooth(rhs_k, x_k, false, s);
+  } else {
+    L.amg->P->run<0>(1.0, 1.0, nullptr, xC, x_k, x_k, s);
+    L.amg->smooth(rhs_k, x_k, false, s);
+  }
+}
+
+void libp_multigrid_s::cycle(const double* r, double* xo, cudaStream_t s) {
+  if (ctype == 1) kcycle(0, const_cast<double*>(r), xo, s);  // level 0 never modifies its right-hand side
+  else vcycle(0, r, xo, s);
 }
 
 // multigrid_t::vcycle (libs/parAlmond/parAlmondVcycle.cpp:34-60)
@@ -910,6 +1072,21 @@ extern "C" int libp_multigrid_vcycle(libp_multigrid_t mg, const libp_dfloat* rhs
   mg->vcycle(0, rhs, x, as_stream(stream));
   LIBP_API_END
 }
+extern "C" int libp_multigrid_set_cycle(libp_multigrid_t mg, int kcycle, int nonsym) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(mg, "null argument");
+  mg->ctype = kcycle ? 1 : 0;
+  mg->ktype = nonsym ? 1 : 0;
+  mg->rhs.clear();  // work space is re-planned by the next prepare()
+  LIBP_API_END
+}
+extern "C" int libp_multigrid_cycle(libp_multigrid_t mg, const libp_dfloat* rhs, libp_dfloat* x, void* stream) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(mg && rhs && x, "null argument");
+  mg->prepare();
+  mg->cycle(rhs, x, as_stream(stream));
+  LIBP_API_END
+}
 extern "C" int libp_multigrid_free(libp_multigrid_t mg) {
   LIBP_API_BEGIN
   delete mg;
@@ -936,6 +1113,6 @@ namespace libp_b200 {
 void multigrid_apply(void* impl, const dfloat* r, dfloat* Mr, cudaStream_t s) {
   auto* mg = static_cast<libp_multigrid_s*>(impl);
   mg->prepare();
-  mg->vcycle(0, r, Mr, s);
+  mg->cycle(r, Mr, s);
 }
 }  // namespace libp_b200

@@ -264,7 +264,8 @@ class MultigridHierarchy:
 
     @classmethod
     def build(cls, fine: EllipticProblem, smoother="CHEBYSHEV", chebyshev_degree=2, amg_smoother=None,
-              strength="SYMMETRIC", aggregation="SMOOTHED", coarse_target=1000, level_rho=None, algebraic_only=False):
+              strength="SYMMETRIC", aggregation="SMOOTHED", coarse_target=1000, level_rho=None, algebraic_only=False,
+              cycle="VCYCLE"):
         """MultiGridPrecon::MultiGridPrecon (ellipticPreconMultiGrid.cpp:40-154) without the reference: the
         HALFDOFS degree ladder, one problem per degree (built in the reference's order: every `unique` ogs setup
         consumes rand() in sequence), Chebyshev/Jacobi bounds from the Arnoldi estimate on the device operator,
@@ -363,4 +364,5 @@ class MultigridHierarchy:
         self.mg.SetCoarse(self.coarse_handle)
         self.coarse_part, self.coarse_dense = part, Acd
         self.level_info.append(dict(kind="exact", rows=int(Ac.shape[0]), nnz=int(Ac.nnz)))
+        self.mg.SetCycle(cycle)  # PARALMOND CYCLE
         return self

@@ -86,6 +86,31 @@ def test_nbpcg_matches_reference(precon, ref_it, ref_hist):
     assert float((x[: p.Ndofs] - x2[: p.Ndofs]).abs().max() / x2[: p.Ndofs].abs().max()) < 1e-6
 
 
+# PARALMOND CYCLE = KCYCLE (libs/parAlmond/parAlmondKcycle.cpp): iteration counts and residual norms printed by the
+# unmodified reference built in this container (ellipticMain, Serial, Hex N=4 10^3, lambda=1).  The K-cycle differs
+# from the V-cycle from the first iteration on (V-cycle: 8.3738e-02 after one MULTIGRID iteration).
+KCYCLE = [("MULTIGRID", "SMOOTHED", 6, [2.960718797524, 8.704311358007e-02, 2.560919450235e-03, 1.450746244500e-04]),
+          ("PARALMOND", "SMOOTHED", 10, [2.960718797524, 2.546306750764e-01, 5.399966726670e-02, 6.132016044317e-03]),
+          ("PARALMOND", "UNSMOOTHED", 19, [2.960718797524, 3.554960101002e-01, 1.721931414151e-01, 5.092862981391e-02])]
+
+
+@pytest.mark.parametrize("precon,agg,ref_it,ref_hist", KCYCLE, ids=[c[0] + "_" + c[1] for c in KCYCLE])
+def test_kcycle_matches_reference(precon, agg, ref_it, ref_hist):
+    import numpy as np
+
+    from libparanumal_b200.problem import MultigridHierarchy
+    libc.srand(1)
+    p = EllipticProblem(4, 10, lam=1.0, boundary_flag=1, coords=True)
+    H = MultigridHierarchy.build(p, aggregation=agg, algebraic_only=(precon == "PARALMOND"), cycle="KCYCLE")
+    r = p.rhs_sine3d()
+    x = p.vec()
+    solver = p.pcg()
+    it = solver.Solve(p.op, H.precon(), x, r, tol=1e-8, maxit=200)
+    assert abs(it - ref_it) <= 1, (it, ref_it)
+    h = solver.residual_history()
+    assert np.allclose(h[:4], ref_hist, rtol=2e-4), h[:4]
+
+
 # LINEAR SOLVER = NBFPCG on the same problem (libs/linearSolver/linearSolverNBFPCG.cpp): iteration counts and the
 # first residual norms printed by the unmodified reference built in this container (ellipticMain, Serial mode;
 # MULTIGRID with the parAlmond defaults).  The unpreconditioned variant takes 146 iterations in the reference too

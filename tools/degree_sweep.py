@@ -7,6 +7,11 @@ import json
 import os
 import sys
 
+# the CPU leg (--cpu-seconds) uses the host's physical cores; libgomp reads OMP_NUM_THREADS once, when it is first
+# loaded, so bench.py (whose import sets it for single-process runs) comes before torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402,F401
+
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -25,6 +30,9 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--pcg-iters", type=int, default=30)
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the per-GPU box edge (smoke runs)")
+    ap.add_argument("--cpu-seconds", type=float, default=0.0,
+                    help="> 0: also time the reference's own CPU kernels of every degree on the host cores (rank 0, "
+                         "single-GPU runs; about this many seconds of applies per degree, box of ~0.6 M DOF)")
     ap.add_argument("--chains", default="", help="comma list of chain:stages configurations of the fused operator "
                     "(0:1 = ax_hex3d_t_kernel); empty = library default")
     a = ap.parse_args()
@@ -62,9 +70,12 @@ def main():
 
     for N in [int(x) for x in a.degrees.split(",")]:
         n = max(2, int(round(BOX[N] * a.scale)))
+        p = None
         for lam, cfg in [(l, c) for l in (0.0, 1.0) for c in (a.chains.split(",") if a.chains else [""])]:
-            if cfg == "" or cfg == (a.chains.split(",")[0] if a.chains else ""):
-                p = EllipticProblem(N, n * sx, n * sy, n * sz, lam=lam, comm=comm, coords=(lam != 0.0))
+            if p is None:
+                p = EllipticProblem(N, n * sx, n * sy, n * sz, lam=lam, comm=comm, coords=True)
+            elif p.lam != lam:
+                p.set_lambda(lam)   # same mesh, maps and ogs: only the operator handle changes
             E, Np = p.mesh.Nelements, p.mesh.Np
             out = {"N": N, "elements_per_gpu": [n, n, n], "n_gpus": world, "lambda": lam, "global_dofs": int(p.NglobalDofs),
                    "local_dofs": int(p.Ndofs)}
@@ -96,10 +107,16 @@ def main():
                 del M, r0, solver, x, r
             if rank == 0:
                 print(json.dumps(out), flush=True)
-            if cfg == "" or cfg == a.chains.split(",")[-1]:
-                p.op.Free()
-                del p
-                torch.cuda.empty_cache()
+        p.op.Free()
+        del p
+        torch.cuda.empty_cache()
+        if a.cpu_seconds > 0 and rank == 0 and world == 1:
+            sys.path.insert(0, ROOT)
+            import bench
+            nc = max(3, int(round((6.0e5) ** (1.0 / 3.0) / N)))
+            gd, dt, threads, ngc, nap, kind = bench.cpu_ax_sample(N, nc, 3, 1, seconds=a.cpu_seconds)
+            print(json.dumps({"N": N, "kind": "cpu_reference_operator", "gdofs": gd, "s_per_apply": dt, "cores": threads,
+                              "cpu_kind": kind, "elements": [nc] * 3, "dofs": ngc, "applies": nap}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

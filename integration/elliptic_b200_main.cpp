@@ -1,0 +1,167 @@
+/* The drop-in demonstrated inside the reference: libParanumal's own driver objects (platform_t in THREAD MODEL = CUDA,
+ * mesh_t, elliptic_t - the UNMODIFIED reference, linked as libelliptic.a + libs) with the hot path bound to
+ * include/libp_b200.h through integration/libp_b200_shim.hpp.
+ *
+ * What runs where:
+ *   reference   settings, mesh, elliptic_t setup (ogsMasked, masks, weights), right-hand side kernels (OCCA-CUDA JIT),
+ *               final scatter / addBC / mass-matrix norm, and - for comparison - its own Operator and PCG solve
+ *   B200 path   ogs setup from the reference's (already signed) maskedGlobalIds, elliptic_t::Operator, Jacobi
+ *               preconditioner, LinearSolver::pcg (ellipticOperatorB200_t, JacobiPreconB200, pcgB200 of the shim)
+ * All device arrays the B200 path touches are the reference's own OCCA allocations (deviceMemory<T>::ptr()).
+ *
+ * Prints, like elliptic_t::Run: iterations and "Solution norm" for both paths, the maximum difference of
+ * Operator(q) and of the solutions, and GDOF/s of both operators (reference OCCA-CUDA kernels vs B200 kernels).
+ *
+ * usage: elliptic_b200_main setup.rc [operator-timing-applies]
+ */
+#include <cmath>
+#include <cstdio>
+#include <string>
+
+#include "libp_b200_shim.hpp"
+#include "timer.hpp"
+
+using namespace libp;
+
+static inline double splitmix_uniform(uint64_t seed, uint64_t n) {
+  uint64_t z = seed + (n + 1) * 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z = z ^ (z >> 31);
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
+}
+
+int main(int argc, char** argv) {
+  Comm::Init(argc, argv);
+  LIBP_ABORT("Usage: ./elliptic_b200_main setupfile [applies]", argc < 2);
+  const int napply = argc > 2 ? atoi(argv[2]) : 50;
+  {
+    comm_t comm(Comm::World().Dup());
+    platformSettings_t platformSettings(comm);
+    meshSettings_t meshSettings(comm);
+    ellipticSettings_t ellipticSettings(comm);
+    ellipticAddRunSettings(ellipticSettings);
+    ellipticSettings.parseFromFile(platformSettings, meshSettings, argv[1]);
+    platform_t platform(platformSettings);
+    mesh_t mesh(platform, meshSettings, comm);
+    dfloat lambda = 0.0;
+    ellipticSettings.getSetting("LAMBDA", lambda);
+    memory<int> BCType(3);
+    BCType[0] = 0; BCType[1] = 1; BCType[2] = 2;
+    elliptic_t elliptic(platform, mesh, ellipticSettings, lambda, 3, BCType);
+    mesh_t& m = elliptic.mesh;
+    const dlong Ndofs = elliptic.Ndofs, Nhalo = elliptic.Nhalo;
+    const size_t Ntot = (size_t)m.Np * m.Nelements;
+    const hlong NglobalDofs = elliptic.ogsMasked.NgatherGlobal;
+
+    // ---- bind the hot path to the B200 library
+    int device_id = 0;
+    platformSettings.getSetting("DEVICE NUMBER", device_id);
+    b200::runtime_t rt;
+    rt.Setup(platform, comm, device_id);
+    b200::ogsB200_t ogs;
+    memory<hlong> ids(Ntot);
+    ids.copyFrom(elliptic.maskedGlobalIds);  // signed by the reference's setup: same owners, no rand() consumed
+    ogs.Setup((dlong)Ntot, ids, rt, ogs::Signed, false, false);
+    LIBP_ABORT("B200 ogs setup disagrees with the reference's counters", ogs.Ngather != Ndofs || ogs.Nhalo != Nhalo);
+    b200::ellipticOperatorB200_t A;
+    A.Setup(elliptic, ogs, rt, 1);
+
+    // ---- Operator(q): reference OCCA-CUDA kernels vs the B200 kernels on the reference's own arrays
+    memory<dfloat> q(Ndofs + Nhalo, 0.0), Aq(Ndofs + Nhalo, 0.0), Aq2(Ndofs + Nhalo, 0.0);
+    for (dlong n = 0; n < Ndofs; ++n) q[n] = splitmix_uniform(1234, (uint64_t)n);
+    deviceMemory<dfloat> o_q = platform.malloc<dfloat>(q);
+    deviceMemory<dfloat> o_Aq = platform.malloc<dfloat>(Aq);
+    deviceMemory<dfloat> o_Aq2 = platform.malloc<dfloat>(Aq2);
+    elliptic.Operator(o_q, o_Aq);
+    A.Operator(o_q, o_Aq2);
+    platform.finish();
+    o_Aq.copyTo(Aq);
+    o_Aq2.copyTo(Aq2);
+    double dmax = 0, amax = 0;
+    for (dlong n = 0; n < Ndofs; ++n) { dmax = std::max(dmax, std::abs(Aq[n] - Aq2[n])); amax = std::max(amax, std::abs(Aq[n])); }
+    printf("B200 Operator vs reference Operator: max rel diff = %.3e (Ndofs = %d)\n", dmax / amax, (int)Ndofs);
+    {
+      for (int i = 0; i < 3; ++i) elliptic.Operator(o_q, o_Aq);
+      platform.finish();
+      timePoint_t t0 = GlobalPlatformTime(platform);
+      for (int i = 0; i < napply; ++i) elliptic.Operator(o_q, o_Aq);
+      timePoint_t t1 = GlobalPlatformTime(platform);
+      const double er = ElapsedTime(t0, t1) / napply;
+      for (int i = 0; i < 3; ++i) A.Operator(o_q, o_Aq2);
+      platform.finish();
+      t0 = GlobalPlatformTime(platform);
+      for (int i = 0; i < napply; ++i) A.Operator(o_q, o_Aq2);
+      t1 = GlobalPlatformTime(platform);
+      const double eb = ElapsedTime(t0, t1) / napply;
+      printf("OPERATOR TIMING: reference OCCA-CUDA %.4f ms/apply = %.2f GDOF/s ; B200 path %.4f ms/apply = %.2f GDOF/s ; "
+             "ratio %.2f\n", er * 1e3, NglobalDofs / er / 1e9, eb * 1e3, NglobalDofs / eb / 1e9, er / eb);
+    }
+
+    // ---- elliptic_t::Run (ellipticRun.cpp:139-246) with the solve routed through the shim
+    properties_t kernelInfo = m.props;
+    std::string dataFileName;
+    ellipticSettings.getSetting("DATA FILE", dataFileName);
+    kernelInfo["includes"] += dataFileName;
+    kernelInfo["includes"] += std::string(DELLIPTIC "/data/ellipticBoundary3D.h");
+    kernelInfo["defines/" "p_Nmax"] = std::max(m.Np, m.Nfaces * m.Nfp);
+    kernelInfo["defines/" "p_Nfields"] = 1;
+    kernel_t forcingKernel = platform.buildKernel(DELLIPTIC "/okl/ellipticRhsHex3D.okl", "ellipticRhsHex3D", kernelInfo);
+    kernel_t rhsBCKernel = platform.buildKernel(DELLIPTIC "/okl/ellipticRhsBCHex3D.okl", "ellipticRhsBCHex3D", kernelInfo);
+    kernel_t addBCKernel = platform.buildKernel(DELLIPTIC "/okl/ellipticAddBCHex3D.okl", "ellipticAddBCHex3D", kernelInfo);
+    memory<dfloat> rL(Ntot, 0.0), xL(Ntot, 0.0), zeros(Ndofs + Nhalo, 0.0);
+    deviceMemory<dfloat> o_rL = platform.malloc<dfloat>(rL);
+    deviceMemory<dfloat> o_xL = platform.malloc<dfloat>(xL);
+    deviceMemory<dfloat> o_r = platform.malloc<dfloat>(zeros);
+    deviceMemory<dfloat> o_x = platform.malloc<dfloat>(zeros);
+    deviceMemory<dfloat> o_MxL = platform.malloc<dfloat>(xL);
+    m.MassMatrixKernelSetup(1);
+    std::string pc;
+    ellipticSettings.getSetting("PRECONDITIONER", pc);
+    double norms[2] = {0, 0};
+    int iters[2] = {0, 0};
+    double secs[2] = {0, 0};
+    memory<dfloat> xs[2];
+    for (int path = 0; path < 2; ++path) {  // 0: reference solver + kernels, 1: B200 operator / Jacobi / pcg
+      forcingKernel(m.Nelements, m.o_wJ, m.o_MM, m.o_x, m.o_y, m.o_z, lambda, o_rL);
+      rhsBCKernel(m.Nelements, m.o_wJ, m.o_ggeo, m.o_sgeo, m.o_D, m.o_S, m.o_MM, m.o_vmapM, m.o_sM, lambda, m.o_x, m.o_y,
+                  m.o_z, elliptic.o_mapB, o_rL);
+      o_x.copyFrom(zeros);
+      elliptic.ogsMasked.Gather(o_r, o_rL, 1, ogs::Add, ogs::Trans);
+      platform.finish();
+      timePoint_t t0 = GlobalPlatformTime(platform);
+      if (path == 0) {
+        linearSolver_t linearSolver;
+        linearSolver.Setup<LinearSolver::pcg>(Ndofs, Nhalo, platform, ellipticSettings, comm);
+        iters[0] = elliptic.Solve(linearSolver, o_x, o_r, 1.0e-8, 5000, 0);
+      } else {
+        b200::pcgB200 solver(Ndofs, Nhalo, platform, ellipticSettings, comm, rt);
+        if (pc == "JACOBI") {
+          b200::JacobiPreconB200 M(elliptic, rt, NglobalDofs);
+          iters[1] = solver.Solve(A, M, o_x, o_r, 1.0e-8, 5000, 0);
+        } else {
+          // any other precon_t of the reference works through the callback path of the shim
+          iters[1] = solver.Solve(A, elliptic.precon, o_x, o_r, 1.0e-8, 5000, 0);
+        }
+      }
+      platform.finish();
+      timePoint_t t1 = GlobalPlatformTime(platform);
+      secs[path] = ElapsedTime(t0, t1);
+      xs[path].malloc(Ndofs);
+      o_x.copyTo(xs[path], Ndofs);
+      elliptic.ogsMasked.Scatter(o_xL, o_x, 1, ogs::NoTrans);
+      addBCKernel(m.Nelements, m.o_x, m.o_y, m.o_z, elliptic.o_mapB, o_xL);
+      m.MassMatrixApply(o_xL, o_MxL);
+      norms[path] = sqrt(platform.linAlg().innerProd((dlong)Ntot, o_xL, o_MxL, m.comm));
+    }
+    double xd = 0, xm = 0;
+    for (dlong n = 0; n < Ndofs; ++n) { xd = std::max(xd, std::abs(xs[0][n] - xs[1][n])); xm = std::max(xm, std::abs(xs[0][n])); }
+    printf("REFERENCE path: iterations = %d, solve %.4f s, %.3f GDOF/s, Solution norm = %17.15lg\n", iters[0], secs[0],
+           (double)NglobalDofs * iters[0] / secs[0] / 1e9, norms[0]);
+    printf("B200 path     : iterations = %d, solve %.4f s, %.3f GDOF/s, Solution norm = %17.15lg\n", iters[1], secs[1],
+           (double)NglobalDofs * iters[1] / secs[1] / 1e9, norms[1]);
+    printf("solutions: max rel diff = %.3e\n", xd / xm);
+  }
+  Comm::Finalize();
+  return 0;
+}

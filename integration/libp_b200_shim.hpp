@@ -64,12 +64,14 @@ struct runtime_t {
     mpicomm = c.comm();
     libp_host_collectives_t host{&mpicomm, &a2a, &a2av, &ar_i64, &ar_f64};
     B200_CHECK(libp_comm_create(c.rank(), c.size(), &host, &comm));
-    char uid[128];
-    std::memset(uid, 0, sizeof(uid));
-    if (c.rank() == 0) B200_CHECK(libp_comm_nccl_unique_id(uid));
-    MPI_Bcast(uid, 128, MPI_CHAR, 0, mpicomm);
-    B200_CHECK(libp_comm_nccl_init(comm, uid));
-    libp_comm_p2p_init(comm, 0);                               // NVLink peer window when every peer is mappable
+    if (c.size() > 1) {
+      char uid[128];
+      std::memset(uid, 0, sizeof(uid));
+      if (c.rank() == 0) B200_CHECK(libp_comm_nccl_unique_id(uid));
+      MPI_Bcast(uid, 128, MPI_CHAR, 0, mpicomm);
+      B200_CHECK(libp_comm_nccl_init(comm, uid));
+      libp_comm_p2p_init(comm, 0);                             // NVLink peer window when every peer is mappable
+    }
   }
 };
 

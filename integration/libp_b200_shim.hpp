@@ -35,6 +35,13 @@ struct runtime_t {
   cudaStream_t stream = nullptr;
   libp_comm_t comm = nullptr;
   MPI_Comm mpicomm;
+  platform_t* plat = nullptr;
+  bool shared_stream = false;
+  // Ordering between OCCA's stream and the library's: either both sides use ONE stream (share_stream: the library's
+  // stream is handed to OCCA with device.wrapStream), or every call into the library drains OCCA's queue first and
+  // the library's stream afterwards (default: robust with any OCCA version, costs two host waits per call).
+  void enter() { if (!shared_stream) plat->finish(); }
+  void leave() { if (!shared_stream) cudaStreamSynchronize(stream); }
 
   static int a2a(void* c, const void* s, void* r, size_t n) {
     return MPI_Alltoall(const_cast<void*>(s), (int)n, MPI_CHAR, r, (int)n, MPI_CHAR, *static_cast<MPI_Comm*>(c));
@@ -57,10 +64,12 @@ struct runtime_t {
   }
 
   // after platform_t selected its device (libs/core/platformDeviceConfig.cpp:33-179)
-  void Setup(platform_t& platform, comm_t c, int device_id) {
+  void Setup(platform_t& platform, comm_t c, int device_id, bool share_stream = false) {
     B200_CHECK(libp_b200_init(device_id));
+    plat = &platform;
+    shared_stream = share_stream;
     cudaStreamCreate(&stream);
-    platform.setStream(platform.device.wrapStream(stream));   // OCCA and the library share one stream
+    if (share_stream) platform.setStream(platform.device.wrapStream(stream));   // OCCA and the library share one stream
     mpicomm = c.comm();
     libp_host_collectives_t host{&mpicomm, &a2a, &a2av, &ar_i64, &ar_f64};
     B200_CHECK(libp_comm_create(c.rank(), c.size(), &host, &comm));
@@ -151,8 +160,9 @@ class ellipticOperatorB200_t : public operator_t {
     d.Nelements = mesh.Nelements;
     d.NlocalGatherElements = mesh.NlocalGatherElements;
     d.NglobalGatherElements = mesh.NglobalGatherElements;
-    d.localGatherElementList = mesh.o_localGatherElementList.ptr();
-    d.globalGatherElementList = mesh.o_globalGatherElementList.ptr();
+    // an element list can be empty (no rank-shared element on one rank): its deviceMemory is then uninitialised
+    d.localGatherElementList = mesh.NlocalGatherElements ? mesh.o_localGatherElementList.ptr() : nullptr;
+    d.globalGatherElementList = mesh.NglobalGatherElements ? mesh.o_globalGatherElementList.ptr() : nullptr;
     d.GlobalToLocal = o_GlobalToLocal.ptr();
     d.wJ = mesh.o_wJ.ptr();
     d.ggeo = mesh.o_ggeo.ptr();
@@ -163,7 +173,9 @@ class ellipticOperatorB200_t : public operator_t {
     B200_CHECK(libp_elliptic_create(&d, &h));
   }
   void Operator(deviceMemory<dfloat>& o_q, deviceMemory<dfloat>& o_Aq) override {
+    rt->enter();
     B200_CHECK(libp_elliptic_operator(h, o_q.ptr(), o_Aq.ptr(), rt->stream));
+    rt->leave();
   }
   ~ellipticOperatorB200_t() { if (h) libp_elliptic_free(h); }
 };
@@ -182,7 +194,9 @@ class JacobiPreconB200 : public operator_t {
     B200_CHECK(libp_precon_jacobi_create(e.Ndofs, o_invDiagA.ptr(), e.allNeumann, NglobalDofs, rt->comm, &h));
   }
   void Operator(deviceMemory<dfloat>& o_r, deviceMemory<dfloat>& o_Mr) override {
+    rt->enter();
     B200_CHECK(libp_precon_apply(h, o_r.ptr(), o_Mr.ptr(), rt->stream));
+    rt->leave();
   }
   ~JacobiPreconB200() { if (h) libp_precon_free(h); }
 };
@@ -191,12 +205,14 @@ class JacobiPreconB200 : public operator_t {
 // include/linearSolver.hpp:99-119.  Native handles take the fused device-resident iteration; any other operator_t
 // (an un-replaced preconditioner, another solver's operator) goes through callbacks.
 inline int op_trampoline(void* ctx, libp_dfloat* in, libp_dfloat* out, void* /*stream*/) {
-  struct ctx_t { operator_t* op; platform_t* platform; dlong Ntotal; };
+  struct ctx_t { operator_t* op; platform_t* platform; dlong Ntotal; runtime_t* rt; };
   ctx_t* c = static_cast<ctx_t*>(ctx);
   try {
     deviceMemory<dfloat> o_in(c->platform->device.wrapMemory<dfloat>(in, c->Ntotal));
     deviceMemory<dfloat> o_out(c->platform->device.wrapMemory<dfloat>(out, c->Ntotal));
+    if (!c->rt->shared_stream) cudaStreamSynchronize(c->rt->stream);  // the library's queue, then OCCA's
     c->op->Operator(o_in, o_out);
+    if (!c->rt->shared_stream) c->platform->finish();
     return LIBP_SUCCESS;
   } catch (...) {
     return LIBP_ERROR;
@@ -217,16 +233,18 @@ class pcgB200 : public LinearSolver::linearSolverBase_t {
   int Solve(operator_t& A, operator_t& M, deviceMemory<dfloat>& o_x, deviceMemory<dfloat>& o_r, const dfloat tol,
             const int MAXIT, const int verbose) override {
     int iters = 0;
+    rt->enter();
     auto* a = dynamic_cast<ellipticOperatorB200_t*>(&A);
     auto* j = dynamic_cast<JacobiPreconB200*>(&M);
     if (a && j) {
       B200_CHECK(libp_pcg_solve(h, a->h, j->h, o_x.ptr(), o_r.ptr(), tol, MAXIT, verbose, rt->stream, &iters));
     } else {
-      struct ctx_t { operator_t* op; platform_t* platform; dlong Ntotal; };
-      ctx_t ca{&A, &platform, N + Nhalo}, cm{&M, &platform, N + Nhalo};
+      struct ctx_t { operator_t* op; platform_t* platform; dlong Ntotal; runtime_t* rt; };
+      ctx_t ca{&A, &platform, N + Nhalo, rt}, cm{&M, &platform, N + Nhalo, rt};
       B200_CHECK(libp_pcg_solve_cb(h, &op_trampoline, &ca, &op_trampoline, &cm, o_x.ptr(), o_r.ptr(), tol, MAXIT, verbose,
                                    rt->stream, &iters));
     }
+    rt->leave();
     return iters;
   }
   ~pcgB200() { if (h) libp_pcg_free(h); }
@@ -244,8 +262,8 @@ class nbpcgB200 : public LinearSolver::linearSolverBase_t {
   int Solve(operator_t& A, operator_t& M, deviceMemory<dfloat>& o_x, deviceMemory<dfloat>& o_r, const dfloat tol,
             const int MAXIT, const int verbose) override {
     int iters = 0;
-    struct ctx_t { operator_t* op; platform_t* platform; dlong Ntotal; };
-    ctx_t ca{&A, &platform, N + Nhalo}, cm{&M, &platform, N + Nhalo};
+    struct ctx_t { operator_t* op; platform_t* platform; dlong Ntotal; runtime_t* rt; };
+    ctx_t ca{&A, &platform, N + Nhalo, rt}, cm{&M, &platform, N + Nhalo, rt};
     B200_CHECK(libp_nbpcg_solve_cb(h, &op_trampoline, &ca, &op_trampoline, &cm, o_x.ptr(), o_r.ptr(), tol, MAXIT, verbose,
                                    rt->stream, &iters));
     return iters;

@@ -7,7 +7,7 @@ REPO="$(cd "$(dirname "$0")/.." && pwd)"
 T="$REPO/baseline/_ref/libp_ref_cuda"
 [ -x "$T/elliptic_b200_main" ] || { echo "run integration/build_shim_demo.sh in the build container first"; exit 1; }
 ln -sfn "$T" /tmp/libp_ref_cuda   # LIBP_DIR / OCCA_BUILD_DIR baked into the binaries
-export LIBP_CACHE_DIR=/tmp/occa_cache_shim OCCA_CACHE_DIR=/tmp/occa_cache_shim OCCA_CXX=g++
+export LIBP_SHIM_TRACE=1 LIBP_CACHE_DIR=/tmp/occa_cache_shim OCCA_CACHE_DIR=/tmp/occa_cache_shim OCCA_CXX=g++
 for case in "$@"; do
   N=${case%%:*}; NX=${case##*:}
   for PC in ${PRECONS:-JACOBI}; do
@@ -18,6 +18,6 @@ for case in "$@"; do
         "DISCRETIZATION=CONTINUOUS" "LINEAR SOLVER=PCG" "PRECONDITIONER=$PC" "OUTPUT TO FILE=FALSE" "VERBOSE=FALSE"; do
         echo "[${kv%%=*}]"; echo "${kv#*=}"; done; } > $RC
     echo "=== Hex3D N=$N ${NX}^3 PRECONDITIONER=$PC (THREAD MODEL = CUDA)"
-    (cd "$T/solvers/elliptic" && "$T/elliptic_b200_main" $RC ${APPLIES:-50} 2>&1 | grep -E "Operator vs|OPERATOR TIMING|path|solutions|rror|what|Message" )
+    (cd "$T/solvers/elliptic" && "$T/elliptic_b200_main" $RC ${APPLIES:-50} > /tmp/shim_run.log 2>&1; grep -E "Operator vs|OPERATOR TIMING|path|solutions|shim\]" /tmp/shim_run.log; grep -q "solutions" /tmp/shim_run.log || tail -25 /tmp/shim_run.log )
   done
 done

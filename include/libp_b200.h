@@ -121,6 +121,9 @@ int libp_comm_p2p_reset(libp_comm_t comm);
  * reference (ogsSetup.cpp:268-274) so maps are bit-identical in the same call sequence.   */
 int libp_ogs_setup(libp_dlong N, libp_hlong* ids, libp_comm_t comm, int kind, int unique, int verbose,
                    libp_ogs_t* ogs);
+/* Test hook: ogsBase_t::Setup depends on the tie order of libstdc++'s std::sort (ogsSetup.cpp:245-275); the library
+ * runs the same introsort as parallel tasks.  Compares the two on n records with nkeys distinct keys. */
+int libp_ogs_sort_selftest(libp_dlong n, libp_dlong nkeys, unsigned int seed, int* same);
 int libp_ogs_free(libp_ogs_t ogs);
 
 typedef struct {

@@ -11,6 +11,7 @@
 //     (ogsSetup.cpp:411-433); columns ascend in local id (ogsSetup.cpp:637-663).
 // Collectives go through libp_comm_s (host callbacks; memcpy when size==1).
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <numeric>
 
@@ -31,17 +32,122 @@ struct Node {
 
 inline hlong habs(hlong v) { return v < 0 ? -v : v; }
 
+// ---- std::sort, run in parallel, with the identical result ------------------------------------------------------
+// The owner copy of an id group depends on the order an UNSTABLE std::sort leaves the group in (ogsSetup.cpp:245-275),
+// so the sort cannot be swapped for another algorithm.  libstdc++'s std::sort is introsort: a loop that partitions
+// around a median-of-three pivot, recurses into the right part and continues with the left one, heap-sorts a range
+// when the depth limit 2*floor(log2 n) is hit, and finishes with one insertion-sort pass over ranges of <= 16
+// elements.  The two parts of a partition never interact, so running the recursion as OpenMP tasks executes exactly
+// the same comparisons and swaps on every range - the output equals std::sort's bit for bit (libp_ogs_sort_selftest
+// checks that against std::sort itself).  The final pass is done per <= 16-element leaf: an element never moves out
+// of its leaf in the sequential pass either (everything left of a leaf compares not-greater).
+// Only comparison outcomes steer the algorithm, so sorting compact (key, index) pairs gives the permutation that
+// sorting the 32-byte records by the same key would give.
+struct KeyIdx { unsigned long long key; dlong idx; };
+
+struct ExactSort {
+  KeyIdx* base;
+  static bool lt(const KeyIdx& a, const KeyIdx& b) { return a.key < b.key; }
+  static void move_median_to_first(KeyIdx* result, KeyIdx* a, KeyIdx* b, KeyIdx* c) {
+    if (lt(*a, *b)) {
+      if (lt(*b, *c)) std::iter_swap(result, b);
+      else if (lt(*a, *c)) std::iter_swap(result, c);
+      else std::iter_swap(result, a);
+    } else if (lt(*a, *c)) std::iter_swap(result, a);
+    else if (lt(*b, *c)) std::iter_swap(result, c);
+    else std::iter_swap(result, b);
+  }
+  static KeyIdx* unguarded_partition(KeyIdx* first, KeyIdx* last, KeyIdx* pivot) {
+    while (true) {
+      while (lt(*first, *pivot)) ++first;
+      --last;
+      while (lt(*pivot, *last)) --last;
+      if (!(first < last)) return first;
+      std::iter_swap(first, last);
+      ++first;
+    }
+  }
+  static void insertion_sort(KeyIdx* first, KeyIdx* last) {  // what the final pass does inside one leaf
+    for (KeyIdx* i = first + 1; i < last; ++i) {
+      KeyIdx val = *i;
+      KeyIdx* pos = i;
+      while (pos > first && lt(val, *(pos - 1))) { *pos = *(pos - 1); --pos; }
+      *pos = val;
+    }
+  }
+  static void loop(KeyIdx* first, KeyIdx* last, long depth) {
+    while (last - first > 16) {
+      if (depth == 0) {
+        std::partial_sort(first, last, last, lt);  // the heap-sort fallback of std::__introsort_loop
+        return;
+      }
+      --depth;
+      KeyIdx* mid = first + (last - first) / 2;
+      move_median_to_first(first, first + 1, mid, last - 1);
+      KeyIdx* cut = unguarded_partition(first + 1, last, first);
+      if (last - cut > (1 << 15)) {
+#pragma omp task default(none) firstprivate(cut, last, depth)
+        loop(cut, last, depth);
+      } else {
+        loop(cut, last, depth);
+      }
+      last = cut;
+    }
+    if (last - first > 1) insertion_sort(first, last);
+  }
+  static void sort(KeyIdx* first, size_t n) {
+    if (n < 2) return;
+    long lg = 0;
+    for (size_t m = n; m > 1; m >>= 1) ++lg;
+#pragma omp parallel
+#pragma omp single nowait
+    loop(first, first + n, 2 * lg);
+  }
+};
+
+// a = a permuted so that it is sorted by key(a[i]) with std::sort's exact tie order
+template <class KeyFn>
+void exact_sort_nodes(std::vector<struct Node>& a, KeyFn key);
+
+template <class KeyFn>
+void exact_sort_nodes(std::vector<Node>& a, KeyFn key) {
+  const size_t n = a.size();
+  std::vector<KeyIdx> k(n);
+#pragma omp parallel for schedule(static)
+  for (size_t i = 0; i < n; ++i) { k[i].key = key(a[i]); k[i].idx = (dlong)i; }
+  const bool timing = getenv("LIBP_OGS_TIMING") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  ExactSort::sort(k.data(), n);
+  if (timing)
+    fprintf(stderr, "[ogs setup]   exact sort of %zu keys: %.3f s\n", n,
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  std::vector<Node> out(n);
+#pragma omp parallel for schedule(static)
+  for (size_t i = 0; i < n; ++i) out[i] = a[(size_t)k[i].idx];
+  a.swap(out);
+}
+
 // out[key(in[n])] = in[n]
 template <class Key>
 void permute_by(std::vector<Node>& a, Key key) {
   std::vector<Node> out(a.size());
-  for (const Node& n : a) out[(size_t)key(n)] = n;
+  const size_t n = a.size();
+#pragma omp parallel for schedule(static)
+  for (size_t i = 0; i < n; ++i) out[(size_t)key(a[i])] = a[i];
   a.swap(out);
 }
 
 void exchange_nodes(const libp_comm_s& comm, const std::vector<Node>& send, const std::vector<int>& sendCounts,
                     std::vector<Node>& recv, std::vector<int>& recvCounts) {
   const int size = comm.size;
+  if (size == 1) {  // one rank: the exchange is a copy
+    recvCounts = sendCounts;
+    recv.resize(send.size());
+    const size_t n = send.size();
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; ++i) recv[i] = send[i];
+    return;
+  }
   recvCounts.assign(size, 0);
   comm.alltoall(sendCounts.data(), recvCounts.data(), sizeof(int));
   std::vector<int64_t> sc(size), so(size), rc(size), ro(size);
@@ -78,7 +184,7 @@ void find_shared_nodes(libp_ogs_s& o, std::vector<Node>& nodes) {
   for (dlong n = 0; n < recvN; ++n) recv[n].newId = n;
 
   // same algorithm + equivalent strict weak order as the reference => same tie order
-  std::sort(recv.begin(), recv.end(), [](const Node& a, const Node& b) { return habs(a.baseId) < habs(b.baseId); });
+  exact_sort_nodes(recv, [](const Node& a) { return (unsigned long long)habs(a.baseId); });
 
   int is_unique = 1;
   dlong start = 0;
@@ -125,10 +231,9 @@ void construct_shared_nodes(libp_ogs_s& o, std::vector<Node>& nodes, std::vector
   const int size = comm.size;
   const dlong Nids = (dlong)nodes.size();
 
-  std::sort(nodes.begin(), nodes.end(), [](const Node& a, const Node& b) {
-    if (habs(a.baseId) < habs(b.baseId)) return true;
-    if (habs(a.baseId) > habs(b.baseId)) return false;
-    return a.baseId > b.baseId;  // owner copy leads its group
+  // |id| ascending, the owner (positive) copy first inside a group: one integer key
+  exact_sort_nodes(nodes, [](const Node& a) {
+    return ((unsigned long long)habs(a.baseId) << 1) | (unsigned long long)(a.baseId < 0 ? 1 : 0);
   });
 
   dlong NbaseIds = 0;
@@ -426,35 +531,72 @@ extern "C" int libp_ogs_setup(libp_dlong N, libp_hlong* ids, libp_comm_t comm, i
   o->unique = unique != 0;
   const int rank = comm->rank, size = comm->size;
 
+  const bool timing = getenv("LIBP_OGS_TIMING") != nullptr;
+  auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t0 = tnow();
+  auto lap = [&](const char* what) {
+    if (timing) { const double t1 = tnow(); fprintf(stderr, "[ogs setup] %-28s %.3f s\n", what, t1 - t0); t0 = t1; }
+  };
+  // compressed list of the non-zero ids (parallel: per-chunk counts, prefix, fill)
   std::vector<Node> nodes;
-  nodes.reserve((size_t)N);
-  for (dlong n = 0; n < N; ++n)
-    if (ids[n] != 0) {
-      Node nd;
-      nd.localId = (dlong)nodes.size();
-      nd.baseId = (kind == LIBP_UNSIGNED) ? habs(ids[n]) : ids[n];
-      nd.newId = 0;
-      nd.sign = 0;
-      nd.rank = rank;
-      nd.destRank = (int)(habs(ids[n]) % size);
-      nodes.push_back(nd);
+  std::vector<dlong> compact((size_t)N);  // position of id n in the compressed list
+  {
+    const int nchunks = 256;
+    std::vector<size_t> cnt((size_t)nchunks + 1, 0);
+    const size_t per = ((size_t)N + nchunks - 1) / nchunks;
+#pragma omp parallel for schedule(static)
+    for (int c = 0; c < nchunks; ++c) {
+      size_t k = 0;
+      const size_t b = std::min<size_t>((size_t)N, c * per), e = std::min<size_t>((size_t)N, b + per);
+      for (size_t n = b; n < e; ++n) k += ids[n] != 0;
+      cnt[(size_t)c + 1] = k;
     }
+    for (int c = 0; c < nchunks; ++c) cnt[(size_t)c + 1] += cnt[(size_t)c];
+    nodes.resize(cnt[(size_t)nchunks]);
+#pragma omp parallel for schedule(static)
+    for (int c = 0; c < nchunks; ++c) {
+      size_t k = cnt[(size_t)c];
+      const size_t b = std::min<size_t>((size_t)N, c * per), e = std::min<size_t>((size_t)N, b + per);
+      for (size_t n = b; n < e; ++n) {
+        compact[n] = -1;
+        if (ids[n] == 0) continue;
+        Node nd;
+        nd.localId = (dlong)k;
+        nd.baseId = (kind == LIBP_UNSIGNED) ? habs(ids[n]) : ids[n];
+        nd.newId = 0;
+        nd.sign = 0;
+        nd.rank = rank;
+        nd.destRank = (int)(habs(ids[n]) % size);
+        nodes[k] = nd;
+        compact[n] = (dlong)k;
+        ++k;
+      }
+    }
+  }
+  lap("node records");
   find_shared_nodes(*o, nodes);
+  lap("find_shared_nodes");
   std::vector<Node> sharedNodes;
   construct_shared_nodes(*o, nodes, sharedNodes);
+  lap("construct_shared_nodes");
   {
-    size_t c = 0;
-    for (dlong n = 0; n < N; ++n)
-      if (ids[n] != 0) {
-        nodes[c].localId = n;
-        if (o->unique) ids[n] = nodes[c].baseId;
-        c++;
-      }
+    const bool uniq = o->unique;
+#pragma omp parallel for schedule(static)
+    for (dlong n = 0; n < N; ++n) {
+      const dlong c = compact[(size_t)n];
+      if (c < 0) continue;
+      nodes[(size_t)c].localId = n;
+      if (uniq) ids[n] = nodes[(size_t)c].baseId;
+    }
+    compact.clear();
+    compact.shrink_to_fit();
   }
   local_setup(*o, nodes);
+  lap("local_setup");
   nodes.clear();
   nodes.shrink_to_fit();
   pairwise_setup(*o, sharedNodes);
+  lap("pairwise_setup");
 
   // device copies; allowed to fail softly when no GPU is present (CPU-side map tests)
   int ndev = 0;
@@ -471,6 +613,31 @@ extern "C" int libp_ogs_setup(libp_dlong N, libp_hlong* ids, libp_comm_t comm, i
     cudaGetLastError();
   }
   *out = o.release();
+  LIBP_API_END
+}
+
+// Development / test hook: the parallel exact sort against std::sort on n records with `nkeys` distinct keys (many
+// ties); *same = 1 when the two permutations are identical.
+extern "C" int libp_ogs_sort_selftest(libp_dlong n, libp_dlong nkeys, unsigned int seed, int* same) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(n >= 0 && nkeys >= 1 && same, "bad argument");
+  std::vector<Node> a((size_t)n);
+  unsigned long long st = seed * 2654435761ull + 12345ull;
+  for (dlong i = 0; i < n; ++i) {
+    st = st * 6364136223846793005ull + 1442695040888963407ull;
+    Node nd{};
+    nd.localId = i;
+    nd.baseId = (hlong)((st >> 33) % (unsigned long long)nkeys) + 1;
+    if ((st >> 20) & 1) nd.baseId = -nd.baseId;
+    a[(size_t)i] = nd;
+  }
+  std::vector<Node> b(a);
+  std::sort(a.begin(), a.end(), [](const Node& x, const Node& y) { return habs(x.baseId) < habs(y.baseId); });
+  exact_sort_nodes(b, [](const Node& x) { return (unsigned long long)habs(x.baseId); });
+  int ok = 1;
+  for (dlong i = 0; i < n; ++i)
+    if (a[(size_t)i].localId != b[(size_t)i].localId) { ok = 0; break; }
+  *same = ok;
   LIBP_API_END
 }
 

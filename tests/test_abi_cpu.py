@@ -117,3 +117,15 @@ def test_ogs_kinds_and_empty_input():
     ids = np.array([5, 5], dtype=np.int64)
     o = Ogs().Setup(2, ids, comm, kind=L.SIGNED, unique=False)
     assert o.gather_defined == 0
+
+
+def test_parallel_exact_sort_equals_std_sort():
+    """ogsBase_t::Setup depends on the tie order of libstdc++'s std::sort (libs/ogs/ogsSetup.cpp:245-275): the library's
+    task-parallel introsort must give the identical permutation (many ties, few ties, sizes around the thresholds)"""
+    import ctypes as C
+    lib = L.load()
+    for n, nkeys, seed in [(0, 1, 1), (1, 1, 1), (16, 2, 2), (17, 3, 3), (33, 1, 4), (1000, 7, 5), (65536, 65536, 6),
+                           (200000, 100, 7), (200000, 199999, 8), (1500000, 2, 9), (1500000, 300000, 10)]:
+        same = C.c_int(0)
+        L.check(lib.libp_ogs_sort_selftest(n, nkeys, seed, C.byref(same)))
+        assert same.value == 1, (n, nkeys, seed)

@@ -447,6 +447,273 @@ ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ trilinear variant
+// ELEMENT MAP = TRILINEAR (ellipticPartialAxTrilinearHex3D, solvers/elliptic/okl/ellipticAxHex3D.okl:440-627): the
+// geometric factors are not streamed but recomputed from the 8 vertices of the element (EXYZ [E][3][8], 192 bytes per
+// element = 0.4 B per node at N = 7).  Same chain structure, pencil orientations, accumulation and connectivity as
+// ax_hex3d_chain_kernel; no TMA stage (there is nothing to stream).  The Jacobian of a trilinear map is linear in each
+// reference coordinate, so a thread (fixed r_i, s_j) keeps two coefficients per entry and evaluates a k-level with one
+// FMA each; an element whose edges are parallel (affine map: every box element) has constant J and cofactors, which
+// are then computed once per element and only scaled by the quadrature weight per node.
+struct TriConst {
+  double z[kMaxNq], w[kMaxNq];  // GLL nodes and weights
+};
+
+template <int Nq, bool kDot, bool kScr, int kMinB>
+__global__ void __launch_bounds__(ChT<Nq>::Threads, kMinB)
+ax_hex3d_chain_tri_kernel(const ChainArgs A, const dfloat* __restrict__ EXYZ, const __grid_constant__ EoD eo,
+                          const __grid_constant__ TriConst gl) {
+  if (A.doneFlag != nullptr && *A.doneFlag) return;
+  using C = ChT<Nq>;
+  constexpr int Nq2 = C::Nq2, Np = C::Np, LD = C::LD, SS = C::SS, ESS = C::ESS, EPB = C::EPB;
+  constexpr int NV = (24 + Nq2 - 1) / Nq2;  // vertex coordinates each thread of a slot fetches
+  __shared__ __align__(16) dfloat s_u[EPB * ESS];
+  __shared__ __align__(16) dfloat s_r[EPB * ESS];
+  __shared__ __align__(16) dfloat s_s[EPB * ESS];
+  __shared__ dfloat s_v[EPB][24];
+
+  const int t = threadIdx.x;
+  const bool valid = t < C::Work;
+  const int es = valid ? t / Nq2 : 0;
+  const int ij = valid ? t - es * Nq2 : 0;
+  const int b = ij / Nq, a = ij - b * Nq;
+  const int nC = ij;
+  const int sC = es * ESS + b * LD + a;
+  const int kA = (Nq == 8) ? a : b, jA = (Nq == 8) ? b : a;
+  const int sA = es * ESS + kA * SS + jA * LD;
+  const int kB = (Nq == 8) ? (4 * (b & 1) + (b >> 1)) : b;
+  const int sB = es * ESS + kB * SS + a;
+  constexpr bool screened = kScr;
+  const uint64_t polS = pol_evict_first(), polK = pol_evict_last();
+  const int chain = blockIdx.x * EPB + es;
+  const bool chainOK = valid && chain < A.nChains;
+  const size_t p0 = (size_t)chain * A.L;
+  const int L = A.L;
+  const dfloat rn = gl.z[a], sn = gl.z[b], wij = gl.w[a] * gl.w[b];
+
+  auto header = [&](int n) -> int { return (chainOK && n < L) ? __ldg(A.hdr + p0 + n) : -1; };
+  auto load_ids = [&](int n, int h, dlong (&id)[Nq], unsigned& fl) {
+    if (h < 0) {
+#pragma unroll
+      for (int k = 0; k < Nq; ++k) id[k] = -1;
+      fl = 0;
+      return;
+    }
+    const size_t p = p0 + n;
+    fl = ld_stream_u16(A.flags + p * Nq2 + ij, polS);
+    if (h & 1) {
+      const dlong* g = A.G2L + (size_t)(h >> 1) * Np + nC;
+#pragma unroll
+      for (int k = 0; k < Nq; ++k) id[k] = ld_stream_i(g + k * Nq2, polS);
+    } else {
+      const int* c = A.cid + p * (2 * Nq2) + (a == 0 ? 0 : Nq2) + b;
+#pragma unroll
+      for (int k = 0; k < Nq; ++k) id[k] = ld_stream_i(c + k * Nq, polS);
+    }
+  };
+  auto decode_ids = [&](int h, dlong (&id)[Nq]) {
+    if (h >= 0 && !(h & 1) && a != 0) {
+#pragma unroll
+      for (int k = 0; k < Nq; ++k) id[k] = (id[k] < 0) ? id[k] : id[k] + (a - 1);
+    }
+  };
+  auto load_vertices = [&](int h, dfloat (&v)[NV]) {
+#pragma unroll
+    for (int m = 0; m < NV; ++m) {
+      const int c = ij + m * Nq2;
+      v[m] = (h >= 0 && c < 24) ? __ldg(EXYZ + (size_t)(h >> 1) * 24 + c) : 0.0;
+    }
+  };
+  const uint32_t su_base = smem_u32(s_u + sC);
+  auto gather_q_async = [&](const dlong (&id)[Nq]) {
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < Nq; ++k) {
+        const bool on = id[k] >= 0;
+        cp_async8(su_base + 8u * (uint32_t)(k * SS), A.q + (on ? id[k] : 0), on ? 8u : 0u, polK);
+      }
+    }
+    cp_async_commit();
+  };
+
+  int h_cur = header(0), h_nxt = header(1), h_nn = header(2);
+  dlong id_cur[Nq], id_nxt[Nq];
+  unsigned fl_cur, fl_nxt;
+  dfloat v_cur[NV], v_nxt[NV];
+  load_ids(0, h_cur, id_cur, fl_cur);
+  load_ids(1, h_nxt, id_nxt, fl_nxt);
+  load_vertices(h_cur, v_cur);
+  load_vertices(h_nxt, v_nxt);
+  decode_ids(h_cur, id_cur);
+  decode_ids(h_nxt, id_nxt);
+  gather_q_async(id_cur);
+  dfloat dacc = 0.0;
+
+  const long long left = (long long)A.count - (long long)blockIdx.x * EPB * L;
+  const int nsteps = (int)(left < (long long)L ? (left < 0 ? 0 : left) : (long long)L);
+  for (int n = 0; n < nsteps; ++n) {
+    const bool active = h_cur >= 0;
+    dlong id_nn[Nq];
+    unsigned fl_nn;
+    dfloat v_nn[NV];
+    load_ids(n + 2, h_nn, id_nn, fl_nn);
+    load_vertices(h_nn, v_nn);
+    const int h_nnn = header(n + 3);
+
+    // ---- phase 0: vertices of this element to shared memory, u from the asynchronous gather, t-derivative
+    if (valid) {
+#pragma unroll
+      for (int m = 0; m < NV; ++m)
+        if (ij + m * Nq2 < 24) s_v[es][ij + m * Nq2] = v_cur[m];
+    }
+    cp_async_wait_all();
+    dfloat q_cur[Nq];
+#pragma unroll
+    for (int k = 0; k < Nq; ++k) q_cur[k] = s_u[sC + k * SS];
+    dfloat r_t[Nq];
+    eo_apply<Nq, false>(eo, q_cur, r_t);
+    __syncthreads();
+
+    // ---- phase 1
+    if (valid) {
+      dfloat v[Nq], o[Nq];
+      load_row<Nq>(&s_u[sA], v);
+      eo_apply<Nq, false>(eo, v, o);
+      store_row<Nq>(&s_r[sA], o);
+#pragma unroll
+      for (int m = 0; m < Nq; ++m) v[m] = s_u[sB + m * LD];
+      eo_apply<Nq, false>(eo, v, o);
+#pragma unroll
+      for (int j = 0; j < Nq; ++j) s_s[sB + j * LD] = o[j];
+    }
+    // Jacobian coefficients of this thread's (r_i, s_j): d/dr and d/ds are linear in t, d/dt does not depend on t
+    dfloat ar[3], br[3], as_[3], bs[3], ct[3];
+    bool affine = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const dfloat* e = s_v[es] + 8 * d;
+      const dfloat e10 = e[1] - e[0], e23 = e[2] - e[3], e54 = e[5] - e[4], e67 = e[6] - e[7];
+      const dfloat e30 = e[3] - e[0], e21 = e[2] - e[1], e74 = e[7] - e[4], e65 = e[6] - e[5];
+      const dfloat e40 = e[4] - e[0], e51 = e[5] - e[1], e62 = e[6] - e[2], e73 = e[7] - e[3];
+      ar[d] = (1 - sn) * e10 + (1 + sn) * e23;  br[d] = (1 - sn) * e54 + (1 + sn) * e67;
+      as_[d] = (1 - rn) * e30 + (1 + rn) * e21; bs[d] = (1 - rn) * e74 + (1 + rn) * e65;
+      ct[d] = 0.125 * ((1 - rn) * (1 - sn) * e40 + (1 + rn) * (1 - sn) * e51 + (1 + rn) * (1 + sn) * e62 + (1 - rn) * (1 + sn) * e73);
+      affine = affine && e10 == e23 && e10 == e54 && e10 == e67 && e30 == e21 && e30 == e74 && e30 == e65 &&
+               e40 == e51 && e40 == e62 && e40 == e73;
+    }
+    __syncthreads();
+    gather_q_async(id_nxt);
+
+    // ---- phase 2: geometric factors on the fly
+    dfloat r_Aq[Nq];
+    dfloat cG[7];  // affine element: cofactor products / J and J, the node only contributes its weight
+    if (affine) {
+      const dfloat xr = 0.25 * ar[0], yr = 0.25 * ar[1], zr = 0.25 * ar[2];
+      const dfloat xs = 0.25 * as_[0], ys = 0.25 * as_[1], zs = 0.25 * as_[2];
+      const dfloat xt = ct[0], yt = ct[1], zt = ct[2];
+      const dfloat rx = (ys * zt - zs * yt), ry = -(xs * zt - zs * xt), rz = (xs * yt - ys * xt);
+      const dfloat sx = -(yr * zt - zr * yt), sy = (xr * zt - zr * xt), sz = -(xr * yt - yr * xt);
+      const dfloat tx = (yr * zs - zr * ys), ty = -(xr * zs - zr * xs), tz = (xr * ys - yr * xs);
+      const dfloat J = xr * rx + yr * ry + zr * rz, iJ = 1.0 / J;
+      cG[0] = iJ * (rx * rx + ry * ry + rz * rz); cG[1] = iJ * (rx * sx + ry * sy + rz * sz);
+      cG[2] = iJ * (rx * tx + ry * ty + rz * tz); cG[3] = iJ * (sx * sx + sy * sy + sz * sz);
+      cG[4] = iJ * (sx * tx + sy * ty + sz * tz); cG[5] = iJ * (tx * tx + ty * ty + tz * tz);
+      cG[6] = J;
+    }
+#pragma unroll
+    for (int k = 0; k < Nq; ++k) {
+      const dfloat qr = s_r[sC + k * SS], qs = s_s[sC + k * SS], qt = r_t[k];
+      const dfloat W = wij * gl.w[k];
+      dfloat G00, G01, G02, G11, G12, G22, GwJ;
+      if (affine) {
+        G00 = W * cG[0]; G01 = W * cG[1]; G02 = W * cG[2]; G11 = W * cG[3]; G12 = W * cG[4]; G22 = W * cG[5];
+        GwJ = W * cG[6];
+      } else {
+        const dfloat c0 = 0.125 * (1 - gl.z[k]), c1 = 0.125 * (1 + gl.z[k]);
+        const dfloat xr = c0 * ar[0] + c1 * br[0], yr = c0 * ar[1] + c1 * br[1], zr = c0 * ar[2] + c1 * br[2];
+        const dfloat xs = c0 * as_[0] + c1 * bs[0], ys = c0 * as_[1] + c1 * bs[1], zs = c0 * as_[2] + c1 * bs[2];
+        const dfloat xt = ct[0], yt = ct[1], zt = ct[2];
+        const dfloat rx = (ys * zt - zs * yt), ry = -(xs * zt - zs * xt), rz = (xs * yt - ys * xt);
+        const dfloat sx = -(yr * zt - zr * yt), sy = (xr * zt - zr * xt), sz = -(xr * yt - yr * xt);
+        const dfloat tx = (yr * zs - zr * ys), ty = -(xr * zs - zr * xs), tz = (xr * ys - yr * xs);
+        const dfloat J = xr * rx + yr * ry + zr * rz;
+        const dfloat sc = W / J;  // delayed J scaling, as the reference kernel
+        G00 = sc * (rx * rx + ry * ry + rz * rz); G01 = sc * (rx * sx + ry * sy + rz * sz);
+        G02 = sc * (rx * tx + ry * ty + rz * tz); G11 = sc * (sx * sx + sy * sy + sz * sz);
+        G12 = sc * (sx * tx + sy * ty + sz * tz); G22 = sc * (tx * tx + ty * ty + tz * tz);
+        GwJ = W * J;
+      }
+      if (valid) {
+        s_r[sC + k * SS] = G00 * qr + G01 * qs + G02 * qt;
+        s_s[sC + k * SS] = G01 * qr + G11 * qs + G12 * qt;
+      }
+      r_t[k] = G02 * qr + G12 * qs + G22 * qt;
+      r_Aq[k] = screened ? GwJ * A.lambda * q_cur[k] : 0.0;
+    }
+    {
+      dfloat o[Nq];
+      eo_apply<Nq, true>(eo, r_t, o);
+#pragma unroll
+      for (int k = 0; k < Nq; ++k) r_Aq[k] += o[k];
+    }
+    __syncthreads();
+
+    // ---- phase 3
+    if (valid) {
+      dfloat v[Nq], o[Nq];
+      load_row<Nq>(&s_r[sA], v);
+      eo_apply<Nq, true>(eo, v, o);
+      store_row<Nq>(&s_r[sA], o);
+#pragma unroll
+      for (int m = 0; m < Nq; ++m) v[m] = s_s[sB + m * LD];
+      eo_apply<Nq, true>(eo, v, o);
+#pragma unroll
+      for (int j = 0; j < Nq; ++j) s_s[sB + j * LD] = o[j];
+    }
+    __syncthreads();
+
+    // ---- phase 4
+#pragma unroll
+    for (int k = 0; k < Nq; ++k) r_Aq[k] += s_r[sC + k * SS] + s_s[sC + k * SS];
+    if (kDot && active) {
+#pragma unroll
+      for (int k = 0; k < Nq; ++k) dacc += q_cur[k] * r_Aq[k];
+    }
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < Nq; ++k) {
+        if (id_cur[k] >= 0) {
+          if ((fl_cur >> k) & 1u) st_keep(A.Aq + id_cur[k], r_Aq[k], polK);
+          else red_keep(A.Aq + id_cur[k], r_Aq[k], polK);
+        }
+      }
+    }
+    decode_ids(h_nn, id_nn);
+    h_cur = h_nxt; h_nxt = h_nn; h_nn = h_nnn;
+    fl_cur = fl_nxt; fl_nxt = fl_nn;
+#pragma unroll
+    for (int k = 0; k < Nq; ++k) { id_cur[k] = id_nxt[k]; id_nxt[k] = id_nn[k]; }
+#pragma unroll
+    for (int m = 0; m < NV; ++m) { v_cur[m] = v_nxt[m]; v_nxt[m] = v_nn[m]; }
+  }
+  cp_async_wait_all();
+
+  if (kDot) {
+    dfloat d = dacc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_down_sync(0xffffffffu, d, o);
+    __shared__ dfloat s_dot[C::Threads / 32];
+    if ((t & 31) == 0) s_dot[t >> 5] = d;
+    __syncthreads();
+    if (t == 0) {
+      dfloat tot = 0.0;
+#pragma unroll
+      for (int w = 0; w < C::Threads / 32; ++w) tot += s_dot[w];
+      A.dotPartials[blockIdx.x] = tot;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ plan kernels
 // position p of the concatenated, chain-padded element sequence -> element (or -1)
 __global__ void __launch_bounds__(256) plan_touch_kernel(size_t nPos, int Np, const int* __restrict__ elem,
@@ -621,6 +888,20 @@ int launch_chain(const ChainArgs& A, const EoD& eo, int stages, cudaStream_t s) 
   return (A.nChains + C::EPB - 1) / C::EPB;
 }
 
+template <int Nq>
+int launch_chain_tri(const ChainArgs& A, const dfloat* EXYZ, const EoD& eo, const TriConst& gl, cudaStream_t s) {
+  using C = ChT<Nq>;
+  constexpr int minb = (384 + C::Threads - 1) / C::Threads;  // ~170 registers per thread: no spills at Nq = 8
+  const int grid = (A.nChains + C::EPB - 1) / C::EPB;
+  const bool scr = A.lambda != 0.0;
+#define GO(DOT, SCR) ax_hex3d_chain_tri_kernel<Nq, DOT, SCR, minb><<<grid, C::Threads, 0, s>>>(A, EXYZ, eo, gl)
+  if (A.dotPartials) { if (scr) GO(true, true); else GO(true, false); }
+  else { if (scr) GO(false, true); else GO(false, false); }
+#undef GO
+  CUDA_CHECK(cudaGetLastError());
+  return grid;
+}
+
 }  // namespace
 
 namespace libp_b200 {
@@ -720,6 +1001,16 @@ int AxChainPlan::launch(int k, const dlong* G2L, const dfloat* wJ, const dfloat*
   A.lambda = lambda; A.nChains = sg.nChains; A.L = L; A.count = sg.count;
   EoD e;
   std::memcpy(&e, eo, sizeof(EoD));
+  if (EXYZ != nullptr) {  // trilinear element map: geometry on the fly
+    TriConst gl;
+    for (int i = 0; i < kMaxNq; ++i) { gl.z[i] = i < Nq ? gllz[i] : 0.0; gl.w[i] = i < Nq ? gllw[i] : 0.0; }
+    switch (Nq) {
+#define CASET(n) case n: return launch_chain_tri<n>(A, EXYZ, e, gl, s);
+      CASET(2) CASET(3) CASET(4) CASET(5) CASET(6) CASET(7) CASET(8) CASET(9)
+#undef CASET
+    }
+    return 0;
+  }
   switch (Nq) {
 #define CASE(n) case n: return launch_chain<n>(A, e, stages, s);
     CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9)

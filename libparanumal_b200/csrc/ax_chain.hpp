@@ -24,6 +24,9 @@ struct AxChainPlan {
   dev_buf<uint16_t> flags;
   dev_buf<uint32_t> zmask;
   alignas(8) unsigned char eo[320];  // even-odd factors of D, passed to the kernel by value
+  // ELEMENT MAP = TRILINEAR: element vertices (device, [E][3][8]) + GLL nodes / weights; nullptr = stored factors
+  const dfloat* EXYZ = nullptr;
+  double gllz[9] = {0}, gllw[9] = {0};
   void build(int Nq, const dfloat* D_host, dlong nRows, dlong NlocalT, const dlong* G2L, int L,
              const AxChainSegDesc (&sd)[3], cudaStream_t s);
   // zero-fills the sectors of Aq[0 : nRows] that are not chain-private (Aq must be 32-byte aligned)

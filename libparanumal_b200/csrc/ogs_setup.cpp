@@ -32,6 +32,21 @@ struct Node {
 
 inline hlong habs(hlong v) { return v < 0 ? -v : v; }
 
+// std::vector without value-initialisation: `NodeVec out(n)` neither zero-fills 4 GB on one thread nor touches the
+// pages - the first touch happens inside the parallel loops that fill it
+template <class T>
+struct default_init_alloc : std::allocator<T> {
+  template <class U> struct rebind { typedef default_init_alloc<U> other; };
+  default_init_alloc() = default;
+  template <class U> default_init_alloc(const default_init_alloc<U>&) {}
+  template <class U, class... Args>
+  void construct(U* p, Args&&... args) {
+    if constexpr (sizeof...(args) == 0) ::new (static_cast<void*>(p)) U;
+    else ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...);
+  }
+};
+typedef std::vector<Node, default_init_alloc<Node>> NodeVec;
+
 // ---- std::sort, run in parallel, with the identical result ------------------------------------------------------
 // The owner copy of an id group depends on the order an UNSTABLE std::sort leaves the group in (ogsSetup.cpp:245-275),
 // so the sort cannot be swapped for another algorithm.  libstdc++'s std::sort is introsort: a loop that partitions
@@ -110,9 +125,9 @@ template <class KeyFn>
 void exact_sort_nodes(std::vector<struct Node>& a, KeyFn key);
 
 template <class KeyFn>
-void exact_sort_nodes(std::vector<Node>& a, KeyFn key) {
+void exact_sort_nodes(NodeVec& a, KeyFn key) {
   const size_t n = a.size();
-  std::vector<KeyIdx> k(n);
+  std::vector<KeyIdx, default_init_alloc<KeyIdx>> k(n);
 #pragma omp parallel for schedule(static)
   for (size_t i = 0; i < n; ++i) { k[i].key = key(a[i]); k[i].idx = (dlong)i; }
   const bool timing = getenv("LIBP_OGS_TIMING") != nullptr;
@@ -121,7 +136,7 @@ void exact_sort_nodes(std::vector<Node>& a, KeyFn key) {
   if (timing)
     fprintf(stderr, "[ogs setup]   exact sort of %zu keys: %.3f s\n", n,
             std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
-  std::vector<Node> out(n);
+  NodeVec out(n);
 #pragma omp parallel for schedule(static)
   for (size_t i = 0; i < n; ++i) out[i] = a[(size_t)k[i].idx];
   a.swap(out);
@@ -129,16 +144,16 @@ void exact_sort_nodes(std::vector<Node>& a, KeyFn key) {
 
 // out[key(in[n])] = in[n]
 template <class Key>
-void permute_by(std::vector<Node>& a, Key key) {
-  std::vector<Node> out(a.size());
+void permute_by(NodeVec& a, Key key) {
+  NodeVec out(a.size());
   const size_t n = a.size();
 #pragma omp parallel for schedule(static)
   for (size_t i = 0; i < n; ++i) out[(size_t)key(a[i])] = a[i];
   a.swap(out);
 }
 
-void exchange_nodes(const libp_comm_s& comm, const std::vector<Node>& send, const std::vector<int>& sendCounts,
-                    std::vector<Node>& recv, std::vector<int>& recvCounts) {
+void exchange_nodes(const libp_comm_s& comm, const NodeVec& send, const std::vector<int>& sendCounts,
+                    NodeVec& recv, std::vector<int>& recvCounts) {
   const int size = comm.size;
   if (size == 1) {  // one rank: the exchange is a copy
     recvCounts = sendCounts;
@@ -165,22 +180,29 @@ void exchange_nodes(const libp_comm_s& comm, const std::vector<Node>& send, cons
 }
 
 // Flag, for every id group, the owner copy (when unique) and whether the group spans ranks.
-void find_shared_nodes(libp_ogs_s& o, std::vector<Node>& nodes) {
+void find_shared_nodes(libp_ogs_s& o, NodeVec& nodes) {
   const libp_comm_s& comm = *o.comm;
   const int size = comm.size;
   std::vector<int> sendCounts(size, 0), sendOffsets(size + 1, 0);
-  for (const Node& n : nodes) sendCounts[n.destRank]++;
-  for (int r = 0; r < size; ++r) sendOffsets[r + 1] = sendOffsets[r] + sendCounts[r];
-  {
-    std::vector<int> fill(size, 0);
-    for (Node& n : nodes) n.newId = sendOffsets[n.destRank] + fill[n.destRank]++;
-  }
-  permute_by(nodes, [](const Node& n) { return n.newId; });  // send order: by destRank, local order inside
-
-  std::vector<Node> recv;
+  NodeVec recv;
   std::vector<int> recvCounts;
-  exchange_nodes(comm, nodes, sendCounts, recv, recvCounts);
+  if (size == 1) {
+    // one rank: send order = local order and the exchange is the identity - no counting, no permutation, no copy
+    sendCounts[0] = (int)nodes.size();
+    recvCounts = sendCounts;
+    recv.swap(nodes);
+  } else {
+    for (const Node& n : nodes) sendCounts[n.destRank]++;
+    for (int r = 0; r < size; ++r) sendOffsets[r + 1] = sendOffsets[r] + sendCounts[r];
+    {
+      std::vector<int> fill(size, 0);
+      for (Node& n : nodes) n.newId = sendOffsets[n.destRank] + fill[n.destRank]++;
+    }
+    permute_by(nodes, [](const Node& n) { return n.newId; });  // send order: by destRank, local order inside
+    exchange_nodes(comm, nodes, sendCounts, recv, recvCounts);
+  }
   const dlong recvN = (dlong)recv.size();
+#pragma omp parallel for schedule(static)
   for (dlong n = 0; n < recvN; ++n) recv[n].newId = n;
 
   // same algorithm + equivalent strict weak order as the reference => same tie order
@@ -219,14 +241,18 @@ void find_shared_nodes(libp_ogs_s& o, std::vector<Node>& nodes) {
   o.gather_defined = (u == 1);
 
   permute_by(recv, [](const Node& n) { return n.newId; });  // back to arrival order
-  std::vector<Node> back;
+  if (size == 1) {
+    nodes.swap(recv);
+    return;
+  }
+  NodeVec back;
   std::vector<int> backCounts;
   exchange_nodes(comm, recv, recvCounts, back, backCounts);
   nodes.swap(back);  // now in send order again, with signs / owner flags filled in
 }
 
 // Number the gathered rows and collect, per shared id, who else holds it.
-void construct_shared_nodes(libp_ogs_s& o, std::vector<Node>& nodes, std::vector<Node>& sharedNodes) {
+void construct_shared_nodes(libp_ogs_s& o, NodeVec& nodes, NodeVec& sharedNodes) {
   const libp_comm_s& comm = *o.comm;
   const int size = comm.size;
   const dlong Nids = (dlong)nodes.size();
@@ -259,7 +285,7 @@ void construct_shared_nodes(libp_ogs_s& o, std::vector<Node>& nodes, std::vector
   comm.allreduce_i64(&ng, 1, LIBP_ADD);
   o.NgatherGlobal = ng;
 
-  std::vector<Node> sendShared;
+  NodeVec sendShared;
   sendShared.reserve((size_t)o.NhaloT);
   for (dlong n = 0; n < Nids; ++n)
     if (n == 0 || habs(nodes[n].baseId) != habs(nodes[n - 1].baseId))
@@ -285,7 +311,7 @@ void construct_shared_nodes(libp_ogs_s& o, std::vector<Node>& nodes, std::vector
   std::sort(sendShared.begin(), sendShared.end(), [](const Node& a, const Node& b) { return a.destRank < b.destRank; });
   std::vector<int> sendCounts(size, 0);
   for (const Node& s : sendShared) sendCounts[s.destRank]++;
-  std::vector<Node> recvShared;
+  NodeVec recvShared;
   std::vector<int> recvCounts;
   exchange_nodes(comm, sendShared, sendCounts, recvShared, recvCounts);
 
@@ -302,7 +328,7 @@ void construct_shared_nodes(libp_ogs_s& o, std::vector<Node>& nodes, std::vector
       start = end;
     }
   for (int r = 0; r < size; ++r) shOffsets[r + 1] = shOffsets[r] + shCounts[r];
-  std::vector<Node> shSend((size_t)shOffsets[size]);
+  NodeVec shSend((size_t)shOffsets[size]);
   std::vector<int> fill(size, 0);
   start = 0;
   for (dlong n = 0; n < recvN; ++n)
@@ -333,7 +359,7 @@ void build_csr(dlong nrows, const std::vector<dlong>& counts, std::vector<dlong>
 
 // gatherLocal / gatherHalo for Signed, Unsigned and Halo kinds
 // (LocalSignedSetup / LocalUnsignedSetup / LocalHaloSetup, ogsSetup.cpp:569-860)
-void local_setup(libp_ogs_s& o, const std::vector<Node>& nodes) {
+void local_setup(libp_ogs_s& o, const NodeVec& nodes) {
   OgsOperator& L = o.gatherLocal;
   OgsOperator& H = o.gatherHalo;
   L.Ncols = H.Ncols = o.N;
@@ -377,7 +403,7 @@ void local_setup(libp_ogs_s& o, const std::vector<Node>& nodes) {
 }
 
 // Pairwise exchange lists + post-exchange combine operator (ogsPairwise.cpp:194-415)
-void pairwise_setup(libp_ogs_s& o, std::vector<Node>& sharedNodes) {
+void pairwise_setup(libp_ogs_s& o, NodeVec& sharedNodes) {
   const libp_comm_s& comm = *o.comm;
   const int size = comm.size;
   const dlong Nhalo = o.gatherHalo.NrowsT, NhaloP = o.gatherHalo.NrowsN;
@@ -396,7 +422,7 @@ void pairwise_setup(libp_ogs_s& o, std::vector<Node>& sharedNodes) {
     if (s.sign == 2) o.exN.sendIds.push_back(s.newId);
     o.exT.sendIds.push_back(s.newId);
   }
-  std::vector<Node> recvNodes;
+  NodeVec recvNodes;
   exchange_nodes(comm, sharedNodes, sendCountsT, recvNodes, recvCountsT);
   const dlong Nrecv = (dlong)recvNodes.size();
 
@@ -538,8 +564,8 @@ extern "C" int libp_ogs_setup(libp_dlong N, libp_hlong* ids, libp_comm_t comm, i
     if (timing) { const double t1 = tnow(); fprintf(stderr, "[ogs setup] %-28s %.3f s\n", what, t1 - t0); t0 = t1; }
   };
   // compressed list of the non-zero ids (parallel: per-chunk counts, prefix, fill)
-  std::vector<Node> nodes;
-  std::vector<dlong> compact((size_t)N);  // position of id n in the compressed list
+  NodeVec nodes;
+  std::vector<dlong, default_init_alloc<dlong>> compact((size_t)N);  // position of id n in the compressed list
   {
     const int nchunks = 256;
     std::vector<size_t> cnt((size_t)nchunks + 1, 0);
@@ -576,7 +602,7 @@ extern "C" int libp_ogs_setup(libp_dlong N, libp_hlong* ids, libp_comm_t comm, i
   lap("node records");
   find_shared_nodes(*o, nodes);
   lap("find_shared_nodes");
-  std::vector<Node> sharedNodes;
+  NodeVec sharedNodes;
   construct_shared_nodes(*o, nodes, sharedNodes);
   lap("construct_shared_nodes");
   {
@@ -621,7 +647,7 @@ extern "C" int libp_ogs_setup(libp_dlong N, libp_hlong* ids, libp_comm_t comm, i
 extern "C" int libp_ogs_sort_selftest(libp_dlong n, libp_dlong nkeys, unsigned int seed, int* same) {
   LIBP_API_BEGIN
   LIBP_CHECK(n >= 0 && nkeys >= 1 && same, "bad argument");
-  std::vector<Node> a((size_t)n);
+  NodeVec a((size_t)n);
   unsigned long long st = seed * 2654435761ull + 12345ull;
   for (dlong i = 0; i < n; ++i) {
     st = st * 6364136223846793005ull + 1442695040888963407ull;
@@ -631,7 +657,7 @@ extern "C" int libp_ogs_sort_selftest(libp_dlong n, libp_dlong nkeys, unsigned i
     if ((st >> 20) & 1) nd.baseId = -nd.baseId;
     a[(size_t)i] = nd;
   }
-  std::vector<Node> b(a);
+  NodeVec b(a);
   std::sort(a.begin(), a.end(), [](const Node& x, const Node& y) { return habs(x.baseId) < habs(y.baseId); });
   exact_sort_nodes(b, [](const Node& x) { return (unsigned long long)habs(x.baseId); });
   int ok = 1;

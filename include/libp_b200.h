@@ -241,6 +241,13 @@ int libp_elliptic_zero_ahead_errors(libp_elliptic_t op, int* errors);
 int libp_elliptic_set_chain(libp_elliptic_t op, int chainElements, int stages);
 int libp_elliptic_set_default_chain(int chainElements, int stages);
 int libp_elliptic_chain_stats(libp_elliptic_t op, libp_dfloat* Aq, long long* stats, void* stream);
+/* ELEMENT MAP = TRILINEAR (ellipticSetup.cpp:131-134 selects ellipticPartialAxTrilinearHex3D,
+ * solvers/elliptic/okl/ellipticAxHex3D.okl:440-627): the operator recomputes the geometric factors from the element
+ * vertices EXYZ (device, [Nelements][3][8], reference vertex order) and the GLL nodes / weights (host, Nq entries)
+ * instead of streaming ggeo / wJ: 16 B per DOF + 0.4 B per node of geometry.  Fused mode, GLL D, chain kernel.
+ * Parallelepiped elements (every box element) take a constant-Jacobian shortcut.  EXYZ = NULL switches back. */
+int libp_elliptic_set_trilinear(libp_elliptic_t op, const libp_dfloat* EXYZ, const libp_dfloat* gllz,
+                                const libp_dfloat* gllw);
 int libp_elliptic_set_chunk(libp_elliptic_t op, libp_dlong chunkElements);
 int libp_elliptic_set_default_chunk(libp_dlong chunkElements);
 /* o_q and o_Aq are gathered vectors of Ndofs+Nhalo entries; the Nhalo tail of o_q is

@@ -116,6 +116,7 @@ SIGNATURES = {
     "libp_elliptic_set_chain": (i32, [vp, i32, i32]),
     "libp_elliptic_set_default_chain": (i32, [i32, i32]),
     "libp_elliptic_chain_stats": (i32, [vp, vp, P(C.c_longlong), vp]),
+    "libp_elliptic_set_trilinear": (i32, [vp, vp, vp, vp]),
     "libp_elliptic_set_chunk": (i32, [vp, i32]),
     "libp_elliptic_set_default_chunk": (i32, [i32]),
     "libp_elliptic_free": (i32, [vp]),

@@ -421,6 +421,17 @@ class Elliptic:
         check(L.load().libp_elliptic_chain_stats(self._h, _ptr(o_Aq), st, _stream()))
         return dict(chain=st[0], sectors=st[1], zero_sectors=st[2], positions=st[3], raw_elements=st[4], stages=st[5])
 
+    def set_trilinear(self, EXYZ, gllz=None, gllw=None):
+        """ELEMENT MAP = TRILINEAR: geometry recomputed from the element vertices EXYZ (device [E][3][8]);
+        EXYZ=None switches back to the stored factors (libp_elliptic_set_trilinear)"""
+        if EXYZ is None:
+            check(L.load().libp_elliptic_set_trilinear(self._h, None, None, None))
+            return
+        self.keep = self.keep + (EXYZ,)
+        z = np.ascontiguousarray(gllz, dtype=np.float64)
+        w = np.ascontiguousarray(gllw, dtype=np.float64)
+        check(L.load().libp_elliptic_set_trilinear(self._h, _ptr(EXYZ), _ptr(z), _ptr(w)))
+
     def set_chunk(self, chunk_elements):
         """elements per zero-fill piece of the fused operator (0 = off); see libp_elliptic_set_chunk"""
         check(L.load().libp_elliptic_set_chunk(self._h, int(chunk_elements)))

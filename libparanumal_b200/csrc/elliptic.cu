@@ -339,6 +339,19 @@ extern "C" int libp_elliptic_set_default_chain(int chainElements, int stages) {
   LIBP_API_END
 }
 
+extern "C" int libp_elliptic_set_trilinear(libp_elliptic_t op, const libp_dfloat* EXYZ, const libp_dfloat* gllz,
+                                           const libp_dfloat* gllw) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(op, "null handle");
+  if (EXYZ == nullptr) { op->chainPlan.EXYZ = nullptr; return LIBP_SUCCESS; }
+  LIBP_CHECK(gllz && gllw, "GLL nodes and weights (host arrays of Nq entries) are required");
+  LIBP_CHECK(op->d.mode == 1 && op->symD, "the trilinear operator needs the fused mode and a GLL derivative matrix");
+  LIBP_CHECK(op->chainL > 0, "the trilinear operator runs in the element-chain kernel (libp_elliptic_set_chain)");
+  op->chainPlan.EXYZ = EXYZ;
+  for (int i = 0; i < op->d.Nq; ++i) { op->chainPlan.gllz[i] = gllz[i]; op->chainPlan.gllw[i] = gllw[i]; }
+  LIBP_API_END
+}
+
 extern "C" int libp_elliptic_chain_stats(libp_elliptic_t op, libp_dfloat* Aq, long long* stats, void* stream) {
   LIBP_API_BEGIN
   LIBP_CHECK(op && stats, "null argument");

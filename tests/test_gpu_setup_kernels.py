@@ -124,3 +124,65 @@ def test_ax_trilinear_vs_oracle_and_stored_geometry(N, lam):
     for e in elist:
         sel[e * Np:(e + 1) * Np] = True
     assert rel(out3.cpu().numpy()[sel], ref3[sel]) < 1e-12
+
+
+def _exyz(mesh, distort=0.0, seed=0):
+    """[E,3,8] vertex array of a BoxMesh, optionally with a consistent random displacement of the lattice vertices"""
+    ex, ey, ez = mesh.element_vertices()
+    EX = np.stack([ex.cpu().numpy(), ey.cpu().numpy(), ez.cpu().numpy()], axis=1)
+    if distort > 0:
+        rng = np.random.default_rng(seed)
+        lat = {}
+        for e in range(EX.shape[0]):
+            for v in range(8):
+                key = tuple(np.round(EX[e, :, v] * 3 * 64).astype(int))
+                if key not in lat:
+                    lat[key] = rng.uniform(-distort, distort, 3)
+                EX[e, :, v] += lat[key]
+    return EX
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("distort", [0.0, 0.03])
+def test_trilinear_operator_mode(N, distort):
+    """libp_elliptic_set_trilinear: the operator with geometry on the fly (chain kernel, affine shortcut for the box,
+    general trilinear otherwise) == the operator on stored factors of the same elements, and == the oracle"""
+    import ctypes
+    from libparanumal_b200.problem import EllipticProblem
+    n, lam = 4, 0.7
+    Nq, Np = N + 1, (N + 1) ** 3
+    ctypes.CDLL("libc.so.6").srand(1)
+    mesh = BoxMesh(N, n, n, n, device="cuda", geometry=False)
+    E = mesh.Nelements
+    EX = _exyz(mesh, distort, 20 + N)
+    x, y, z = (torch.empty(E * Np, dtype=torch.float64, device="cuda") for _ in range(3))
+    api.mesh_physical_nodes_hex3d(Nq, E, dev(EX[:, 0].copy()), dev(EX[:, 1].copy()), dev(EX[:, 2].copy()), dev(mesh.gllz), x, y, z)
+    mesh.ggeo = torch.empty(E, 6, Np, dtype=torch.float64, device="cuda")
+    mesh.wJ = torch.empty(E, Np, dtype=torch.float64, device="cuda")
+    api.mesh_geometric_factors_hex3d(Nq, E, x, y, z, mesh.D, dev(mesh.gllw), mesh.ggeo, mesh.wJ)
+    p = EllipticProblem(N, n, lam=lam, mesh=mesh)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    q = p.vec()
+    q[: p.Ndofs] = torch.rand(p.Ndofs, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    ref = p.operator(q)[: p.Ndofs].cpu().numpy()
+    AqL = er.ax_trilinear_hex3d(Nq, EX, mesh.gllz, mesh.gllw, mesh.D_host, lam, q[: p.Ndofs].cpu().numpy(), G2L=p.G2L_host)
+    mp = p.ogs.maps("local")
+    oracle = er.gather_add(mp["rowStartsT"], mp["colIdsT"], AqL)
+    assert rel(ref, oracle) < 1e-11
+    dEX = dev(EX.reshape(-1))
+    p.op.set_trilinear(dEX, mesh.gllz, mesh.gllw)
+    for L_ in (8, 1, 3):
+        p.op.set_chain(L_, 1)
+        Aq = p.vec(fill=float("nan"))
+        p.op.Operator(q, Aq)
+        assert rel(Aq[: p.Ndofs].cpu().numpy(), oracle) < 1e-12, (N, distort, L_)
+    # Jacobi-PCG through the trilinear operator: same iteration count as on stored factors
+    M = p.jacobi()
+    r = p.vec()
+    r[: p.Ndofs] = torch.rand(p.Ndofs, dtype=torch.float64, device="cuda", generator=g)
+    its = []
+    for tri in (True, False):
+        p.op.set_trilinear(dEX if tri else None, mesh.gllz, mesh.gllw)
+        xs = p.vec()
+        its.append(p.pcg().Solve(p.op, M, xs, r.clone(), tol=1e-8, maxit=500))
+    assert abs(its[0] - its[1]) <= 1, its

@@ -20,6 +20,9 @@ ap.add_argument("--elements", type=int, default=64)
 ap.add_argument("--lam", type=float, default=0.0)
 ap.add_argument("--steps", type=int, default=50)
 ap.add_argument("--grid", default="0:2,4:2,8:2,16:2,32:2,64:2,16:3,32:3")
+ap.add_argument("--trilinear", action="store_true",
+                help="ELEMENT MAP = TRILINEAR: geometry recomputed from the element vertices (libp_elliptic_set_trilinear); "
+                     "fractions are of the trilinear byte model 16 B per DOF + 192 B per element")
 a = ap.parse_args()
 api.init(0)
 peak = 6545.3
@@ -33,10 +36,17 @@ q = p.vec()
 q[: p.Ndofs] = torch.rand(p.Ndofs, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
 E, Np = p.mesh.Nelements, p.mesh.Np
 alg = 8.0 * (6 + (a.lam != 0)) * E * Np + 16.0 * p.Ndofs
+if a.trilinear:
+    import numpy as np
+    ex, ey, ez = p.mesh.element_vertices()
+    EXYZ = torch.stack([ex, ey, ez], dim=1).contiguous().reshape(-1)
+    alg = 16.0 * p.Ndofs + 192.0 * E
 ref = None
 for item in a.grid.split(","):
     L, S = (int(v) for v in item.split(":"))
     p.op.set_chain(L, S)
+    if a.trilinear and L > 0:
+        p.op.set_trilinear(EXYZ, p.mesh.gllz, p.mesh.gllw)
     Aq = p.vec(fill=float("nan"))
     for _ in range(5):
         p.op.Operator(q, Aq)
@@ -55,7 +65,7 @@ for item in a.grid.split(","):
     if ref is None:
         ref = Aq.clone()
     diff = float((Aq[: p.Ndofs] - ref[: p.Ndofs]).abs().max() / ref[: p.Ndofs].abs().max())
-    print(json.dumps({"N": a.degree, "elements": a.elements, "lambda": a.lam, "chain": L, "stages": S,
+    print(json.dumps({"N": a.degree, "elements": a.elements, "lambda": a.lam, "chain": L, "stages": S, "trilinear": bool(a.trilinear and L > 0),
                       "ms_per_apply": ms, "gdofs": p.NglobalDofs / ms / 1e6, "step_frac": alg / ms / 1e6 / peak,
                       "zero_fill_ms": zms, "ax_ms": kms, "kernel_frac": alg / kms / 1e6 / peak,
                       "plan": st, "rel_diff_vs_first": diff}), flush=True)

@@ -16,3 +16,4 @@ grep -i "ogs\|setup" gpurun_out/r2q_bench_1gpu.err | head -40
 cat gpurun_out/r2q_bench_1gpu.json | cut -c1-1500
 timeout 2400 python -m pytest tests -x -q -m gpu > gpurun_out/r2q_pytest_gpu.log 2>&1
 tail -5 gpurun_out/r2q_pytest_gpu.log
+bash tools/profile_chain_orders.sh

@@ -86,3 +86,12 @@ g++ -fopenmp -O2 -std=c++17 -march=native -Wno-unused-function \
   -L"$W/libs" -llinearSolver -lmesh -lparAdogs -logs -llinAlg -lcore \
   "$W/libmpistub.a" -Wl,-rpath,"$BL" -L"$BL" -l:"$BLSO" -Wl,-rpath,"$W/occa/lib" -L"$W/occa/lib" -locca
 echo "initial-guess dump driver built: $OUT/dump_ig_driver"
+# 7. IPDG dump driver (our own code, oracle/refbuild/dump_ipdg_driver.cpp; single rank or under mpirun_stub.sh)
+g++ -fopenmp -O2 -std=c++17 -march=native -Wno-unused-function \
+  -DLIBP_DIR="\"$W\"" \
+  -I"$HERE/mpistub" -include "$W/lapack_rename.h" -I"$W/include" -I"$W/occa/include" -I"$W/solvers/elliptic" \
+  -o "$OUT/dump_ipdg_driver" "$HERE/dump_ipdg_driver.cpp" \
+  "$W/solvers/elliptic/libelliptic.a" \
+  -L"$W/libs" -lparAlmond -llinearSolver -lmesh -lparAdogs -logs -llinAlg -lcore \
+  "$W/libmpistub.a" -Wl,-rpath,"$BL" -L"$BL" -l:"$BLSO" -Wl,-rpath,"$W/occa/lib" -L"$W/occa/lib" -locca
+echo "IPDG dump driver built: $OUT/dump_ipdg_driver"

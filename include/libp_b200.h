@@ -124,6 +124,9 @@ int libp_ogs_setup(libp_dlong N, libp_hlong* ids, libp_comm_t comm, int kind, in
 /* Test hook: ogsBase_t::Setup depends on the tie order of libstdc++'s std::sort (ogsSetup.cpp:245-275); the library
  * runs the same introsort as parallel tasks.  Compares the two on n records with nkeys distinct keys. */
 int libp_ogs_sort_selftest(libp_dlong n, libp_dlong nkeys, unsigned int seed, int* same);
+/* Self-test of the bulk rand() draw of the setup (one draw per id group, ogsSetup.cpp:262): srand(seed), n draws taken
+ * in bulk from glibc's generator state followed by 100 rand() calls must equal n + 100 rand() calls.  Reseeds rand(). */
+int libp_ogs_rand_selftest(unsigned int seed, libp_dlong n, int* same);
 int libp_ogs_free(libp_ogs_t ogs);
 
 typedef struct {

@@ -128,18 +128,28 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 template <int Nq>
 __device__ __forceinline__ void load_row(const dfloat* __restrict__ row, dfloat (&v)[Nq]) {
+  if constexpr (Nq == 5 || Nq == 7 || Nq == 9) {  // dense rows (ChT::kDense) are not 16-byte aligned
 #pragma unroll
-  for (int c = 0; c < Nq / 2; ++c) {
-    const double2 w = *reinterpret_cast<const double2*>(row + 2 * c);
-    v[2 * c] = w.x; v[2 * c + 1] = w.y;
+    for (int c = 0; c < Nq; ++c) v[c] = row[c];
+  } else {
+#pragma unroll
+    for (int c = 0; c < Nq / 2; ++c) {
+      const double2 w = *reinterpret_cast<const double2*>(row + 2 * c);
+      v[2 * c] = w.x; v[2 * c + 1] = w.y;
+    }
+    if (Nq & 1) v[Nq - 1] = row[Nq - 1];
   }
-  if (Nq & 1) v[Nq - 1] = row[Nq - 1];
 }
 template <int Nq>
 __device__ __forceinline__ void store_row(dfloat* __restrict__ row, const dfloat (&o)[Nq]) {
+  if constexpr (Nq == 5 || Nq == 7 || Nq == 9) {
 #pragma unroll
-  for (int c = 0; c < Nq / 2; ++c) *reinterpret_cast<double2*>(row + 2 * c) = make_double2(o[2 * c], o[2 * c + 1]);
-  if (Nq & 1) row[Nq - 1] = o[Nq - 1];
+    for (int c = 0; c < Nq; ++c) row[c] = o[c];
+  } else {
+#pragma unroll
+    for (int c = 0; c < Nq / 2; ++c) *reinterpret_cast<double2*>(row + 2 * c) = make_double2(o[2 * c], o[2 * c + 1]);
+    if (Nq & 1) row[Nq - 1] = o[Nq - 1];
+  }
 }
 
 // Shared-memory geometry of the staging arrays.  Nq = 8: dense rows (LD = 8), slab stride 66; with layout C on
@@ -149,15 +159,29 @@ __device__ __forceinline__ void store_row(dfloat* __restrict__ row, const dfloat
 template <int Nq>
 struct ChT {
   static constexpr int Nq2 = Nq * Nq, Np = Nq * Nq * Nq;
-  static constexpr int EPB = (Nq == 2) ? 16 : (Nq == 3) ? 7 : (Nq == 4) ? 4 : (Nq == 5) ? 5 : (Nq == 6) ? 5
-                           : (Nq == 7) ? 2 : 1;
-  static constexpr int Work = EPB * Nq2;
+  // Odd orders (Nq = 5, 7, 9): "dense" geometry.  A 64-bit shared access is served per half-warp (16 lanes, 16
+  // eight-byte banks), so an element's Nq2 columns are padded to a multiple of 16 threads (half-warps never straddle
+  // two elements), rows and slabs are stored without row padding (layout C and the TMA-written factors are contiguous
+  // per half-warp), and the pencils of layouts A and B are dealt to the lanes by a table (ChainPerm) such that the 16
+  // lanes of a half-warp start in 16 different banks.  Slab strides below are the ones for which such a deal exists
+  // (every residue of k*SS + j*Nq resp. k*SS + i mod 16 occurs at most TPE/16 times); Nq = 5 has no common stride
+  // for A and B, so s_r / s_s get their own and s_u keeps one two-way conflict in layout B.
+  static constexpr bool kDense = (Nq == 5 || Nq == 7 || Nq == 9);
+  static constexpr int TPE = kDense ? ((Nq2 + 15) / 16) * 16 : Nq2;  // threads per element
+  static constexpr int EPB = kDense ? (Nq == 5 ? 4 : Nq == 7 ? 2 : 1)
+                           : (Nq == 2) ? 16 : (Nq == 3) ? 7 : (Nq == 4) ? 4 : (Nq == 6) ? 5 : 1;
+  static constexpr int Work = EPB * TPE;
   static constexpr int Threads = ((Work + 31) / 32) * 32;
-  static constexpr int LD = (Nq == 8) ? 8 : (Nq == 2) ? 2 : (Nq <= 4) ? 4 : (Nq <= 6) ? 6 : 10;
-  static constexpr int SS = (Nq == 8) ? 66 : (Nq == 2) ? 4 : (Nq == 3) ? 12 : (Nq == 4) ? 18 : (Nq == 5) ? 30
-                          : (Nq == 6) ? 38 : (Nq == 7) ? 70 : 90;
-  static constexpr int ESS = (Nq == 8) ? 8 * 66 : (Nq == 2) ? 10 : (Nq == 3) ? 42 : (Nq == 4) ? 72 : (Nq == 5) ? 150
-                           : (Nq == 6) ? 228 : (Nq == 7) ? 496 : Nq * SS;
+  static constexpr int LD = kDense ? Nq : (Nq == 8) ? 8 : (Nq == 2) ? 2 : (Nq <= 4) ? 4 : 6;
+  static constexpr int SS = (Nq == 8) ? 66 : (Nq == 2) ? 4 : (Nq == 3) ? 12 : (Nq == 4) ? 18 : (Nq == 6) ? 38 : 0;
+  static constexpr int ESS = (Nq == 8) ? 8 * 66 : (Nq == 2) ? 10 : (Nq == 3) ? 42 : (Nq == 4) ? 72 : (Nq == 6) ? 228 : 0;
+  // slab stride / element stride of s_u, s_r (layouts C + A), s_s (layouts C + B)
+  static constexpr int SSu = kDense ? (Nq == 5 ? 25 : Nq == 7 ? 50 : 82) : SS;
+  static constexpr int SSr = kDense ? (Nq == 5 ? 25 : Nq == 7 ? 50 : 82) : SS;
+  static constexpr int SSs = kDense ? (Nq == 5 ? 26 : Nq == 7 ? 50 : 82) : SS;
+  static constexpr int ESu = kDense ? (((Nq - 1) * SSu + Nq2 + 1) & ~1) : ESS;
+  static constexpr int ESr = kDense ? (((Nq - 1) * SSr + Nq2 + 1) & ~1) : ESS;
+  static constexpr int ESs = kDense ? (((Nq - 1) * SSs + Nq2 + 1) & ~1) : ESS;
   // wJ can only ride the bulk copy when its per-element block keeps 16-byte alignment
   static constexpr bool kBulkWJ = (Np % 2 == 0);
   // components per stage: 6 geometric factors (+ wJ for the screened operator)
@@ -167,10 +191,52 @@ struct ChT {
   __host__ __device__ static constexpr int stage_doubles(bool scr) { return EPB * slot_doubles(scr); }
 };
 
+// Dense orders: lane c of an element's TPE threads -> the i-pencil (k*Nq + j) it owns in layout A and the j-pencil
+// (k*Nq + i) it owns in layout B; 255 = idle in that phase.  Built on the host (chain_perm<Nq>()).
+struct ChainPerm {
+  unsigned char A[96], B[96];
+};
+
+// Per-thread shared-memory offsets of the three pencil orientations
+template <int Nq>
+struct ChIdx {
+  int es, ij, a, b;
+  bool valid, vA, vB;
+  int uC, rC, sC, uA, rA, uB, sB;
+  __device__ __forceinline__ ChIdx(int t, const ChainPerm& pm) {
+    using C = ChT<Nq>;
+    constexpr int Nq2 = C::Nq2, LD = C::LD;
+    const bool inSlot = (C::Work == C::Threads) ? true : t < C::Work;  // folded away when the block has no idle lanes
+    const int e0 = t / C::TPE, c = t - e0 * C::TPE;
+    es = inSlot ? e0 : 0;
+    valid = (C::TPE == Nq2) ? inSlot : (inSlot && c < Nq2);
+    ij = valid ? c : 0;
+    b = ij / Nq; a = ij - b * Nq;
+    uC = es * C::ESu + b * LD + a;
+    rC = es * C::ESr + b * LD + a;
+    sC = es * C::ESs + b * LD + a;
+    int kA, jA, kB, iB;
+    if constexpr (C::kDense) {
+      const int pA = pm.A[c], pB = pm.B[c];
+      vA = inSlot && pA != 255; vB = inSlot && pB != 255;
+      kA = vA ? pA / Nq : 0; jA = vA ? pA - kA * Nq : 0;
+      kB = vB ? pB / Nq : 0; iB = vB ? pB - kB * Nq : 0;
+    } else {
+      vA = vB = valid;
+      kA = (Nq == 8) ? a : b; jA = (Nq == 8) ? b : a;      // layout A: i-pencil (row)
+      kB = (Nq == 8) ? (4 * (b & 1) + (b >> 1)) : b; iB = a;  // layout B: j-pencil (column)
+    }
+    uA = es * C::ESu + kA * C::SSu + jA * LD;
+    rA = es * C::ESr + kA * C::SSr + jA * LD;
+    uB = es * C::ESu + kB * C::SSu + iB;
+    sB = es * C::ESs + kB * C::SSs + iB;
+  }
+};
+
 template <int Nq, int S, bool kScr>
 constexpr size_t chain_smem_bytes() {
   using C = ChT<Nq>;
-  return (size_t)8 * (S * C::stage_doubles(kScr) + 3 * C::EPB * C::ESS) + 8 * S + 4 * C::EPB + 16;
+  return (size_t)8 * (S * C::stage_doubles(kScr) + C::EPB * (C::ESu + C::ESr + C::ESs)) + 8 * S + 4 * C::EPB + 16;
 }
 
 struct ChainArgs {
@@ -191,31 +257,24 @@ struct ChainArgs {
 
 template <int Nq, int S, bool kDot, bool kScr, int kMinB>
 __global__ void __launch_bounds__(ChT<Nq>::Threads, kMinB)
-ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
+ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo, const __grid_constant__ ChainPerm pm) {
   if (A.doneFlag != nullptr && *A.doneFlag) return;
   using C = ChT<Nq>;
-  constexpr int Nq2 = C::Nq2, Np = C::Np, LD = C::LD, SS = C::SS, ESS = C::ESS, EPB = C::EPB;
+  constexpr int Nq2 = C::Nq2, Np = C::Np, LD = C::LD, SSu = C::SSu, SSr = C::SSr, SSs = C::SSs, EPB = C::EPB;
   constexpr int StageDoubles = C::stage_doubles(kScr), SlotDoubles = C::slot_doubles(kScr);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   dfloat* s_g = reinterpret_cast<dfloat*>(smem_raw);                    // [S][EPB][NG][Np]
   dfloat* s_u = s_g + S * StageDoubles;
-  dfloat* s_r = s_u + EPB * ESS;
-  dfloat* s_s = s_r + EPB * ESS;
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_s + EPB * ESS);       // [S]
+  dfloat* s_r = s_u + EPB * C::ESu;
+  dfloat* s_s = s_r + EPB * C::ESr;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_s + EPB * C::ESs);    // [S]
   int* s_hdr = reinterpret_cast<int*>(s_bar + S);                       // [EPB] header of the step to be issued next
 
   const int t = threadIdx.x;
-  const bool valid = t < C::Work;
-  const int es = valid ? t / Nq2 : 0;
-  const int ij = valid ? t - es * Nq2 : 0;
-  const int b = ij / Nq, a = ij - b * Nq;
-  const int nC = ij;                               // layout C: i = a, j = b (natural)
-  const int sC = es * ESS + b * LD + a;
-  // layout A: i-pencil (row); layout B: j-pencil (column)
-  const int kA = (Nq == 8) ? a : b, jA = (Nq == 8) ? b : a;
-  const int sA = es * ESS + kA * SS + jA * LD;
-  const int kB = (Nq == 8) ? (4 * (b & 1) + (b >> 1)) : b;
-  const int sB = es * ESS + kB * SS + a;
+  const ChIdx<Nq> X(t, pm);                        // layout C: i = a, j = b (natural); A: i-pencils; B: j-pencils
+  const bool valid = X.valid;
+  const int es = X.es, ij = X.ij, a = X.a, b = X.b;
+  const int nC = ij;
 
   constexpr bool screened = kScr;  // lambda != 0
   constexpr bool bulkW = screened && C::kBulkWJ;
@@ -293,13 +352,13 @@ ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
   };
   // q of a step is gathered straight into s_u (layout C slots of this thread) by 8-byte asynchronous copies: no
   // registers are held while the gathers are in flight
-  const uint32_t su_base = smem_u32(s_u + sC);
+  const uint32_t su_base = smem_u32(s_u + X.uC);
   auto gather_q_async = [&](const dlong (&id)[Nq]) {
     if (valid) {
 #pragma unroll
       for (int k = 0; k < Nq; ++k) {
         const bool on = id[k] >= 0;
-        cp_async8(su_base + 8u * (uint32_t)(k * SS), A.q + (on ? id[k] : 0), on ? 8u : 0u, polK);
+        cp_async8(su_base + 8u * (uint32_t)(k * SSu), A.q + (on ? id[k] : 0), on ? 8u : 0u, polK);
       }
     }
     cp_async_commit();
@@ -341,22 +400,25 @@ ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
     cp_async_wait_all();
     dfloat q_cur[Nq];
 #pragma unroll
-    for (int k = 0; k < Nq; ++k) q_cur[k] = s_u[sC + k * SS];
+    for (int k = 0; k < Nq; ++k) q_cur[k] = valid ? s_u[X.uC + k * SSu] : 0.0;  // idle lanes of a padded element would only add bank conflicts
     dfloat r_t[Nq];
     eo_apply<Nq, false>(eo, q_cur, r_t);
     __syncthreads();
 
     // ---- phase 1: r-derivative on i-pencils (layout A), s-derivative on j-pencils (layout B)
-    if (valid) {
+    if (X.vA) {
       dfloat v[Nq], o[Nq];
-      load_row<Nq>(&s_u[sA], v);
+      load_row<Nq>(&s_u[X.uA], v);
       eo_apply<Nq, false>(eo, v, o);
-      store_row<Nq>(&s_r[sA], o);
+      store_row<Nq>(&s_r[X.rA], o);
+    }
+    if (X.vB) {
+      dfloat v[Nq], o[Nq];
 #pragma unroll
-      for (int m = 0; m < Nq; ++m) v[m] = s_u[sB + m * LD];
+      for (int m = 0; m < Nq; ++m) v[m] = s_u[X.uB + m * LD];
       eo_apply<Nq, false>(eo, v, o);
 #pragma unroll
-      for (int j = 0; j < Nq; ++j) s_s[sB + j * LD] = o[j];
+      for (int j = 0; j < Nq; ++j) s_s[X.sB + j * LD] = o[j];
     }
     __syncthreads();
     // s_u is free: gather q of the next step into it while phases 2-4 run
@@ -367,7 +429,7 @@ ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
     dfloat r_Aq[Nq];
 #pragma unroll
     for (int k = 0; k < Nq; ++k) {
-      const dfloat qr = s_r[sC + k * SS], qs = s_s[sC + k * SS], qt = r_t[k];
+      const dfloat qr = valid ? s_r[X.rC + k * SSr] : 0.0, qs = valid ? s_s[X.sC + k * SSs] : 0.0, qt = r_t[k];
       dfloat G00 = 0, G01 = 0, G02 = 0, G11 = 0, G12 = 0, G22 = 0, GwJ = 0;
       if (active) {
         G00 = sg[0 * Np + k * Nq2]; G01 = sg[1 * Np + k * Nq2]; G02 = sg[2 * Np + k * Nq2];
@@ -375,8 +437,8 @@ ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
         if (screened) GwJ = C::kBulkWJ ? sg[6 * Np + k * Nq2] : r_w[k];
       }
       if (valid) {
-        s_r[sC + k * SS] = G00 * qr + G01 * qs + G02 * qt;
-        s_s[sC + k * SS] = G01 * qr + G11 * qs + G12 * qt;
+        s_r[X.rC + k * SSr] = G00 * qr + G01 * qs + G02 * qt;
+        s_s[X.sC + k * SSs] = G01 * qr + G11 * qs + G12 * qt;
       }
       r_t[k] = G02 * qr + G12 * qs + G22 * qt;
       r_Aq[k] = screened ? GwJ * A.lambda * q_cur[k] : 0.0;
@@ -391,22 +453,25 @@ ax_hex3d_chain_kernel(const ChainArgs A, const __grid_constant__ EoD eo) {
     if (t == 0) issue(n + S);
 
     // ---- phase 3: transposed derivatives, in place
-    if (valid) {
+    if (X.vA) {
       dfloat v[Nq], o[Nq];
-      load_row<Nq>(&s_r[sA], v);
+      load_row<Nq>(&s_r[X.rA], v);
       eo_apply<Nq, true>(eo, v, o);
-      store_row<Nq>(&s_r[sA], o);
+      store_row<Nq>(&s_r[X.rA], o);
+    }
+    if (X.vB) {
+      dfloat v[Nq], o[Nq];
 #pragma unroll
-      for (int m = 0; m < Nq; ++m) v[m] = s_s[sB + m * LD];
+      for (int m = 0; m < Nq; ++m) v[m] = s_s[X.sB + m * LD];
       eo_apply<Nq, true>(eo, v, o);
 #pragma unroll
-      for (int j = 0; j < Nq; ++j) s_s[sB + j * LD] = o[j];
+      for (int j = 0; j < Nq; ++j) s_s[X.sB + j * LD] = o[j];
     }
     __syncthreads();
 
     // ---- phase 4 (layout C): collect, p.Ap partial, plain store (first touch of a private row) or reduction
 #pragma unroll
-    for (int k = 0; k < Nq; ++k) r_Aq[k] += s_r[sC + k * SS] + s_s[sC + k * SS];
+    for (int k = 0; k < Nq; ++k) r_Aq[k] += valid ? s_r[X.rC + k * SSr] + s_s[X.sC + k * SSs] : 0.0;
     if (kDot && active) {
 #pragma unroll
       for (int k = 0; k < Nq; ++k) dacc += q_cur[k] * r_Aq[k];
@@ -462,27 +527,21 @@ struct TriConst {
 template <int Nq, bool kDot, bool kScr, int kMinB>
 __global__ void __launch_bounds__(ChT<Nq>::Threads, kMinB)
 ax_hex3d_chain_tri_kernel(const ChainArgs A, const dfloat* __restrict__ EXYZ, const __grid_constant__ EoD eo,
-                          const __grid_constant__ TriConst gl) {
+                          const __grid_constant__ TriConst gl, const __grid_constant__ ChainPerm pm) {
   if (A.doneFlag != nullptr && *A.doneFlag) return;
   using C = ChT<Nq>;
-  constexpr int Nq2 = C::Nq2, Np = C::Np, LD = C::LD, SS = C::SS, ESS = C::ESS, EPB = C::EPB;
+  constexpr int Nq2 = C::Nq2, Np = C::Np, LD = C::LD, SSu = C::SSu, SSr = C::SSr, SSs = C::SSs, EPB = C::EPB;
   constexpr int NV = (24 + Nq2 - 1) / Nq2;  // vertex coordinates each thread of a slot fetches
-  __shared__ __align__(16) dfloat s_u[EPB * ESS];
-  __shared__ __align__(16) dfloat s_r[EPB * ESS];
-  __shared__ __align__(16) dfloat s_s[EPB * ESS];
+  __shared__ __align__(16) dfloat s_u[EPB * C::ESu];
+  __shared__ __align__(16) dfloat s_r[EPB * C::ESr];
+  __shared__ __align__(16) dfloat s_s[EPB * C::ESs];
   __shared__ dfloat s_v[EPB][24];
 
   const int t = threadIdx.x;
-  const bool valid = t < C::Work;
-  const int es = valid ? t / Nq2 : 0;
-  const int ij = valid ? t - es * Nq2 : 0;
-  const int b = ij / Nq, a = ij - b * Nq;
+  const ChIdx<Nq> X(t, pm);                        // layout C: i = a, j = b (natural); A: i-pencils; B: j-pencils
+  const bool valid = X.valid;
+  const int es = X.es, ij = X.ij, a = X.a, b = X.b;
   const int nC = ij;
-  const int sC = es * ESS + b * LD + a;
-  const int kA = (Nq == 8) ? a : b, jA = (Nq == 8) ? b : a;
-  const int sA = es * ESS + kA * SS + jA * LD;
-  const int kB = (Nq == 8) ? (4 * (b & 1) + (b >> 1)) : b;
-  const int sB = es * ESS + kB * SS + a;
   constexpr bool screened = kScr;
   const uint64_t polS = pol_evict_first(), polK = pol_evict_last();
   const int chain = blockIdx.x * EPB + es;
@@ -524,13 +583,13 @@ ax_hex3d_chain_tri_kernel(const ChainArgs A, const dfloat* __restrict__ EXYZ, co
       v[m] = (h >= 0 && c < 24) ? __ldg(EXYZ + (size_t)(h >> 1) * 24 + c) : 0.0;
     }
   };
-  const uint32_t su_base = smem_u32(s_u + sC);
+  const uint32_t su_base = smem_u32(s_u + X.uC);
   auto gather_q_async = [&](const dlong (&id)[Nq]) {
     if (valid) {
 #pragma unroll
       for (int k = 0; k < Nq; ++k) {
         const bool on = id[k] >= 0;
-        cp_async8(su_base + 8u * (uint32_t)(k * SS), A.q + (on ? id[k] : 0), on ? 8u : 0u, polK);
+        cp_async8(su_base + 8u * (uint32_t)(k * SSu), A.q + (on ? id[k] : 0), on ? 8u : 0u, polK);
       }
     }
     cp_async_commit();
@@ -569,22 +628,25 @@ ax_hex3d_chain_tri_kernel(const ChainArgs A, const dfloat* __restrict__ EXYZ, co
     cp_async_wait_all();
     dfloat q_cur[Nq];
 #pragma unroll
-    for (int k = 0; k < Nq; ++k) q_cur[k] = s_u[sC + k * SS];
+    for (int k = 0; k < Nq; ++k) q_cur[k] = valid ? s_u[X.uC + k * SSu] : 0.0;  // idle lanes of a padded element would only add bank conflicts
     dfloat r_t[Nq];
     eo_apply<Nq, false>(eo, q_cur, r_t);
     __syncthreads();
 
     // ---- phase 1
-    if (valid) {
+    if (X.vA) {
       dfloat v[Nq], o[Nq];
-      load_row<Nq>(&s_u[sA], v);
+      load_row<Nq>(&s_u[X.uA], v);
       eo_apply<Nq, false>(eo, v, o);
-      store_row<Nq>(&s_r[sA], o);
+      store_row<Nq>(&s_r[X.rA], o);
+    }
+    if (X.vB) {
+      dfloat v[Nq], o[Nq];
 #pragma unroll
-      for (int m = 0; m < Nq; ++m) v[m] = s_u[sB + m * LD];
+      for (int m = 0; m < Nq; ++m) v[m] = s_u[X.uB + m * LD];
       eo_apply<Nq, false>(eo, v, o);
 #pragma unroll
-      for (int j = 0; j < Nq; ++j) s_s[sB + j * LD] = o[j];
+      for (int j = 0; j < Nq; ++j) s_s[X.sB + j * LD] = o[j];
     }
     // Jacobian coefficients of this thread's (r_i, s_j): d/dr and d/ds are linear in t, d/dt does not depend on t
     dfloat ar[3], br[3], as_[3], bs[3], ct[3];
@@ -622,7 +684,7 @@ ax_hex3d_chain_tri_kernel(const ChainArgs A, const dfloat* __restrict__ EXYZ, co
     }
 #pragma unroll
     for (int k = 0; k < Nq; ++k) {
-      const dfloat qr = s_r[sC + k * SS], qs = s_s[sC + k * SS], qt = r_t[k];
+      const dfloat qr = valid ? s_r[X.rC + k * SSr] : 0.0, qs = valid ? s_s[X.sC + k * SSs] : 0.0, qt = r_t[k];
       const dfloat W = wij * gl.w[k];
       dfloat G00, G01, G02, G11, G12, G22, GwJ;
       if (affine) {
@@ -644,8 +706,8 @@ ax_hex3d_chain_tri_kernel(const ChainArgs A, const dfloat* __restrict__ EXYZ, co
         GwJ = W * J;
       }
       if (valid) {
-        s_r[sC + k * SS] = G00 * qr + G01 * qs + G02 * qt;
-        s_s[sC + k * SS] = G01 * qr + G11 * qs + G12 * qt;
+        s_r[X.rC + k * SSr] = G00 * qr + G01 * qs + G02 * qt;
+        s_s[X.sC + k * SSs] = G01 * qr + G11 * qs + G12 * qt;
       }
       r_t[k] = G02 * qr + G12 * qs + G22 * qt;
       r_Aq[k] = screened ? GwJ * A.lambda * q_cur[k] : 0.0;
@@ -659,22 +721,25 @@ ax_hex3d_chain_tri_kernel(const ChainArgs A, const dfloat* __restrict__ EXYZ, co
     __syncthreads();
 
     // ---- phase 3
-    if (valid) {
+    if (X.vA) {
       dfloat v[Nq], o[Nq];
-      load_row<Nq>(&s_r[sA], v);
+      load_row<Nq>(&s_r[X.rA], v);
       eo_apply<Nq, true>(eo, v, o);
-      store_row<Nq>(&s_r[sA], o);
+      store_row<Nq>(&s_r[X.rA], o);
+    }
+    if (X.vB) {
+      dfloat v[Nq], o[Nq];
 #pragma unroll
-      for (int m = 0; m < Nq; ++m) v[m] = s_s[sB + m * LD];
+      for (int m = 0; m < Nq; ++m) v[m] = s_s[X.sB + m * LD];
       eo_apply<Nq, true>(eo, v, o);
 #pragma unroll
-      for (int j = 0; j < Nq; ++j) s_s[sB + j * LD] = o[j];
+      for (int j = 0; j < Nq; ++j) s_s[X.sB + j * LD] = o[j];
     }
     __syncthreads();
 
     // ---- phase 4
 #pragma unroll
-    for (int k = 0; k < Nq; ++k) r_Aq[k] += s_r[sC + k * SS] + s_s[sC + k * SS];
+    for (int k = 0; k < Nq; ++k) r_Aq[k] += valid ? s_r[X.rC + k * SSr] + s_s[X.sC + k * SSs] : 0.0;
     if (kDot && active) {
 #pragma unroll
       for (int k = 0; k < Nq; ++k) dacc += q_cur[k] * r_Aq[k];
@@ -850,6 +915,38 @@ __global__ void __launch_bounds__(256) zero_fill_kernel(size_t nSectors, dlong n
 
 int grid_for(size_t n) { return (int)std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 32); }
 
+// Deal the pencils of layouts A and B to the lanes of an element (dense orders, see ChT): the pencils whose first
+// word falls into the same 8-byte bank go to different half-warps.
+template <int Nq>
+const ChainPerm& chain_perm() {
+  static const ChainPerm pm = [] {
+    using C = ChT<Nq>;
+    ChainPerm p;
+    std::memset(&p, 255, sizeof(p));
+    if (C::kDense) {
+      constexpr int G = C::TPE / 16;
+      auto deal = [&](unsigned char* out, int SSx, bool isA) {
+        int used[8] = {0}, cnt[16] = {0};
+        for (int k = 0; k < Nq; ++k)
+          for (int x = 0; x < Nq; ++x) {
+            const int r = (k * SSx + (isA ? x * Nq : x)) & 15;
+            int g = cnt[r]++;
+            if (g >= G || used[g] >= 16) {  // more copies of a residue than half-warps: least loaded group
+              g = 0;
+              for (int h = 1; h < G; ++h)
+                if (used[h] < used[g]) g = h;
+            }
+            out[16 * g + used[g]++] = (unsigned char)(k * Nq + x);
+          }
+      };
+      deal(p.A, C::SSr, true);
+      deal(p.B, C::SSs, false);
+    }
+    return p;
+  }();
+  return pm;
+}
+
 template <int Nq, int S, bool kDot, bool kScr>
 void launch_chain_t(const ChainArgs& A, const EoD& eo, cudaStream_t s) {
   using C = ChT<Nq>;
@@ -865,7 +962,7 @@ void launch_chain_t(const ChainArgs& A, const EoD& eo, cudaStream_t s) {
     configured = true;
   }
   const int grid = (A.nChains + C::EPB - 1) / C::EPB;
-  kern<<<grid, C::Threads, smem, s>>>(A, eo);
+  kern<<<grid, C::Threads, smem, s>>>(A, eo, chain_perm<Nq>());
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -894,7 +991,7 @@ int launch_chain_tri(const ChainArgs& A, const dfloat* EXYZ, const EoD& eo, cons
   constexpr int minb = (384 + C::Threads - 1) / C::Threads;  // ~170 registers per thread: no spills at Nq = 8
   const int grid = (A.nChains + C::EPB - 1) / C::EPB;
   const bool scr = A.lambda != 0.0;
-#define GO(DOT, SCR) ax_hex3d_chain_tri_kernel<Nq, DOT, SCR, minb><<<grid, C::Threads, 0, s>>>(A, EXYZ, eo, gl)
+#define GO(DOT, SCR) ax_hex3d_chain_tri_kernel<Nq, DOT, SCR, minb><<<grid, C::Threads, 0, s>>>(A, EXYZ, eo, gl, chain_perm<Nq>())
   if (A.dotPartials) { if (scr) GO(true, true); else GO(true, false); }
   else { if (scr) GO(false, true); else GO(false, false); }
 #undef GO

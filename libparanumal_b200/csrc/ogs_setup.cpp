@@ -11,8 +11,11 @@
 //     (ogsSetup.cpp:411-433); columns ascend in local id (ogsSetup.cpp:637-663).
 // Collectives go through libp_comm_s (host callbacks; memcpy when size==1).
 #include <algorithm>
+#include <array>
 #include <chrono>
+#include <cstdint>
 #include <cstdlib>
+#include <string>
 #include <numeric>
 
 #include "ogs.hpp"
@@ -120,6 +123,67 @@ struct ExactSort {
   }
 };
 
+// ---- glibc rand() in bulk ----------------------------------------------------------------------------------------
+// ogsBase_t::FindSharedNodes draws one rand() per id group (ogsSetup.cpp:262) from the stream the embedding program
+// seeded; 89 M calls through rand()'s lock cost close to a second at 64^3.  glibc's default generator (TYPE_3 of
+// random_r: r[i] = r[i-3] + r[i-31], output r[i] >> 1) keeps its table in a state array that initstate()/setstate()
+// hand out, with the rear index saved in word 0 (5 * rear + type) whenever the state is switched.  take() switches to
+// a scratch state, advances the REAL table n steps inline, and switches back: the values are the ones n rand() calls
+// would have returned and the process-wide stream continues exactly where they would have left it.  Any other
+// generator type (a program that called initstate itself) falls back to calling rand().
+struct GlibcRandBulk {
+  static void take(std::vector<int, default_init_alloc<int>>& out, size_t n) {
+    out.resize(n);
+    if (n == 0) return;
+    alignas(8) static int32_t scratch[32];
+    char* oldp = initstate(1u, reinterpret_cast<char*>(scratch), 128);
+    int32_t* st = reinterpret_cast<int32_t*>(oldp);
+    if (oldp == nullptr || st[0] % 5 != 3 || st[0] < 0 || st[0] / 5 >= 31) {
+      if (oldp != nullptr) setstate(oldp);
+      for (size_t i = 0; i < n; ++i) out[i] = rand();
+      return;
+    }
+    int rear = st[0] / 5, front = (rear + 3) % 31;
+    uint32_t tbl[31];
+    for (int i = 0; i < 31; ++i) tbl[i] = (uint32_t)st[1 + i];
+    for (size_t i = 0; i < n; ++i) {
+      const uint32_t v = (tbl[front] += tbl[rear]);
+      out[i] = (int)(v >> 1);
+      if (++front == 31) front = 0;
+      if (++rear == 31) rear = 0;
+    }
+    for (int i = 0; i < 31; ++i) st[1 + i] = (int32_t)tbl[i];
+    st[0] = 5 * rear + 3;
+    setstate(oldp);
+  }
+};
+
+// ---- records sorted by |baseId|: cut into chunks that start at group boundaries --------------------------------
+struct GroupChunks {
+  std::vector<size_t> begin;   // [nchunks + 1] record index, every entry is the first record of a group (or n)
+  std::vector<size_t> group0;  // [nchunks + 1] index of the chunk's first group
+  size_t ngroups = 0;
+  GroupChunks(const NodeVec& a, int nchunks) : begin((size_t)nchunks + 1), group0((size_t)nchunks + 1, 0) {
+    const size_t n = a.size(), per = (n + nchunks - 1) / std::max(nchunks, 1);
+    for (int c = 0; c <= nchunks; ++c) {
+      size_t b = std::min(n, (size_t)c * per);
+      while (b > 0 && b < n && habs(a[b].baseId) == habs(a[b - 1].baseId)) ++b;
+      begin[(size_t)c] = b;
+    }
+    begin[(size_t)nchunks] = n;
+#pragma omp parallel for schedule(static)
+    for (int c = 0; c < nchunks; ++c) {
+      size_t g = 0;
+      for (size_t i = begin[(size_t)c]; i < begin[(size_t)c + 1]; ++i)
+        g += (i == begin[(size_t)c]) || habs(a[i].baseId) != habs(a[i - 1].baseId);
+      group0[(size_t)c + 1] = g;
+    }
+    for (int c = 0; c < nchunks; ++c) group0[(size_t)c + 1] += group0[(size_t)c];
+    ngroups = group0[(size_t)nchunks];
+  }
+};
+constexpr int kSetupChunks = 1024;
+
 // a = a permuted so that it is sorted by key(a[i]) with std::sort's exact tie order
 template <class KeyFn>
 void exact_sort_nodes(std::vector<struct Node>& a, KeyFn key);
@@ -208,33 +272,50 @@ void find_shared_nodes(libp_ogs_s& o, NodeVec& nodes) {
   // same algorithm + equivalent strict weak order as the reference => same tie order
   exact_sort_nodes(recv, [](const Node& a) { return (unsigned long long)habs(a.baseId); });
 
+  // one pass per id group, groups dealt to threads in chunks; the rand() draws are taken from the stream up front,
+  // one per group in sorted order, exactly as the sequential loop of the reference consumes them
   int is_unique = 1;
-  dlong start = 0;
-  for (dlong n = 0; n < recvN; ++n) {
-    if (n == recvN - 1 || habs(recv[n].baseId) != habs(recv[n + 1].baseId)) {
-      const dlong end = n + 1;
-      int positiveCount = 0;
-      if (o.unique) {
-        const hlong baseId = habs(recv[start].baseId);
-        const int m = rand() % (end - start);  // glibc stream shared with the embedding program
-        for (dlong i = start; i < end; ++i) recv[i].baseId = -baseId;
-        recv[start + m].baseId = baseId;
-        positiveCount = 1;
-      } else {
-        for (dlong i = start; i < end; ++i)
-          if (recv[i].baseId > 0) positiveCount++;
-        if (positiveCount != 1) is_unique = 0;
+  {
+    const GroupChunks gc(recv, kSetupChunks);
+    std::vector<int, default_init_alloc<int>> draws;
+    if (o.unique) GlibcRandBulk::take(draws, gc.ngroups);
+    long long badId = 0;
+    int badCount = -1;
+#pragma omp parallel for schedule(dynamic, 4) reduction(min : is_unique)
+    for (int c = 0; c < kSetupChunks; ++c) {
+      size_t g = gc.group0[(size_t)c];
+      dlong start = (dlong)gc.begin[(size_t)c];
+      const dlong cend = (dlong)gc.begin[(size_t)c + 1];
+      for (dlong n = start; n < cend; ++n) {
+        if (n == cend - 1 || habs(recv[n].baseId) != habs(recv[n + 1].baseId)) {
+          const dlong end = n + 1;
+          int positiveCount = 0;
+          if (o.unique) {
+            const hlong baseId = habs(recv[start].baseId);
+            const int m = draws[g] % (end - start);
+            for (dlong i = start; i < end; ++i) recv[i].baseId = -baseId;
+            recv[start + m].baseId = baseId;
+            positiveCount = 1;
+          } else {
+            for (dlong i = start; i < end; ++i)
+              if (recv[i].baseId > 0) positiveCount++;
+            if (positiveCount != 1) is_unique = 0;
+          }
+          if (o.kind == LIBP_HALO && positiveCount != 1) {
+#pragma omp critical(libp_ogs_bad_halo)
+            { badId = (long long)habs(recv[start].baseId); badCount = positiveCount; }
+          }
+          int shared = 1;
+          const int r0 = recv[start].rank;
+          for (dlong i = start + 1; i < end; ++i)
+            if (recv[i].rank != r0) { shared = 2; break; }
+          for (dlong i = start; i < end; ++i) recv[i].sign = shared;
+          start = end;
+          ++g;
+        }
       }
-      LIBP_CHECK(!(o.kind == LIBP_HALO && positiveCount != 1),
-                 "Found " + std::to_string(positiveCount) + " positive Ids for baseId: " +
-                     std::to_string((long long)habs(recv[start].baseId)) + ".");
-      int shared = 1;
-      const int r0 = recv[start].rank;
-      for (dlong i = start + 1; i < end; ++i)
-        if (recv[i].rank != r0) { shared = 2; break; }
-      for (dlong i = start; i < end; ++i) recv[i].sign = shared;
-      start = end;
     }
+    LIBP_CHECK(badCount < 0, "Found " + std::to_string(badCount) + " positive Ids for baseId: " + std::to_string(badId) + ".");
   }
   int64_t u = is_unique;
   comm.allreduce_i64(&u, 1, LIBP_MIN);
@@ -262,24 +343,39 @@ void construct_shared_nodes(libp_ogs_s& o, NodeVec& nodes, NodeVec& sharedNodes)
     return ((unsigned long long)habs(a.baseId) << 1) | (unsigned long long)(a.baseId < 0 ? 1 : 0);
   });
 
-  dlong NbaseIds = 0;
-  o.NlocalT = o.NlocalP = o.NhaloT = o.NhaloP = 0;
-  dlong start = 0;
-  for (dlong n = 0; n < Nids; ++n) {
-    if (n == Nids - 1 || habs(nodes[n].baseId) != habs(nodes[n + 1].baseId)) {
-      const dlong end = n + 1;
-      int sign = std::abs(nodes[start].sign);
-      if (nodes[start].baseId < 0) {
-        sign = -sign;
-        for (dlong i = start; i < end; ++i) nodes[i].sign = sign;
+  // group pass (parallel over chunks of whole groups): ownership sign, group number, first local appearance
+  const GroupChunks gc(nodes, kSetupChunks);
+  const dlong NbaseIds = (dlong)gc.ngroups;
+  std::vector<dlong, default_init_alloc<dlong>> firstPos((size_t)NbaseIds);
+  std::vector<signed char, default_init_alloc<signed char>> groupSign((size_t)NbaseIds);
+  std::vector<NodeVec> chunkShared((size_t)kSetupChunks);
+  long long nLT = 0, nLP = 0, nHT = 0, nHP = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : nLT, nLP, nHT, nHP)
+  for (int c = 0; c < kSetupChunks; ++c) {
+    dlong g = (dlong)gc.group0[(size_t)c];
+    dlong start = (dlong)gc.begin[(size_t)c];
+    const dlong cend = (dlong)gc.begin[(size_t)c + 1];
+    for (dlong n = start; n < cend; ++n) {
+      if (n == cend - 1 || habs(nodes[n].baseId) != habs(nodes[n + 1].baseId)) {
+        const dlong end = n + 1;
+        int sign = std::abs(nodes[start].sign);
+        if (nodes[start].baseId < 0) {
+          sign = -sign;
+          for (dlong i = start; i < end; ++i) nodes[i].sign = sign;
+        }
+        if (std::abs(sign) == 1) { nLT++; if (sign == 1) nLP++; }
+        else { nHT++; if (sign == 2) nHP++; }
+        dlong fp = nodes[start].localId;
+        for (dlong i = start; i < end; ++i) { nodes[i].newId = g; fp = std::min(fp, nodes[i].localId); }
+        firstPos[(size_t)g] = fp;
+        groupSign[(size_t)g] = (signed char)sign;
+        if (std::abs(sign) == 2) chunkShared[(size_t)c].push_back(nodes[start]);
+        ++g;
+        start = end;
       }
-      if (std::abs(sign) == 1) { o.NlocalT++; if (sign == 1) o.NlocalP++; }
-      else { o.NhaloT++; if (sign == 2) o.NhaloP++; }
-      for (dlong i = start; i < end; ++i) nodes[i].newId = NbaseIds;
-      NbaseIds++;
-      start = end;
     }
   }
+  o.NlocalT = (dlong)nLT; o.NlocalP = (dlong)nLP; o.NhaloT = (dlong)nHT; o.NhaloP = (dlong)nHP;
   o.Ngather = o.NlocalP + o.NhaloP;
   int64_t ng = o.Ngather;
   comm.allreduce_i64(&ng, 1, LIBP_ADD);
@@ -287,24 +383,43 @@ void construct_shared_nodes(libp_ogs_s& o, NodeVec& nodes, NodeVec& sharedNodes)
 
   NodeVec sendShared;
   sendShared.reserve((size_t)o.NhaloT);
-  for (dlong n = 0; n < Nids; ++n)
-    if (n == 0 || habs(nodes[n].baseId) != habs(nodes[n - 1].baseId))
-      if (std::abs(nodes[n].sign) == 2) sendShared.push_back(nodes[n]);
+  for (const NodeVec& v : chunkShared) sendShared.insert(sendShared.end(), v.begin(), v.end());
+  chunkShared.clear();
 
   permute_by(nodes, [](const Node& n) { return n.localId; });  // compressed local order
 
-  // renumber groups by first appearance: owner-local, other-local, owner-halo, other-halo
-  std::vector<dlong> indexMap((size_t)NbaseIds, -1);
-  dlong localCntN = 0, localCntT = o.NlocalP, haloCntN = 0, haloCntT = o.NhaloP;
-  for (dlong n = 0; n < Nids; ++n) {
-    const dlong g = nodes[n].newId;
-    if (indexMap[g] == -1) {
-      if (nodes[n].sign == 1) indexMap[g] = localCntN++;
-      else if (nodes[n].sign == -1) indexMap[g] = localCntT++;
-      else if (nodes[n].sign == 2) indexMap[g] = haloCntN++;
-      else indexMap[g] = haloCntT++;
+  // renumber groups by first appearance: owner-local, other-local, owner-halo, other-halo.  A group's new number is
+  // the count of groups of its class that appear earlier in local order = a prefix sum over the first appearances.
+  std::vector<dlong, default_init_alloc<dlong>> indexMap((size_t)NbaseIds);
+  {
+    auto cls = [](int sign) { return sign == 1 ? 0 : sign == -1 ? 1 : sign == 2 ? 2 : 3; };
+    const int nch = kSetupChunks;
+    const size_t per = ((size_t)Nids + nch - 1) / nch;
+    std::vector<std::array<dlong, 4>> cnt((size_t)nch + 1, std::array<dlong, 4>{0, 0, 0, 0});
+#pragma omp parallel for schedule(static)
+    for (int c = 0; c < nch; ++c) {
+      std::array<dlong, 4> k{0, 0, 0, 0};
+      const size_t b = std::min<size_t>((size_t)Nids, c * per), e = std::min<size_t>((size_t)Nids, b + per);
+      for (size_t n = b; n < e; ++n) {
+        const dlong g = nodes[n].newId;
+        if (firstPos[(size_t)g] == (dlong)n) k[(size_t)cls(groupSign[(size_t)g])]++;
+      }
+      cnt[(size_t)c + 1] = k;
     }
-    nodes[n].newId = indexMap[g];
+    cnt[0] = {0, o.NlocalP, 0, o.NhaloP};
+    for (int c = 0; c < nch; ++c)
+      for (int q = 0; q < 4; ++q) cnt[(size_t)c + 1][(size_t)q] += cnt[(size_t)c][(size_t)q];
+#pragma omp parallel for schedule(static)
+    for (int c = 0; c < nch; ++c) {
+      std::array<dlong, 4> k = cnt[(size_t)c];
+      const size_t b = std::min<size_t>((size_t)Nids, c * per), e = std::min<size_t>((size_t)Nids, b + per);
+      for (size_t n = b; n < e; ++n) {
+        const dlong g = nodes[n].newId;
+        if (firstPos[(size_t)g] == (dlong)n) indexMap[(size_t)g] = k[(size_t)cls(groupSign[(size_t)g])]++;
+      }
+    }
+#pragma omp parallel for schedule(static)
+    for (dlong n = 0; n < Nids; ++n) nodes[n].newId = indexMap[(size_t)nodes[n].newId];
   }
   for (Node& s : sendShared) s.localId = indexMap[s.newId];
 
@@ -320,7 +435,7 @@ void construct_shared_nodes(libp_ogs_s& o, NodeVec& nodes, NodeVec& sharedNodes)
 
   const dlong recvN = (dlong)recvShared.size();
   std::vector<int> shCounts(size, 0), shOffsets(size + 1, 0);
-  start = 0;
+  dlong start = 0;
   for (dlong n = 0; n < recvN; ++n)
     if (n == recvN - 1 || habs(recvShared[n].baseId) != habs(recvShared[n + 1].baseId)) {
       const dlong end = n + 1;
@@ -373,33 +488,53 @@ void local_setup(libp_ogs_s& o, const NodeVec& nodes) {
     if (isHaloKind) return n.sign == 2;
     return n.baseId > 0;
   };
-  for (const Node& n : nodes) {
+  // row lengths, then columns: both passes run over the nodes in parallel with relaxed atomic cursors, which leaves
+  // the entries of a row in arrival order; a per-row sort restores the reference's order (ascending local id,
+  // ogsSetup.cpp:637-663) - rows are a handful of entries long
+  auto bump = [](dlong& c) { return __atomic_fetch_add(&c, 1, __ATOMIC_RELAXED); };
+  const size_t nn = nodes.size();
+#pragma omp parallel for schedule(static)
+  for (size_t i = 0; i < nn; ++i) {
+    const Node& n = nodes[i];
     if (std::abs(n.sign) == 1) {
       if (isHaloKind) continue;
-      if (inN(n)) lN[n.newId]++;
-      lT[n.newId]++;
+      if (inN(n)) bump(lN[n.newId]);
+      bump(lT[n.newId]);
     } else {
-      if (inN(n)) hN[n.newId]++;
-      hT[n.newId]++;
+      if (inN(n)) bump(hN[n.newId]);
+      bump(hT[n.newId]);
     }
   }
   build_csr(L.NrowsT, lN, L.rowStartsN); build_csr(L.NrowsT, lT, L.rowStartsT);
   build_csr(H.NrowsT, hN, H.rowStartsN); build_csr(H.NrowsT, hT, H.rowStartsT);
-  L.colIdsN.assign((size_t)L.nnzN(), 0); L.colIdsT.assign((size_t)L.nnzT(), 0);
-  H.colIdsN.assign((size_t)H.nnzN(), 0); H.colIdsT.assign((size_t)H.nnzT(), 0);
-  std::fill(lN.begin(), lN.end(), 0); std::fill(lT.begin(), lT.end(), 0);
-  std::fill(hN.begin(), hN.end(), 0); std::fill(hT.begin(), hT.end(), 0);
-  for (const Node& n : nodes) {
+  L.colIdsN.resize((size_t)L.nnzN()); L.colIdsT.resize((size_t)L.nnzT());
+  H.colIdsN.resize((size_t)H.nnzN()); H.colIdsT.resize((size_t)H.nnzT());
+  auto zero = [](std::vector<dlong>& v) {
+    const size_t m = v.size();
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < m; ++i) v[i] = 0;
+  };
+  zero(lN); zero(lT); zero(hN); zero(hT);
+#pragma omp parallel for schedule(static)
+  for (size_t i = 0; i < nn; ++i) {
+    const Node& n = nodes[i];
     const dlong g = n.newId;
     if (std::abs(n.sign) == 1) {
       if (isHaloKind) continue;
-      if (inN(n)) L.colIdsN[L.rowStartsN[g] + lN[g]++] = n.localId;
-      L.colIdsT[L.rowStartsT[g] + lT[g]++] = n.localId;
+      if (inN(n)) L.colIdsN[L.rowStartsN[g] + bump(lN[g])] = n.localId;
+      L.colIdsT[L.rowStartsT[g] + bump(lT[g])] = n.localId;
     } else {
-      if (inN(n)) H.colIdsN[H.rowStartsN[g] + hN[g]++] = n.localId;
-      H.colIdsT[H.rowStartsT[g] + hT[g]++] = n.localId;
+      if (inN(n)) H.colIdsN[H.rowStartsN[g] + bump(hN[g])] = n.localId;
+      H.colIdsT[H.rowStartsT[g] + bump(hT[g])] = n.localId;
     }
   }
+  auto sort_rows = [](dlong nrows, const std::vector<dlong>& rs, std::vector<dlong>& cols) {
+#pragma omp parallel for schedule(static)
+    for (dlong r = 0; r < nrows; ++r)
+      if (rs[r + 1] - rs[r] > 1) std::sort(cols.begin() + rs[r], cols.begin() + rs[r + 1]);
+  };
+  sort_rows(L.NrowsT, L.rowStartsN, L.colIdsN); sort_rows(L.NrowsT, L.rowStartsT, L.colIdsT);
+  sort_rows(H.NrowsT, H.rowStartsN, H.colIdsN); sort_rows(H.NrowsT, H.rowStartsT, H.colIdsT);
 }
 
 // Pairwise exchange lists + post-exchange combine operator (ogsPairwise.cpp:194-415)
@@ -663,6 +798,25 @@ extern "C" int libp_ogs_sort_selftest(libp_dlong n, libp_dlong nkeys, unsigned i
   int ok = 1;
   for (dlong i = 0; i < n; ++i)
     if (a[(size_t)i].localId != b[(size_t)i].localId) { ok = 0; break; }
+  *same = ok;
+  LIBP_API_END
+}
+
+extern "C" int libp_ogs_rand_selftest(unsigned int seed, libp_dlong n, int* same) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(n >= 0 && same, "bad argument");
+  // n draws in bulk + 100 through rand() must equal n + 100 draws through rand() from the same seed
+  std::vector<int> ref((size_t)n + 100);
+  srand(seed);
+  for (int& v : ref) v = rand();
+  srand(seed);
+  std::vector<int, default_init_alloc<int>> got;
+  GlibcRandBulk::take(got, (size_t)n);
+  int ok = 1;
+  for (dlong i = 0; i < n; ++i)
+    if (got[(size_t)i] != ref[(size_t)i]) { ok = 0; break; }
+  for (int i = 0; i < 100; ++i)
+    if (rand() != ref[(size_t)n + i]) { ok = 0; break; }
   *same = ok;
   LIBP_API_END
 }

@@ -129,3 +129,15 @@ def test_parallel_exact_sort_equals_std_sort():
         same = C.c_int(0)
         L.check(lib.libp_ogs_sort_selftest(n, nkeys, seed, C.byref(same)))
         assert same.value == 1, (n, nkeys, seed)
+
+
+def test_bulk_rand_draws_equal_glibc_rand():
+    """ogsBase_t::FindSharedNodes draws one rand() per id group; the setup takes them in bulk from glibc's generator
+    state (csrc/ogs_setup.cpp GlibcRandBulk) - same values, and the process-wide stream continues where n rand() calls
+    would have left it"""
+    import ctypes as C
+    lib = L.load()
+    for seed, n in [(1, 0), (1, 1), (1, 30), (1, 31), (7, 34), (123, 1000), (1, 1000003)]:
+        same = C.c_int(0)
+        L.check(lib.libp_ogs_rand_selftest(seed, n, C.byref(same)))
+        assert same.value == 1, (seed, n)

@@ -50,6 +50,19 @@ struct default_init_alloc : std::allocator<T> {
 };
 typedef std::vector<Node, default_init_alloc<Node>> NodeVec;
 
+// LIBP_OGS_TIMING=1: wall-clock laps of the setup stages on stderr
+struct SubLap {
+  bool on;
+  std::chrono::steady_clock::time_point t;
+  SubLap() : on(getenv("LIBP_OGS_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
+  void operator()(const char* what) {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[ogs setup]     %-32s %.3f s\n", what, std::chrono::duration<double>(n - t).count());
+    t = n;
+  }
+};
+
 // ---- std::sort, run in parallel, with the identical result ------------------------------------------------------
 // The owner copy of an id group depends on the order an UNSTABLE std::sort leaves the group in (ogsSetup.cpp:245-275),
 // so the sort cannot be swapped for another algorithm.  libstdc++'s std::sort is introsort: a loop that partitions
@@ -265,20 +278,24 @@ void find_shared_nodes(libp_ogs_s& o, NodeVec& nodes) {
     permute_by(nodes, [](const Node& n) { return n.newId; });  // send order: by destRank, local order inside
     exchange_nodes(comm, nodes, sendCounts, recv, recvCounts);
   }
+  SubLap sub;
   const dlong recvN = (dlong)recv.size();
 #pragma omp parallel for schedule(static)
   for (dlong n = 0; n < recvN; ++n) recv[n].newId = n;
 
   // same algorithm + equivalent strict weak order as the reference => same tie order
   exact_sort_nodes(recv, [](const Node& a) { return (unsigned long long)habs(a.baseId); });
+  sub("find: sort by |id|");
 
   // one pass per id group, groups dealt to threads in chunks; the rand() draws are taken from the stream up front,
   // one per group in sorted order, exactly as the sequential loop of the reference consumes them
   int is_unique = 1;
   {
     const GroupChunks gc(recv, kSetupChunks);
+    sub("find: group chunks");
     std::vector<int, default_init_alloc<int>> draws;
     if (o.unique) GlibcRandBulk::take(draws, gc.ngroups);
+    sub("find: rand() draws");
     long long badId = 0;
     int badCount = -1;
 #pragma omp parallel for schedule(dynamic, 4) reduction(min : is_unique)
@@ -317,11 +334,13 @@ void find_shared_nodes(libp_ogs_s& o, NodeVec& nodes) {
     }
     LIBP_CHECK(badCount < 0, "Found " + std::to_string(badCount) + " positive Ids for baseId: " + std::to_string(badId) + ".");
   }
+  sub("find: owner / shared flags");
   int64_t u = is_unique;
   comm.allreduce_i64(&u, 1, LIBP_MIN);
   o.gather_defined = (u == 1);
 
   permute_by(recv, [](const Node& n) { return n.newId; });  // back to arrival order
+  sub("find: back to arrival order");
   if (size == 1) {
     nodes.swap(recv);
     return;
@@ -338,11 +357,13 @@ void construct_shared_nodes(libp_ogs_s& o, NodeVec& nodes, NodeVec& sharedNodes)
   const int size = comm.size;
   const dlong Nids = (dlong)nodes.size();
 
+  SubLap sub;
   // |id| ascending, the owner (positive) copy first inside a group: one integer key
   exact_sort_nodes(nodes, [](const Node& a) {
     return ((unsigned long long)habs(a.baseId) << 1) | (unsigned long long)(a.baseId < 0 ? 1 : 0);
   });
 
+  sub("construct: sort by (|id|, owner)");
   // group pass (parallel over chunks of whole groups): ownership sign, group number, first local appearance
   const GroupChunks gc(nodes, kSetupChunks);
   const dlong NbaseIds = (dlong)gc.ngroups;
@@ -386,7 +407,9 @@ void construct_shared_nodes(libp_ogs_s& o, NodeVec& nodes, NodeVec& sharedNodes)
   for (const NodeVec& v : chunkShared) sendShared.insert(sendShared.end(), v.begin(), v.end());
   chunkShared.clear();
 
+  sub("construct: group pass");
   permute_by(nodes, [](const Node& n) { return n.localId; });  // compressed local order
+  sub("construct: back to local order");
 
   // renumber groups by first appearance: owner-local, other-local, owner-halo, other-halo.  A group's new number is
   // the count of groups of its class that appear earlier in local order = a prefix sum over the first appearances.
@@ -421,6 +444,7 @@ void construct_shared_nodes(libp_ogs_s& o, NodeVec& nodes, NodeVec& sharedNodes)
 #pragma omp parallel for schedule(static)
     for (dlong n = 0; n < Nids; ++n) nodes[n].newId = indexMap[(size_t)nodes[n].newId];
   }
+  sub("construct: first-appearance renumbering");
   for (Node& s : sendShared) s.localId = indexMap[s.newId];
 
   std::sort(sendShared.begin(), sendShared.end(), [](const Node& a, const Node& b) { return a.destRank < b.destRank; });
@@ -535,6 +559,171 @@ void local_setup(libp_ogs_s& o, const NodeVec& nodes) {
   };
   sort_rows(L.NrowsT, L.rowStartsN, L.colIdsN); sort_rows(L.NrowsT, L.rowStartsT, L.colIdsT);
   sort_rows(H.NrowsT, H.rowStartsN, H.colIdsN); sort_rows(H.NrowsT, H.rowStartsT, H.colIdsT);
+}
+
+// ---- one rank, Signed / Unsigned kinds: the whole setup on the sorted (key, index) pairs ------------------------
+// With a single rank the rendezvous rank is the rank itself, nothing is shared, and FindSharedNodes /
+// ConstructSharedNodes / Local*Setup (ogsSetup.cpp:192-331, 333-497, 569-860) look at the same records three times in
+// three orders.  Only ONE piece of that depends on an order: the owner of a group is the (rand() % size)-th record in
+// the tie order std::sort leaves (the exact sort below).  Everything else is a property of the group (sign, size,
+// first local appearance) or of the local order (row numbers by first appearance, columns ascending), so the 32-byte
+// records never have to be permuted: one sort of 12-byte pairs, one pass over the groups, prefix sums, one fill.
+// `orig[k]` = position of compressed record k in the caller's id array.
+void single_rank_setup(libp_ogs_s& o, NodeVec& nodes, const std::vector<dlong, default_init_alloc<dlong>>& orig,
+                       hlong* ids) {
+  SubLap sub;
+  const size_t n = nodes.size();
+  std::vector<KeyIdx, default_init_alloc<KeyIdx>> k(n);
+#pragma omp parallel for schedule(static)
+  for (size_t i = 0; i < n; ++i) { k[i].key = (unsigned long long)habs(nodes[i].baseId); k[i].idx = (dlong)i; }
+  ExactSort::sort(k.data(), n);
+  sub("1 rank: exact sort of (|id|, index)");
+
+  // chunks of whole groups
+  const int nch = kSetupChunks;
+  std::vector<size_t> cb((size_t)nch + 1), g0((size_t)nch + 1, 0);
+  {
+    const size_t per = (n + nch - 1) / nch;
+    for (int c = 0; c <= nch; ++c) {
+      size_t b = std::min(n, (size_t)c * per);
+      while (b > 0 && b < n && k[b].key == k[b - 1].key) ++b;
+      cb[(size_t)c] = b;
+    }
+    cb[(size_t)nch] = n;
+#pragma omp parallel for schedule(static)
+    for (int c = 0; c < nch; ++c) {
+      size_t g = 0;
+      for (size_t i = cb[(size_t)c]; i < cb[(size_t)c + 1]; ++i) g += (i == cb[(size_t)c]) || k[i].key != k[i - 1].key;
+      g0[(size_t)c + 1] = g;
+    }
+    for (int c = 0; c < nch; ++c) g0[(size_t)c + 1] += g0[(size_t)c];
+  }
+  const size_t ngroups = g0[(size_t)nch];
+  std::vector<int, default_init_alloc<int>> draws;
+  if (o.unique) GlibcRandBulk::take(draws, ngroups);
+  sub("1 rank: group chunks + rand() draws");
+
+  // group pass: owner, sign, first appearance, sizes; groupStart[g] = first pair of group g
+  std::vector<dlong, default_init_alloc<dlong>> firstPos(ngroups), groupStart(ngroups + 1), cntN(ngroups);
+  std::vector<signed char, default_init_alloc<signed char>> groupSign(ngroups);
+  groupStart[ngroups] = (dlong)n;
+  const bool unsignedKind = (o.kind == LIBP_UNSIGNED);
+  int is_unique = 1;
+  long long nLT = 0, nLP = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(min : is_unique) reduction(+ : nLT, nLP)
+  for (int c = 0; c < nch; ++c) {
+    size_t g = g0[(size_t)c];
+    size_t start = cb[(size_t)c];
+    const size_t cend = cb[(size_t)c + 1];
+    for (size_t i = start; i < cend; ++i) {
+      if (i == cend - 1 || k[i].key != k[i + 1].key) {
+        const size_t end = i + 1;
+        int positiveCount = 0;
+        if (o.unique) {
+          const hlong baseId = (hlong)k[start].key;
+          const int m = draws[g] % (int)(end - start);
+          for (size_t j = start; j < end; ++j) nodes[(size_t)k[j].idx].baseId = -baseId;
+          nodes[(size_t)k[start + m].idx].baseId = baseId;
+          positiveCount = 1;
+        } else {
+          for (size_t j = start; j < end; ++j) positiveCount += nodes[(size_t)k[j].idx].baseId > 0;
+          if (positiveCount != 1) is_unique = 0;
+        }
+        const int sign = positiveCount > 0 ? 1 : -1;  // a group without an owner copy only takes part in `Trans` maps
+        dlong fp = k[start].idx;
+        for (size_t j = start; j < end; ++j) {
+          Node& nd = nodes[(size_t)k[j].idx];
+          nd.sign = sign;
+          nd.newId = (dlong)g;
+          fp = std::min(fp, k[j].idx);
+        }
+        firstPos[g] = fp;
+        groupSign[g] = (signed char)sign;
+        groupStart[g] = (dlong)start;
+        cntN[g] = unsignedKind ? (dlong)(end - start) : (dlong)positiveCount;
+        nLT++;
+        if (sign == 1) nLP++;
+        ++g;
+        start = end;
+      }
+    }
+  }
+  o.gather_defined = (is_unique == 1);
+  o.NlocalT = (dlong)nLT; o.NlocalP = (dlong)nLP; o.NhaloT = o.NhaloP = 0;
+  o.Ngather = o.NlocalP;
+  o.NgatherGlobal = o.Ngather;
+  sub("1 rank: group pass");
+
+  // rows numbered by first appearance in local order, owner rows first (ogsSetup.cpp:411-433)
+  std::vector<dlong, default_init_alloc<dlong>> indexMap(ngroups);
+  {
+    const size_t per = (n + nch - 1) / nch;
+    std::vector<std::array<dlong, 2>> cnt((size_t)nch + 1, std::array<dlong, 2>{0, 0});
+#pragma omp parallel for schedule(static)
+    for (int c = 0; c < nch; ++c) {
+      std::array<dlong, 2> q{0, 0};
+      const size_t b = std::min(n, (size_t)c * per), e = std::min(n, b + per);
+      for (size_t i = b; i < e; ++i) {
+        const dlong g = nodes[i].newId;
+        if (firstPos[(size_t)g] == (dlong)i) q[groupSign[(size_t)g] == 1 ? 0 : 1]++;
+      }
+      cnt[(size_t)c + 1] = q;
+    }
+    cnt[0] = {0, o.NlocalP};
+    for (int c = 0; c < nch; ++c) { cnt[(size_t)c + 1][0] += cnt[(size_t)c][0]; cnt[(size_t)c + 1][1] += cnt[(size_t)c][1]; }
+#pragma omp parallel for schedule(static)
+    for (int c = 0; c < nch; ++c) {
+      std::array<dlong, 2> q = cnt[(size_t)c];
+      const size_t b = std::min(n, (size_t)c * per), e = std::min(n, b + per);
+      for (size_t i = b; i < e; ++i) {
+        const dlong g = nodes[i].newId;
+        if (firstPos[(size_t)g] == (dlong)i) indexMap[(size_t)g] = q[groupSign[(size_t)g] == 1 ? 0 : 1]++;
+      }
+    }
+  }
+  if (o.unique) {
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; ++i) ids[orig[i]] = nodes[i].baseId;
+  }
+  sub("1 rank: first-appearance renumbering");
+
+  // gatherLocal straight from the groups: row = indexMap[group], columns = the members' positions, ascending
+  OgsOperator& L = o.gatherLocal;
+  OgsOperator& H = o.gatherHalo;
+  L.Ncols = H.Ncols = o.N;
+  L.NrowsN = o.NlocalP; L.NrowsT = o.NlocalT;
+  H.NrowsN = H.NrowsT = 0;
+  H.rowStartsN.assign(1, 0); H.rowStartsT.assign(1, 0);
+  H.colIdsN.clear(); H.colIdsT.clear();
+  L.rowStartsN.resize((size_t)L.NrowsT + 1); L.rowStartsT.resize((size_t)L.NrowsT + 1);
+  L.rowStartsN[0] = L.rowStartsT[0] = 0;
+#pragma omp parallel for schedule(static)
+  for (size_t g = 0; g < ngroups; ++g) {
+    const size_t r = (size_t)indexMap[g];
+    L.rowStartsT[r + 1] = groupStart[g + 1] - groupStart[g];
+    L.rowStartsN[r + 1] = cntN[g];
+  }
+  for (size_t r = 0; r < (size_t)L.NrowsT; ++r) {
+    L.rowStartsT[r + 1] += L.rowStartsT[r];
+    L.rowStartsN[r + 1] += L.rowStartsN[r];
+  }
+  L.colIdsN.resize((size_t)L.nnzN()); L.colIdsT.resize((size_t)L.nnzT());
+#pragma omp parallel for schedule(static)
+  for (size_t g = 0; g < ngroups; ++g) {
+    const size_t r = (size_t)indexMap[g];
+    const size_t b = (size_t)groupStart[g], e = (size_t)groupStart[g + 1];
+    dlong* ct = L.colIdsT.data() + L.rowStartsT[r];
+    for (size_t j = b; j < e; ++j) ct[j - b] = k[j].idx;  // compressed positions ascend with the caller's positions
+    if (e - b > 1) std::sort(ct, ct + (e - b));
+    dlong* cn = L.colIdsN.data() + L.rowStartsN[r];
+    size_t m = 0;
+    for (size_t j = 0; j < e - b; ++j) {
+      const dlong c = ct[j];
+      if (unsignedKind || nodes[(size_t)c].baseId > 0) cn[m++] = orig[(size_t)c];
+    }
+    for (size_t j = 0; j < e - b; ++j) ct[j] = orig[(size_t)ct[j]];
+  }
+  sub("1 rank: gatherLocal maps");
 }
 
 // Pairwise exchange lists + post-exchange combine operator (ogsPairwise.cpp:194-415)
@@ -701,6 +890,7 @@ extern "C" int libp_ogs_setup(libp_dlong N, libp_hlong* ids, libp_comm_t comm, i
   // compressed list of the non-zero ids (parallel: per-chunk counts, prefix, fill)
   NodeVec nodes;
   std::vector<dlong, default_init_alloc<dlong>> compact((size_t)N);  // position of id n in the compressed list
+  std::vector<dlong, default_init_alloc<dlong>> orig;                // ... and back
   {
     const int nchunks = 256;
     std::vector<size_t> cnt((size_t)nchunks + 1, 0);
@@ -714,6 +904,7 @@ extern "C" int libp_ogs_setup(libp_dlong N, libp_hlong* ids, libp_comm_t comm, i
     }
     for (int c = 0; c < nchunks; ++c) cnt[(size_t)c + 1] += cnt[(size_t)c];
     nodes.resize(cnt[(size_t)nchunks]);
+    orig.resize(cnt[(size_t)nchunks]);
 #pragma omp parallel for schedule(static)
     for (int c = 0; c < nchunks; ++c) {
       size_t k = cnt[(size_t)c];
@@ -730,14 +921,21 @@ extern "C" int libp_ogs_setup(libp_dlong N, libp_hlong* ids, libp_comm_t comm, i
         nd.destRank = (int)(habs(ids[n]) % size);
         nodes[k] = nd;
         compact[n] = (dlong)k;
+        orig[k] = (dlong)n;
         ++k;
       }
     }
   }
   lap("node records");
+  NodeVec sharedNodes;
+  if (size == 1 && kind != LIBP_HALO && getenv("LIBP_OGS_GENERIC_SETUP") == nullptr) {
+    compact.clear();
+    compact.shrink_to_fit();
+    single_rank_setup(*o, nodes, orig, ids);
+    lap("single-rank setup");
+  } else {
   find_shared_nodes(*o, nodes);
   lap("find_shared_nodes");
-  NodeVec sharedNodes;
   construct_shared_nodes(*o, nodes, sharedNodes);
   lap("construct_shared_nodes");
   {
@@ -754,6 +952,7 @@ extern "C" int libp_ogs_setup(libp_dlong N, libp_hlong* ids, libp_comm_t comm, i
   }
   local_setup(*o, nodes);
   lap("local_setup");
+  }
   nodes.clear();
   nodes.shrink_to_fit();
   pairwise_setup(*o, sharedNodes);
@@ -883,13 +1082,17 @@ extern "C" int libp_ogs_global_to_local(libp_ogs_t o, libp_dlong* g2l) {
   LIBP_API_BEGIN
   LIBP_CHECK(o && g2l, "null argument");
   LIBP_CHECK(o->NgatherGlobal != 0, "ogs handle is not set up.");
-  for (dlong n = 0; n < o->N; ++n) g2l[n] = -1;
+  const dlong N = o->N;
+#pragma omp parallel for schedule(static)
+  for (dlong n = 0; n < N; ++n) g2l[n] = -1;
   const OgsOperator* ops[2] = {&o->gatherLocal, &o->gatherHalo};
   const dlong offs[2] = {0, o->NlocalT};
   for (int w = 0; w < 2; ++w) {
     const OgsOperator& op = *ops[w];
-    for (dlong r = 0; r < op.NrowsT; ++r)
-      for (dlong g = op.rowStartsT[r]; g < op.rowStartsT[r + 1]; ++g) g2l[op.colIdsT[g]] = r + offs[w];
+    const dlong off = offs[w];
+#pragma omp parallel for schedule(static)
+    for (dlong r = 0; r < op.NrowsT; ++r)  // every local node sits in exactly one row: no write conflicts
+      for (dlong g = op.rowStartsT[r]; g < op.rowStartsT[r + 1]; ++g) g2l[op.colIdsT[g]] = r + off;
   }
   LIBP_API_END
 }

@@ -46,7 +46,7 @@ def test_ipdg_oracle_vs_reference_single_rank(name):
     m = min(k, 15)  # rounding differences grow along an unpreconditioned CG history: tight at the start, loose overall
     assert np.allclose(hist[:m], g["pcg_history"][:m], rtol=1e-6)
     assert np.allclose(hist[:k], g["pcg_history"][:k], rtol=0.2)
-    assert rel(x, g["r0_xsol"]) < 1e-9
+    assert rel(x, g["r0_xsol"]) < 1e-7  # both solves stop at the same 1e-8 residual; the iterates differ by rounding
 
 
 @pytest.mark.parametrize("name", MULTI)

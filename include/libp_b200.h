@@ -221,6 +221,58 @@ typedef struct {
 } libp_elliptic_desc_t;
 int libp_elliptic_create(const libp_elliptic_desc_t* desc, libp_elliptic_t* op);
 int libp_elliptic_free(libp_elliptic_t op);
+
+/* ---- DISCRETIZATION = IPDG on hexahedra -------------------------------------------------------------
+ * elliptic_t::Operator, IPDG branch (solvers/elliptic/src/ellipticOperator.cpp:108-160): ellipticPartialGradientHex3D
+ * (okl/ellipticGradientHex3D.okl:97-169), traceHalo.Exchange of the (dq/dx, dq/dy, dq/dz, q) array with 4 entries per
+ * node, ellipticPartialAxIpdgHex3D on the internal and then the halo elements (okl/ellipticAxIpdgHex3D.okl:359-642).
+ * All arrays are the reference's (device pointers): vgeo [Nelements][12][Np] (mesh_t::vgeo, RX..IJW), sgeo
+ * [Nelements][6*Nq^2][8] (NX,NY,NZ,SJ,IJ,IH,WSJ,WIJ), vmapM / vmapP [Nelements][6*Nq^2] node numbers in the
+ * (Nelements + NhaloElementsTotal) * Np node array, EToB [Nelements][6] boundary TYPE after the BCType translation of
+ * ellipticBoundarySetup.cpp:37-48 (1 Dirichlet, 2 Neumann, <= 0 none), tau = elliptic_t::tau (ellipticSetup.cpp:66-75).
+ * traceHalo = handle of the halo set up from mesh_t::HaloTraceSetup's ids (NULL on one rank); internalElementIds /
+ * haloElementIds = mesh_t::internalElementIds / haloElementIds (both NULL: every element is internal).
+ * The handle is a libp_elliptic_t: libp_elliptic_operator, libp_pcg_solve, ... take it; vectors are
+ * [Nelements*Np | NhaloElementsTotal*Np] as elliptic_t::Ndofs / Nhalo (ellipticSetup.cpp:162-163). */
+typedef struct {
+  int Nq;
+  libp_dlong Nelements, NhaloElementsTotal;           /* mesh.Nelements, mesh.totalHaloPairs */
+  libp_dlong NinternalElements, NhaloElements;        /* lengths of the two element lists */
+  const libp_dlong* internalElementIds;
+  const libp_dlong* haloElementIds;
+  const libp_dlong* vmapM;
+  const libp_dlong* vmapP;
+  const libp_dfloat* vgeo;
+  const libp_dfloat* sgeo;
+  const int* EToB;
+  const libp_dfloat* D;
+  libp_dfloat lambda, tau;
+  libp_ogs_t traceHalo;
+} libp_ipdg_desc_t;
+int libp_elliptic_create_ipdg(const libp_ipdg_desc_t* desc, libp_elliptic_t* op);
+/* elliptic_t::o_grad of an IPDG handle (device, [(Nelements + NhaloElementsTotal)*Np][4]) after the last apply */
+int libp_elliptic_ipdg_gradient(libp_elliptic_t op, const libp_dfloat** grad);
+/* BuildOperatorDiagonalIpdgHex3D (solvers/elliptic/src/ellipticBuildOperatorDiagonal.cpp:868-996): A [Nelements*Np];
+ * EToB here is the translated boundary TYPE as above */
+int libp_elliptic_build_diagonal_ipdg_hex3d(int Nq, libp_dlong Nelements, const libp_dfloat* vgeo,
+                                            const libp_dfloat* sgeo, const int* EToB, const libp_dfloat* D,
+                                            libp_dfloat lambda, libp_dfloat tau, libp_dfloat* A, void* stream);
+/* ellipticRhsBCIpdgHex3D (solvers/elliptic/okl/ellipticRhsBCIpdgHex3D.okl, called from ellipticRun.cpp:150-163):
+ * rhs += boundary-data terms of the IPDG form.  uD / gN: nodal Dirichlet values / Neumann fluxes n.grad(u) per face
+ * node [Nelements][6*Nq^2] (the data-file functions the reference inlines at JIT time); either may be NULL (= 0). */
+int libp_elliptic_rhs_bc_ipdg_hex3d(int Nq, libp_dlong Nelements, libp_dfloat tau, const libp_dfloat* vgeo,
+                                    const libp_dfloat* sgeo, const int* EToB, const libp_dfloat* D, const libp_dfloat* uD,
+                                    const libp_dfloat* gN, libp_dfloat* rhs, void* stream);
+/* mesh_t::SurfaceGeometricFactorsHex3D (libs/mesh/meshSurfaceGeometricFactorsHex3D.cpp:31-195) in two steps, because
+ * the penalty length IHID = max(sJ/J of both sides) needs the neighbours' values across ranks in between:
+ *   1. sgeo (all entries but IHID) and h[Nelements*6*Nq^2] = sJ/J from the physical nodes x, y, z;
+ *   2. IHID from h (own + halo part, exchanged by the caller with mesh_t::halo) through mapP (face-node index of the
+ *      neighbour in h, < 0: none). */
+int libp_mesh_surface_geometric_factors_hex3d(int Nq, libp_dlong Nelements, const libp_dfloat* x, const libp_dfloat* y,
+                                              const libp_dfloat* z, const libp_dfloat* D, const libp_dfloat* gllw,
+                                              libp_dfloat* sgeo, libp_dfloat* h, void* stream);
+int libp_mesh_surface_hinv_hex3d(int Nq, libp_dlong Nelements, const libp_dlong* mapP, const libp_dfloat* h,
+                                 libp_dfloat* sgeo, void* stream);
 /* Fused mode only (no reference counterpart; tuning of this implementation): the element lists are run in
  * pieces of `chunkElements` elements and the accumulator o_Aq is zero-filled piece by piece, just ahead of
  * the reductions that land in it, so the zero lines are still in L2 (saves one DRAM read + one write of the

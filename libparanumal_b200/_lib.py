@@ -48,6 +48,12 @@ class EllipticDesc(C.Structure):
                 ("wJ", vp), ("ggeo", vp), ("D", vp), ("lambda_", f64), ("ogsMasked", vp), ("mode", i32)]
 
 
+class IpdgDesc(C.Structure):
+    _fields_ = [("Nq", i32), ("Nelements", i32), ("NhaloElementsTotal", i32), ("NinternalElements", i32),
+                ("NhaloElements", i32), ("internalElementIds", vp), ("haloElementIds", vp), ("vmapM", vp), ("vmapP", vp),
+                ("vgeo", vp), ("sgeo", vp), ("EToB", vp), ("D", vp), ("lambda_", f64), ("tau", f64), ("traceHalo", vp)]
+
+
 class MGLevelDesc(C.Structure):
     _fields_ = [("fine", vp), ("coarse", vp), ("NqF", i32), ("NqC", i32), ("P", vp), ("invDiagA", vp), ("weightG", vp),
                 ("smoother", i32), ("lambda0", f64), ("lambda1", f64), ("ChebyshevIterations", i32)]
@@ -107,6 +113,12 @@ SIGNATURES = {
     "libp_elliptic_build_diagonal_hex3d": (i32, [i32, i32, vp, vp, vp, vp, f64, f64, vp, vp]),
     "libp_ax_trilinear_hex3d": (i32, [i32, i32, vp, vp, vp, vp, vp, f64, vp, vp, vp]),
     "libp_elliptic_create": (i32, [P(EllipticDesc), P(vp)]),
+    "libp_elliptic_create_ipdg": (i32, [P(IpdgDesc), P(vp)]),
+    "libp_elliptic_ipdg_gradient": (i32, [vp, P(vp)]),
+    "libp_elliptic_build_diagonal_ipdg_hex3d": (i32, [i32, i32, vp, vp, vp, vp, f64, f64, vp, vp]),
+    "libp_mesh_surface_geometric_factors_hex3d": (i32, [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "libp_mesh_surface_hinv_hex3d": (i32, [i32, i32, vp, vp, vp, vp]),
+    "libp_elliptic_rhs_bc_ipdg_hex3d": (i32, [i32, i32, f64, vp, vp, vp, vp, vp, vp, vp, vp]),
     "libp_elliptic_rhs_forcing_hex3d": (i32, [i32, i32, vp, vp, vp, vp]),
     "libp_elliptic_rhs_bc_hex3d": (i32, [i32, i32, vp, vp, vp, f64, vp, vp, vp, vp]),
     "libp_elliptic_add_bc_hex3d": (i32, [i32, i32, vp, vp, vp, vp]),

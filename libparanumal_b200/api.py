@@ -367,6 +367,28 @@ def mesh_geometric_factors_hex3d(Nq, Nelements, x, y, z, D, gllw, ggeo, wJ, vgeo
                                                      _stream()))
 
 
+def mesh_surface_geometric_factors_hex3d(Nq, Nelements, x, y, z, D, gllw, sgeo, h):
+    """step 1 of mesh_t::SurfaceGeometricFactorsHex3D: sgeo (all but IHID) and h = sJ/J per face node"""
+    check(L.load().libp_mesh_surface_geometric_factors_hex3d(Nq, Nelements, _ptr(x), _ptr(y), _ptr(z), _ptr(D), _ptr(gllw),
+                                                             _ptr(sgeo), _ptr(h), _stream()))
+
+
+def mesh_surface_hinv_hex3d(Nq, Nelements, mapP, h, sgeo):
+    """step 2: IHID = max(h-, h+) through mapP (h includes the exchanged halo part on several ranks)"""
+    check(L.load().libp_mesh_surface_hinv_hex3d(Nq, Nelements, _ptr(mapP), _ptr(h), _ptr(sgeo), _stream()))
+
+
+def rhs_bc_ipdg_hex3d(Nq, Nelements, tau, vgeo, sgeo, EToB, D, uD, gN, rhs):
+    check(L.load().libp_elliptic_rhs_bc_ipdg_hex3d(Nq, Nelements, float(tau), _ptr(vgeo), _ptr(sgeo), _ptr(EToB), _ptr(D),
+                                                   _ptr(uD) if uD is not None else None,
+                                                   _ptr(gN) if gN is not None else None, _ptr(rhs), _stream()))
+
+
+def elliptic_build_diagonal_ipdg_hex3d(Nq, Nelements, vgeo, sgeo, EToB, D, lam, tau, A):
+    check(L.load().libp_elliptic_build_diagonal_ipdg_hex3d(Nq, Nelements, _ptr(vgeo), _ptr(sgeo), _ptr(EToB), _ptr(D),
+                                                           float(lam), float(tau), _ptr(A), _stream()))
+
+
 def elliptic_build_diagonal_hex3d(Nq, Nelements, ggeo, wJ, D, mapB, lam, boost, diagL):
     check(L.load().libp_elliptic_build_diagonal_hex3d(Nq, Nelements, _ptr(ggeo), _ptr(wJ), _ptr(D), _ptr(mapB), float(lam),
                                                       float(boost), _ptr(diagL), _stream()))
@@ -452,6 +474,39 @@ class Elliptic:
 
 
 # --------------------------------------------------------------------------- linAlg_t
+class EllipticIpdg(Elliptic):
+    """The IPDG branch of elliptic_t::Operator (ellipticOperator.cpp:108-160) as an operator_t; every array is the
+    reference's (mesh_t::vgeo, sgeo, vmapM, vmapP, elliptic_t::EToB), traceHalo an Ogs of kind HALO set up from
+    mesh_t::HaloTraceSetup's ids (None on one rank)."""
+
+    def __init__(self, Nq, Nelements, vmapM, vmapP, vgeo, sgeo, EToB, D, lam, tau, NhaloElementsTotal=0, traceHalo=None,
+                 internalElementIds=None, haloElementIds=None):
+        self.keep = (vmapM, vmapP, vgeo, sgeo, EToB, D, traceHalo, internalElementIds, haloElementIds)
+        d = L.IpdgDesc()
+        d.Nq, d.Nelements, d.NhaloElementsTotal = Nq, int(Nelements), int(NhaloElementsTotal)
+        d.NinternalElements = 0 if internalElementIds is None else internalElementIds.numel()
+        d.NhaloElements = 0 if haloElementIds is None else haloElementIds.numel()
+        d.internalElementIds = _ptr(internalElementIds) if d.NinternalElements else None
+        d.haloElementIds = _ptr(haloElementIds) if d.NhaloElements else None
+        d.vmapM, d.vmapP, d.vgeo, d.sgeo, d.EToB, d.D = (_ptr(a) for a in (vmapM, vmapP, vgeo, sgeo, EToB, D))
+        d.lambda_, d.tau = float(lam), float(tau)
+        d.traceHalo = traceHalo.handle if traceHalo is not None else None
+        self._h = C.c_void_p()
+        check(L.load().libp_elliptic_create_ipdg(C.byref(d), C.byref(self._h)))
+        Np = Nq ** 3
+        self.Ndofs, self.Nhalo = int(Nelements) * Np, int(NhaloElementsTotal) * Np
+
+    def gradient(self):
+        """elliptic_t::o_grad after the last apply: tensor [(Nelements + halo elements)*Np, 4] (a view, not a copy)"""
+        p = C.c_void_p()
+        check(L.load().libp_elliptic_ipdg_gradient(self._h, C.byref(p)))
+        n = (self.Ndofs + self.Nhalo) * 4
+
+        class _P:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(p.value), False), "version": 2}
+        return torch.as_tensor(_P(), device="cuda").reshape(-1, 4)
+
+
 class LinAlg:
     """linAlg_t (include/linAlg.hpp:52-120) on torch float64 tensors."""
 

@@ -312,6 +312,50 @@ class BoxMesh:
             g[:, 5] = (JW * (tx * tx + ty * ty + tz * tz)).reshape(n, Np)
             self.wJ[e0:e0 + n] = JW.reshape(n, Np)
 
+    # ---- discontinuous-Galerkin connectivity of the box (one rank): mesh_t::ConnectFaceNodes for this mesh
+    def face_nodes(self):
+        """[6, Nq^2] volume node of every face node; faces 0..5 = t=-1, s=-1, r=+1, s=+1, r=-1, t=+1 (the reference's
+        hexahedron: libs/mesh/meshReferenceNodesHex3D.cpp faceNodes)"""
+        Nq, N = self.Nq, self.N
+        n = torch.arange(Nq * Nq, device=self.device)
+        a, b = n % Nq, n // Nq
+        return torch.stack([a + b * Nq, a + b * Nq * Nq, N + a * Nq + b * Nq * Nq, a + N * Nq + b * Nq * Nq,
+                            a * Nq + b * Nq * Nq, a + b * Nq + N * Nq * Nq]).to(torch.int64)
+
+    def dg_connectivity(self):
+        """(vmapM, vmapP, mapP [E, 6*Nq^2] int32, EToB [E, 6] int32 mesh boundary flag, -1 = interior face).
+        Neighbouring box elements see a shared face with the same (a, b) face-node numbering, so face node n of face f
+        meets face node n of the opposite face of the neighbour; a boundary face maps to itself."""
+        assert self.size == 1, "single-rank harness (multi-rank IPDG runs use the reference's own connectivity)"
+        nx, ny, nz = self.nloc
+        E, Np, Nfp = self.Nelements, self.Np, self.Nq * self.Nq
+        dev = self.device
+        e = torch.arange(E, device=dev)
+        ex, ey, ez = e % nx, (e // nx) % ny, e // (nx * ny)
+        fn = self.face_nodes()
+        periodic = self.boundary_flag == -1
+        shifts = [(0, 0, -1, 5), (0, -1, 0, 3), (1, 0, 0, 4), (0, 1, 0, 1), (-1, 0, 0, 2), (0, 0, 1, 0)]
+        n = torch.arange(Nfp, device=dev)
+        vmapM = (e[:, None, None] * Np + fn[None]).reshape(E, 6 * Nfp)
+        vmapP = torch.empty((E, 6, Nfp), dtype=torch.int64, device=dev)
+        mapP = torch.empty((E, 6, Nfp), dtype=torch.int64, device=dev)
+        EToB = torch.full((E, 6), -1, dtype=torch.int32, device=dev)
+        for f, (sx, sy, sz, fP) in enumerate(shifts):
+            px, py, pz = ex + sx, ey + sy, ez + sz
+            outside = (px < 0) | (px >= nx) | (py < 0) | (py >= ny) | (pz < 0) | (pz >= nz)
+            eP = (px % nx) + (py % ny) * nx + (pz % nz) * nx * ny
+            bnd = outside & (not periodic)
+            vP = eP[:, None] * Np + fn[fP][None]
+            mP = eP[:, None] * 6 * Nfp + fP * Nfp + n[None]
+            vM = e[:, None] * Np + fn[f][None]
+            mM = e[:, None] * 6 * Nfp + f * Nfp + n[None]
+            vmapP[:, f] = torch.where(bnd[:, None], vM, vP)
+            mapP[:, f] = torch.where(bnd[:, None], mM, mP)
+            EToB[:, f] = torch.where(bnd, torch.tensor(self.boundary_flag, dtype=torch.int32, device=dev),
+                                     torch.tensor(-1, dtype=torch.int32, device=dev))
+        return (vmapM.to(torch.int32).contiguous(), vmapP.reshape(E, 6 * Nfp).to(torch.int32).contiguous(),
+                mapP.reshape(E, 6 * Nfp).to(torch.int32).contiguous(), EToB.contiguous())
+
     def masked_global_ids(self, bc_type=(0, 1, 2)):
         """(elliptic mapB, maskedGlobalIds): Dirichlet nodes get id 0 (ellipticBoundarySetup.cpp:55-86)."""
         bt = torch.tensor(bc_type, dtype=torch.int32, device=self.device)

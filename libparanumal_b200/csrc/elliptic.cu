@@ -141,12 +141,17 @@ void libp_elliptic_s::build_chain_plan(cudaStream_t s) {
 }
 
 libp_elliptic_s::~libp_elliptic_s() {
+  if (ipdg) libp_b200::ipdg_data_free(ipdg);
   if (side) cudaStreamDestroy(side);
   if (e_fork) cudaEventDestroy(e_fork);
   if (e_join) cudaEventDestroy(e_join);
 }
 
 void libp_elliptic_s::apply(dfloat* q, dfloat* Aq, bool want_dot, const int* doneFlag, cudaStream_t s, bool zeroed) {
+  if (ipdg) {
+    libp_b200::ipdg_apply(*this, q, Aq, want_dot, doneFlag, s);
+    return;
+  }
   libp_ogs_s& ogs = *d.ogsMasked;
   const dlong nL = d.NlocalGatherElements, nG = d.NglobalGatherElements;
   const dlong nL0 = nL / 2, nL1 = (nL + 1) / 2;

@@ -6,6 +6,7 @@
 #include "common.hpp"
 #include "ogs.hpp"
 
+struct libp_elliptic_s;
 namespace libp_b200 {
 int ax_hex3d_launch(int Nq, bool fused, const AxD& dc, bool sym, dlong Nelements, const dlong* elementList,
                     const dlong* G2L, const dfloat* wJ, const dfloat* ggeo, dfloat lambda,
@@ -21,6 +22,10 @@ void halo_finish_f64(libp_ogs_s& o, double* v, cudaStream_t s);
 void halo_combine_start_f64(libp_ogs_s& o, double* gv, cudaStream_t s);
 void halo_combine_finish_f64(libp_ogs_s& o, double* gv, cudaStream_t s);
 void multigrid_apply(void* impl, const dfloat* r, dfloat* Mr, cudaStream_t s);
+// DISCRETIZATION = IPDG (csrc/ipdg.cu): the handle carries its own data and apply
+struct IpdgData;
+void ipdg_apply(libp_elliptic_s& op, dfloat* q, dfloat* Aq, bool want_dot, const int* doneFlag, cudaStream_t s);
+void ipdg_data_free(IpdgData* p);
 }  // namespace libp_b200
 
 struct libp_elliptic_s {
@@ -28,6 +33,7 @@ struct libp_elliptic_s {
   int Np = 0;
   bool symD = false;  // D verified centro-antisymmetric at create time -> even-odd contractions
   dlong Ndofs = 0, Nhalo = 0;
+  libp_b200::IpdgData* ipdg = nullptr;     // non-null: interior-penalty DG operator (libp_elliptic_create_ipdg)
   libp_b200::dev_buf<dfloat> AqL;          // mode 0 scratch, Nelements*Np
   libp_b200::dev_buf<dfloat> dotPartials;  // one per Ax block (p.Ap partial sums)
   int nDotPartials = 0;

@@ -284,6 +284,13 @@ void halo_start(libp_ogs_s& o, T* v, int K, cudaStream_t s) {
   if (o.comm->size == 1) return;
   o.alloc_buffers((size_t)K * sizeof(T));
   T* hb = reinterpret_cast<T*>(o.haloBuf.p);
+  if (o.kind == LIBP_HALO) {
+    // a halo set up from ids (mesh_t::halo, the trace halo of IPDG; not built from a gathered ogs): the owned copies
+    // are collected through gatherHalo and the received ones scattered back through it (ogsHalo.cpp:56-58, 111)
+    op_gather<T>(o.gatherHalo, hb, v, K, LIBP_ADD, LIBP_NOTRANS, s);
+    exchange_start<T>(o, hb, K, LIBP_NOTRANS, s);
+    return;
+  }
   if (o.NhaloP)
     CUDA_CHECK(cudaMemcpyAsync(hb, v + (size_t)K * o.NlocalT, (size_t)K * o.NhaloP * sizeof(T),
                                cudaMemcpyDeviceToDevice, s));
@@ -294,6 +301,10 @@ void halo_finish(libp_ogs_s& o, T* v, int K, cudaStream_t s) {
   if (o.comm->size == 1) return;
   T* hb = reinterpret_cast<T*>(o.haloBuf.p);
   exchange_finish<T>(o, hb, K, LIBP_ADD, LIBP_NOTRANS, s);
+  if (o.kind == LIBP_HALO) {
+    op_scatter<T>(o.gatherHalo, v, hb, K, LIBP_NOTRANS, s);
+    return;
+  }
   const dlong Nhalo = o.NhaloT - o.NhaloP;
   if (Nhalo)
     CUDA_CHECK(cudaMemcpyAsync(v + (size_t)K * (o.NlocalT + o.NhaloP), hb + (size_t)K * o.NhaloP,
@@ -557,14 +568,14 @@ int libp_halo_exchange_start(libp_ogs_t o, void* v, int k, int type, void* strea
   LIBP_API_BEGIN
   check(o, k);
   LIBP_CHECK(o->gather_defined, "Gather operation not well-defined.");
-  if (type == LIBP_DOUBLE && k == 1 && o->p2p.enabled) halo_start_f64(*o, (double*)v, as_stream(stream));
+  if (type == LIBP_DOUBLE && k == 1 && o->p2p.enabled && o->kind != LIBP_HALO) halo_start_f64(*o, (double*)v, as_stream(stream));
   else DISPATCH_TYPE(type, halo_start<T>(*o, (T*)v, k, as_stream(stream)));
   LIBP_API_END
 }
 int libp_halo_exchange_finish(libp_ogs_t o, void* v, int k, int type, void* stream) {
   LIBP_API_BEGIN
   check(o, k);
-  if (type == LIBP_DOUBLE && k == 1 && o->p2p.enabled) halo_finish_f64(*o, (double*)v, as_stream(stream));
+  if (type == LIBP_DOUBLE && k == 1 && o->p2p.enabled && o->kind != LIBP_HALO) halo_finish_f64(*o, (double*)v, as_stream(stream));
   else DISPATCH_TYPE(type, halo_finish<T>(*o, (T*)v, k, as_stream(stream)));
   LIBP_API_END
 }

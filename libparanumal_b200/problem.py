@@ -187,6 +187,81 @@ class EllipticProblem:
         return arnoldi_rho(apply, v0, self.NglobalDofs, dot=dot)
 
 
+class IpdgProblem:
+    """DISCRETIZATION = IPDG on the box (one rank): the elliptic_t setup pieces the IPDG operator needs
+    (ellipticSetup.cpp:55-80 tau and gradient buffer, mesh_t vgeo / sgeo / vmapM / vmapP, ellipticBoundarySetup.cpp:37-48
+    EToB translation) and elliptic_t::Run for data/ellipticSine3D.h (ellipticRun.cpp:139-246, IPDG branch).
+    Vectors are element-local [Nelements*Np]."""
+
+    def __init__(self, N, NX, NY=None, NZ=None, lam=1.0, boundary_flag=1, device="cuda", bc_type=(0, 1, 2)):
+        from . import api
+        NY = NX if NY is None else NY
+        NZ = NX if NZ is None else NZ
+        self.comm = Comm()
+        self.device = torch.device(device)
+        self.N, self.Nq, self.lam = N, N + 1, float(lam)
+        m = self.mesh = BoxMesh(N, NX, NY, NZ, 0, 1, boundary_flag, device=device, coords=True)
+        E, Np, Nq, Nfp = m.Nelements, m.Np, m.Nq, m.Nq * m.Nq
+        self.tau = 2.0 * (N + 1) * (N + 3)
+        gw = torch.from_numpy(m.gllw).to(self.device)
+        self.vgeo = torch.empty(E * 12 * Np, dtype=torch.float64, device=self.device)
+        api.mesh_geometric_factors_hex3d(Nq, E, m.x, m.y, m.z, m.D, gw, m.ggeo, m.wJ, self.vgeo)
+        self.vmapM, self.vmapP, self.mapP, meshEToB = m.dg_connectivity()
+        bt = torch.tensor(bc_type, dtype=torch.int32, device=self.device)
+        self.EToB = torch.where(meshEToB > 0, bt[meshEToB.clamp(min=0).long()], torch.zeros_like(meshEToB)).contiguous()
+        self.sgeo = torch.empty(E * 6 * Nfp * 8, dtype=torch.float64, device=self.device)
+        h = torch.empty(E * 6 * Nfp, dtype=torch.float64, device=self.device)
+        api.mesh_surface_geometric_factors_hex3d(Nq, E, m.x, m.y, m.z, m.D, gw, self.sgeo, h)
+        api.mesh_surface_hinv_hex3d(Nq, E, self.mapP, h, self.sgeo)
+        self.op = api.EllipticIpdg(Nq, E, self.vmapM, self.vmapP, self.vgeo, self.sgeo, self.EToB, m.D, self.lam, self.tau)
+        self.Ndofs, self.Nhalo = E * Np, 0
+        self.NglobalDofs = self.Ndofs
+        self.allNeumann = (self.lam == 0.0) and (boundary_flag == -1)
+
+    def vec(self, fill=0.0):
+        return torch.full((self.Ndofs,), fill, dtype=torch.float64, device=self.device)
+
+    def operator(self, q, Aq=None):
+        Aq = self.vec() if Aq is None else Aq
+        self.op.Operator(q, Aq)
+        return Aq
+
+    def diagonal(self):
+        from .api import elliptic_build_diagonal_ipdg_hex3d
+        m = self.mesh
+        A = self.vec()
+        elliptic_build_diagonal_ipdg_hex3d(self.Nq, m.Nelements, self.vgeo, self.sgeo, self.EToB, m.D, self.lam, self.tau, A)
+        return A
+
+    def jacobi(self):
+        return Precon.Jacobi(self.Ndofs, 1.0 / self.diagonal(), self.allNeumann, self.NglobalDofs, self.comm)
+
+    def pcg(self, flexible=False):
+        return Pcg(self.Ndofs, self.Nhalo, self.comm, flexible=flexible)
+
+    def rhs_sine3d(self):
+        """forcing + boundary data of data/ellipticSine3D.h: u = sin(pi x) sin(pi y) sin(pi z), Dirichlet faces carry u"""
+        from .api import rhs_bc_ipdg_hex3d, rhs_forcing_hex3d
+        m = self.mesh
+        PI = 3.14159265358979323846
+        s = (torch.sin(PI * m.x) * torch.sin(PI * m.y) * torch.sin(PI * m.z)).reshape(-1).contiguous()
+        f = (3 * PI * PI + self.lam) * s
+        r = torch.empty_like(f)
+        rhs_forcing_hex3d(m.Nelements, m.Np, m.wJ, f, r)
+        uD = s[self.vmapM.reshape(-1).long()].contiguous()  # boundary values at the face nodes
+        rhs_bc_ipdg_hex3d(self.Nq, m.Nelements, self.tau, self.vgeo, self.sgeo, self.EToB, m.D, uD, None, r)
+        return r
+
+    def run(self, precon="NONE", tol=1e-8, maxit=5000):
+        """Returns (iterations, solution norm as elliptic_t::Run prints it, x)"""
+        M = Precon.Identity(self.Ndofs) if precon == "NONE" else self.jacobi()
+        r = self.rhs_sine3d()
+        x = self.vec()
+        it = self.pcg().Solve(self.op, M, x, r, tol=tol, maxit=maxit)
+        norm = float(torch.sqrt(torch.sum(x * self.mesh.wJ.reshape(-1) * x)))
+        return it, norm, x
+
+
 def degree_raise_1d(Nc, Nf):
     """mesh_t::DegreeRaiseMatrix1D (libs/mesh/meshBasis1D.cpp): P[NqF, NqC], degree-Nc GLL Lagrange basis
     evaluated at the degree-Nf GLL nodes."""

@@ -87,13 +87,73 @@ def run_rank(rank, size, name, device_index, modes=(1, 0), comm=None, group=None
     return out
 
 
+def run_rank_ipdg(rank, size, name, device_index, group=None):
+    """DISCRETIZATION = IPDG on P ranks (tests/golden/ipdg_*_p<P>.npz): the reference's per-rank vgeo / sgeo / vmapM /
+    vmapP / EToB / element lists, the trace halo set up through the C ABI from mesh_t::HaloTraceSetup's ids; checks the
+    exchanged gradient traces, Operator(q), the diagonal and the Jacobi-PCG iteration count against the dumps."""
+    from libparanumal_b200 import _lib as L
+    from libparanumal_b200 import api
+    from libparanumal_b200.api import Comm, EllipticIpdg, Ogs, Pcg, Precon
+    g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    N, lam = int(g["config_N"]), float(g["config_lambda"])
+    assert int(g["config_P"]) == size
+    k = f"r{rank}_"
+    Nq, Np = N + 1, (N + 1) ** 3
+    api.init(device_index)
+    comm = Comm(rank, size)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    meta = [int(v) for v in g[k + "meta"]]
+    E, Eh = meta[3], meta[4]
+    tau = float(g[k + "dmeta"][1])
+    ids = g[k + "traceGlobalIds"].astype(np.int64).copy()
+    halo = Ogs().Setup(ids.size, ids, comm, kind=L.HALO, unique=False)
+    op = EllipticIpdg(Nq, E, dev(g[k + "vmapM"]), dev(g[k + "vmapP"]), dev(g[k + "vgeo"]), dev(g[k + "sgeo"]),
+                      dev(g[k + "EToB"]), dev(g[k + "D"]), lam, tau, NhaloElementsTotal=Eh, traceHalo=halo,
+                      internalElementIds=dev(g[k + "internalElementIds"]), haloElementIds=dev(g[k + "haloElementIds"]))
+    q = torch.zeros((E + Eh) * Np, dtype=torch.float64, device="cuda")
+    q[: E * Np] = dev(g[k + "q"])
+    Aq = torch.full_like(q, float("nan"))
+    op.Operator(q, Aq)
+
+    def gmax(v):
+        t = torch.tensor([float(v)], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        return float(t[0])
+    ref = g[k + "Aq"]
+    err = float(np.abs(Aq[: E * Np].cpu().numpy() - ref).max()) / gmax(np.abs(ref).max())
+    assert err < 1e-12, ("Operator", err)
+    gr, gref = op.gradient().cpu().numpy(), g[k + "grad"].reshape(-1, 4)
+    tr = np.nonzero(ids < 0)[0]  # the trace nodes this rank receives
+    gerr = float(np.abs(gr[tr] - gref[tr]).max()) / gmax(np.abs(gref).max()) if tr.size else 0.0
+    assert gerr < 1e-12, ("trace halo of the gradient", gerr)
+    A = torch.empty(E * Np, dtype=torch.float64, device="cuda")
+    api.elliptic_build_diagonal_ipdg_hex3d(Nq, E, dev(g[k + "vgeo"]), dev(g[k + "sgeo"]), dev(g[k + "EToB"]), dev(g[k + "D"]),
+                                           lam, tau, A)
+    derr = float(np.abs(A.cpu().numpy() - g[k + "diagA"]).max() / np.abs(g[k + "diagA"]).max())
+    assert derr < 1e-12, ("diagA", derr)
+    M = Precon.Identity(E * Np) if str(g["config_precon"]) == "NONE" else Precon.Jacobi(E * Np, 1.0 / A)
+    r = torch.zeros_like(q)
+    r[: E * Np] = dev(g[k + "r"])
+    x = torch.zeros_like(q)
+    solver = Pcg(E * Np, Eh * Np, comm)
+    it = solver.Solve(op, M, x, r, tol=1e-8, maxit=5000)
+    it_ref = int(g[k + "iterations"][0])
+    assert abs(it - it_ref) <= 1, ("iterations", it, it_ref)
+    xs = g[k + "xsol"]
+    xerr = float(np.abs(x[: E * Np].cpu().numpy() - xs).max()) / gmax(np.abs(xs).max())
+    assert xerr < 1e-7, ("solution", xerr)
+    op.Free()
+    return dict(operator_err=err, trace_err=gerr, diag_err=derr, iterations=it, iterations_ref=it_ref, x_err=xerr)
+
+
 def main():
     rank, size = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     name = sys.argv[1]
     one_gpu = os.environ.get("LIBP_MR_ONE_GPU", "0") == "1"
     dist.init_process_group("gloo", rank=rank, world_size=size)
     try:
-        res = run_rank(rank, size, name, 0 if one_gpu else int(os.environ.get("LOCAL_RANK", rank)))
+        device = 0 if one_gpu else int(os.environ.get("LOCAL_RANK", rank))
+        res = run_rank_ipdg(rank, size, name, device) if name.startswith("ipdg_") else run_rank(rank, size, name, device)
         dist.barrier()
         if rank == 0:
             print("MR_GPU_OK", name, res)

@@ -196,3 +196,56 @@ def test_multirank_parcsr_halo_plan(size):
         wanted_from_r = np.sort(np.concatenate([w[(w >= starts[r]) & (w < starts[r + 1])]
                                                 for k, w in ((k, res[k]["want"]) for k in range(size)) if k != r]))
         assert np.array_equal(np.sort(res[r]["send"]), wanted_from_r)
+
+
+def _halo_worker(rank, size, port, name, outq):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        from libparanumal_b200 import _lib as L
+        from libparanumal_b200.api import Comm, Ogs
+        g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+        ids = g[f"r{rank}_traceGlobalIds"].astype(np.int64).copy()
+        halo = Ogs().Setup(ids.size, ids, Comm(rank, size), kind=L.HALO, unique=False)
+        outq.put(dict(rank=rank, ids=ids, counts=[halo.N, halo.NlocalT, halo.NhaloT, halo.NhaloP],
+                      halo=halo.maps("halo"), exN=halo.exchange_lists(L.NOTRANS)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["ipdg_n3_e4x4x4_p2", "ipdg_n2_e5x4x3_p4"])
+def test_trace_halo_setup_from_reference_ids(name):
+    """kind = Halo setup (mesh_t::HaloTraceSetup's ids of the P-rank reference run, libs/mesh/meshHaloTraceSetup.cpp):
+    every flagged trace node becomes one halo row scattered to exactly that node, every owned node some other rank
+    flagged becomes an owned halo row, and the rows the ranks send add up to the rows the others receive"""
+    size = int(name.rsplit("_p", 1)[1])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_halo_worker, args=(r, size, port, name, q)) for r in range(size)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(size)], key=lambda d: d["rank"])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    needed = {}
+    for d in res:
+        for v in -d["ids"][d["ids"] < 0]:
+            needed[int(v)] = needed.get(int(v), 0) + 1
+    for d in res:
+        ids = d["ids"]
+        N, NlocalT, NhaloT, NhaloP = d["counts"]
+        neg = np.nonzero(ids < 0)[0]
+        owned_needed = np.nonzero((ids > 0) & np.isin(ids, list(needed)))[0]
+        assert NhaloT - NhaloP == neg.size and NhaloP == owned_needed.size
+        h = d["halo"]
+        assert h["NrowsN"] == NhaloP and h["NrowsT"] == NhaloT
+        # owned rows gather from / scatter to the owned node, received rows scatter to the flagged node
+        assert sorted(h["colIdsN"].tolist()) == sorted(owned_needed.tolist())
+        assert sorted(h["colIdsT"][h["rowStartsT"][NhaloP]:].tolist()) == sorted(neg.tolist())
+    sent = sum(int(d["exN"]["sendCounts"].sum()) for d in res)
+    recvd = sum(int(d["exN"]["recvCounts"].sum()) for d in res)
+    assert sent == recvd == sum(needed.values())

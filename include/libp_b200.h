@@ -258,8 +258,8 @@ int libp_elliptic_build_diagonal_ipdg_hex3d(int Nq, libp_dlong Nelements, const 
                                             const libp_dfloat* sgeo, const int* EToB, const libp_dfloat* D,
                                             libp_dfloat lambda, libp_dfloat tau, libp_dfloat* A, void* stream);
 /* ellipticRhsBCIpdgHex3D (solvers/elliptic/okl/ellipticRhsBCIpdgHex3D.okl, called from ellipticRun.cpp:150-163):
- * rhs += boundary-data terms of the IPDG form.  uD / gN: nodal Dirichlet values / Neumann fluxes n.grad(u) per face
- * node [Nelements][6*Nq^2] (the data-file functions the reference inlines at JIT time); either may be NULL (= 0). */
+ * rhs -= boundary functional of the IPDG form.  uD / gN: nodal Dirichlet values / Neumann data n.(uxB,uyB,uzB) per face
+ * node [Nelements][6*Nq^2] (the data-file macros the reference inlines at JIT time); either may be NULL (= 0). */
 int libp_elliptic_rhs_bc_ipdg_hex3d(int Nq, libp_dlong Nelements, libp_dfloat tau, const libp_dfloat* vgeo,
                                     const libp_dfloat* sgeo, const int* EToB, const libp_dfloat* D, const libp_dfloat* uD,
                                     const libp_dfloat* gN, libp_dfloat* rhs, void* stream);

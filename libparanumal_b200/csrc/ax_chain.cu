@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdint>
+#include <vector>
 
 #include "ax_chain.hpp"
 
@@ -167,6 +168,11 @@ struct ChT {
   // (every residue of k*SS + j*Nq resp. k*SS + i mod 16 occurs at most TPE/16 times); Nq = 5 has no common stride
   // for A and B, so s_r / s_s get their own and s_u keeps one two-way conflict in layout B.
   static constexpr bool kDense = (Nq == 5 || Nq == 7 || Nq == 9);
+  // Even orders with several elements per block (Nq = 4, 6): lanes stay packed (element e owns lanes e*Nq2 ...), but
+  // in layouts A and B a lane works on the (element, pencil) pair a table deals to it - any pair of the block - so
+  // that the 8 lanes of a quarter-warp (128-bit rows, layout A) / the 16 lanes of a half-warp (layout B) start in
+  // different banks although elements straddle those groups.
+  static constexpr bool kDeal = (Nq == 4 || Nq == 6);
   static constexpr int TPE = kDense ? ((Nq2 + 15) / 16) * 16 : Nq2;  // threads per element
   static constexpr int EPB = kDense ? (Nq == 5 ? 4 : Nq == 7 ? 2 : 1)
                            : (Nq == 2) ? 16 : (Nq == 3) ? 7 : (Nq == 4) ? 4 : (Nq == 6) ? 5 : 1;
@@ -187,14 +193,22 @@ struct ChT {
   // components per stage: 6 geometric factors (+ wJ for the screened operator)
   __host__ __device__ static constexpr int ng(bool scr) { return (scr && kBulkWJ) ? 7 : 6; }
   // bulk-copy destinations must be 16-byte aligned
-  __host__ __device__ static constexpr int slot_doubles(bool scr) { return ng(scr) * Np + ((ng(scr) * Np) & 1); }
+  // ... and, where lanes of two elements share a half-warp (packed even orders), congruent to Nq2 mod 16 doubles so
+  // that layout C reads of the dense factor blocks stay contiguous in bank space across the element boundary
+  __host__ __device__ static constexpr int slot_doubles(bool scr) {
+    const int base = ng(scr) * Np;
+    if ((Nq2 & 1) || EPB == 1 || kDense) return base + (base & 1);
+    return base + ((Nq2 - base) % 16 + 16) % 16;
+  }
   __host__ __device__ static constexpr int stage_doubles(bool scr) { return EPB * slot_doubles(scr); }
 };
 
-// Dense orders: lane c of an element's TPE threads -> the i-pencil (k*Nq + j) it owns in layout A and the j-pencil
-// (k*Nq + i) it owns in layout B; 255 = idle in that phase.  Built on the host (chain_perm<Nq>()).
+// Dense and dealt orders: lane t of the block -> the i-pencil it works on in layout A and the j-pencil it works on in
+// layout B, encoded element_slot * Nq2 + (k*Nq + j) resp. (k*Nq + i); kIdle = no work in that phase.  Built on the
+// host (chain_perm<Nq>()).
 struct ChainPerm {
-  unsigned char A[96], B[96];
+  static constexpr unsigned short kIdle = 0xffff;
+  unsigned short A[192], B[192];
 };
 
 // Per-thread shared-memory offsets of the three pencil orientations
@@ -215,21 +229,23 @@ struct ChIdx {
     uC = es * C::ESu + b * LD + a;
     rC = es * C::ESr + b * LD + a;
     sC = es * C::ESs + b * LD + a;
-    int kA, jA, kB, iB;
-    if constexpr (C::kDense) {
-      const int pA = pm.A[c], pB = pm.B[c];
-      vA = inSlot && pA != 255; vB = inSlot && pB != 255;
-      kA = vA ? pA / Nq : 0; jA = vA ? pA - kA * Nq : 0;
-      kB = vB ? pB / Nq : 0; iB = vB ? pB - kB * Nq : 0;
+    int kA, jA, kB, iB, eA = es, eB = es;
+    if constexpr (C::kDense || C::kDeal) {
+      const int cA = pm.A[t], cB = pm.B[t];
+      vA = cA != ChainPerm::kIdle; vB = cB != ChainPerm::kIdle;
+      eA = vA ? cA / Nq2 : 0; eB = vB ? cB / Nq2 : 0;
+      const int pA = vA ? cA - eA * Nq2 : 0, pB = vB ? cB - eB * Nq2 : 0;
+      kA = pA / Nq; jA = pA - kA * Nq;
+      kB = pB / Nq; iB = pB - kB * Nq;
     } else {
       vA = vB = valid;
       kA = (Nq == 8) ? a : b; jA = (Nq == 8) ? b : a;      // layout A: i-pencil (row)
       kB = (Nq == 8) ? (4 * (b & 1) + (b >> 1)) : b; iB = a;  // layout B: j-pencil (column)
     }
-    uA = es * C::ESu + kA * C::SSu + jA * LD;
-    rA = es * C::ESr + kA * C::SSr + jA * LD;
-    uB = es * C::ESu + kB * C::SSu + iB;
-    sB = es * C::ESs + kB * C::SSs + iB;
+    uA = eA * C::ESu + kA * C::SSu + jA * LD;
+    rA = eA * C::ESr + kA * C::SSr + jA * LD;
+    uB = eB * C::ESu + kB * C::SSu + iB;
+    sB = eB * C::ESs + kB * C::SSs + iB;
   }
 };
 
@@ -921,26 +937,44 @@ template <int Nq>
 const ChainPerm& chain_perm() {
   static const ChainPerm pm = [] {
     using C = ChT<Nq>;
+    constexpr int Nq2 = C::Nq2;
     ChainPerm p;
-    std::memset(&p, 255, sizeof(p));
-    if (C::kDense) {
-      constexpr int G = C::TPE / 16;
-      auto deal = [&](unsigned char* out, int SSx, bool isA) {
-        int used[8] = {0}, cnt[16] = {0};
-        for (int k = 0; k < Nq; ++k)
-          for (int x = 0; x < Nq; ++x) {
-            const int r = (k * SSx + (isA ? x * Nq : x)) & 15;
-            int g = cnt[r]++;
-            if (g >= G || used[g] >= 16) {  // more copies of a residue than half-warps: least loaded group
-              g = 0;
-              for (int h = 1; h < G; ++h)
-                if (used[h] < used[g]) g = h;
-            }
-            out[16 * g + used[g]++] = (unsigned char)(k * Nq + x);
-          }
-      };
-      deal(p.A, C::SSr, true);
-      deal(p.B, C::SSs, false);
+    for (int i = 0; i < 192; ++i) p.A[i] = p.B[i] = ChainPerm::kIdle;
+    // deal `n` pencils (code, bank residue) to lane groups of `gs` lanes starting at lane `lane0`: the m-th pencil of
+    // a residue goes to the m-th group that does not hold that residue yet
+    auto deal = [&](unsigned short* out, int lane0, int lanes, int gs, int nres, int n, auto code, auto residue) {
+      const int G = lanes / gs;
+      std::vector<int> used(G, 0);
+      std::vector<std::vector<char>> has(G, std::vector<char>(nres, 0));
+      std::vector<int> next(nres, 0);
+      for (int q = 0; q < n; ++q) {
+        const int r = residue(q);
+        int g = next[r];
+        while (g < G && (has[g][r] || used[g] >= gs)) ++g;
+        if (g >= G) {  // more copies of a residue than groups: least loaded group, one conflict
+          g = 0;
+          for (int h = 1; h < G; ++h)
+            if (used[h] < used[g]) g = h;
+        } else {
+          next[r] = g + 1;
+        }
+        has[g][r] = 1;
+        out[lane0 + gs * g + used[g]++] = (unsigned short)code(q);
+      }
+    };
+    if (C::kDense) {  // per element: its own TPE lanes, 64-bit accesses (half-warps, 16 eight-byte banks)
+      for (int e = 0; e < C::EPB; ++e) {
+        deal(p.A, e * C::TPE, C::TPE, 16, 16, Nq2, [&](int q) { return e * Nq2 + q; },
+             [&](int q) { return ((q / Nq) * C::SSr + (q % Nq) * Nq) & 15; });
+        deal(p.B, e * C::TPE, C::TPE, 16, 16, Nq2, [&](int q) { return e * Nq2 + q; },
+             [&](int q) { return ((q / Nq) * C::SSs + (q % Nq)) & 15; });
+      }
+    } else if (C::kDeal) {  // whole block; layout A reads 128-bit row pieces (quarter-warps, 8 sixteen-byte banks)
+      const int n = C::EPB * Nq2;
+      deal(p.A, 0, C::Threads, 8, 8, n, [&](int q) { return q; },
+           [&](int q) { const int e = q / Nq2, pc = q % Nq2; return ((e * C::ESr + (pc / Nq) * C::SSr + (pc % Nq) * C::LD) / 2) & 7; });
+      deal(p.B, 0, C::Threads, 16, 16, n, [&](int q) { return q; },
+           [&](int q) { const int e = q / Nq2, pc = q % Nq2; return (e * C::ESs + (pc / Nq) * C::SSs + (pc % Nq)) & 15; });
     }
     return p;
   }();

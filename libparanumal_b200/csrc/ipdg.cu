@@ -194,8 +194,8 @@ __global__ void __launch_bounds__(Nq * Nq) ipdg_ax_kernel(dlong Nlist, const dlo
 
 // boundary data into the right-hand side (ellipticRhsBCIpdgHex3D, solvers/elliptic/okl/ellipticRhsBCIpdgHex3D.okl): the
 // element pass with a zero interior state and the ghost state (uD, 0) on Dirichlet faces / (0, gN) on Neumann faces.
-// uD, gN: nodal boundary data per face node [Nelements][6*Nq^2] (gN = n . grad u), the data-file functions the
-// reference inlines at JIT time.
+// uD, gN: nodal boundary data per face node [Nelements][6*Nq^2] (gN = n . (uxB, uyB, uzB) as the data file's Neumann
+// macro returns them), the data-file functions the reference inlines at JIT time.
 template <int Nq>
 __global__ void __launch_bounds__(Nq * Nq) ipdg_rhs_bc_kernel(dlong Nelements, dfloat tau, const dfloat* __restrict__ vgeo,
                                                               const dfloat* __restrict__ sgeo, const int* __restrict__ EToB,
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(Nq * Nq) ipdg_rhs_bc_kernel(dlong Nelements, d
   }
   dfloat* out = rhs + (size_t)e * Np + t;
 #pragma unroll
-  for (int k = 0; k < Nq; ++k) out[k * Nq2] += r_r[k];
+  for (int k = 0; k < Nq; ++k) out[k * Nq2] -= r_r[k];  // the reference subtracts the boundary functional
 }
 
 // diagonal: volume lines through the node + the faces the node lies on

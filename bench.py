@@ -82,6 +82,7 @@ def parse():
     ap.add_argument("--no-pcg", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-trilinear", action="store_true", help="skip the ELEMENT MAP = TRILINEAR operator line")
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
                     help="c2: BP5 operator + Jacobi-PCG on the 64^3 box (BASELINE configs[1], [2]); "
                          "c4: MULTIGRID-PCG, Hex N=7, 96^3 box (configs[3], meant for --gpus 8)")
@@ -335,6 +336,35 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "elements_per_launch": E,
                 "launches_per_apply": (1 if world == 1 else 2)}
 
+    # ------------------------------------------------------------------ ELEMENT MAP = TRILINEAR
+    # the same operator with the geometric factors recomputed from the element vertices instead of streamed
+    # (libp_elliptic_set_trilinear); its own byte model: 16 B per DOF + 192 B of vertices per element
+    trilinear = None
+    if world == 1 and chain_on and args.mode == 1 and not args.no_trilinear:
+        ex, ey, ez = m.element_vertices()
+        EXYZ = torch.stack([ex, ey, ez], dim=1).contiguous().reshape(-1)
+        p.op.set_trilinear(EXYZ, m.gllz, m.gllw)
+        At = p.vec(fill=float("nan"))
+        for _ in range(3):
+            p.op.Operator(q, At)
+        tdiff = float((At[: p.Ndofs] - Aq[: p.Ndofs]).abs().max() / Aq[: p.Ndofs].abs().max())
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tsteps = min(steps, 50)
+        torch.cuda.synchronize()
+        t0.record()
+        for _ in range(tsteps):
+            p.op.Operator(q, At)
+        t1.record()
+        torch.cuda.synchronize()
+        tms = t0.elapsed_time(t1) / tsteps
+        tbytes = 16.0 * p.Ndofs + 192.0 * E
+        trilinear = {"value": p.NglobalDofs / (tms * 1e-3) / 1e9, "unit": "GDOF/s", "ms_per_apply": tms,
+                     "algorithmic_bytes_per_apply": tbytes, "hbm_frac": tbytes / (tms * 1e-3) / 1e9 / peak,
+                     "bound": "fp64 pipe (geometry recomputed per node; affine elements take the constant-Jacobian path)",
+                     "rel_diff_vs_stored_factors": tdiff}
+        p.op.set_trilinear(None)
+        del At, EXYZ
+
     # ------------------------------------------------------------------ e2e: host buffers through the C ABI
     # Each step copies that step's q from pinned host memory, applies the operator through the C ABI and
     # copies Aq back to pinned host memory.  Two buffer sets alternate so that the D2H of step i overlaps
@@ -477,7 +507,7 @@ def main():
                 "exchange": ("nvlink-peer-window" if p2p else "nccl") if world > 1 else "none",
                 "setup_seconds": round(t_setup, 1), "chain_plan": plan_stats,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * steps,
-                "roofline": roofline, "cpu_baseline": cpu, "pcg": pcg, "checks": checks}
+                "roofline": roofline, "cpu_baseline": cpu, "pcg": pcg, "trilinear": trilinear, "checks": checks}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -912,21 +912,33 @@ __global__ void __launch_bounds__(256) plan_count_raw_kernel(size_t nPos, const 
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
 }
 
-// zero-fill of the sectors the plan marks (4 rows = 32 bytes each); one thread per sector
+// zero-fill of the sectors the plan marks (4 rows = 32 bytes each); one thread per sector, four sectors of the
+// grid-stride loop in flight per thread (the loop is latency-bound on the mask words otherwise)
+__device__ __forceinline__ void zero_sector(size_t s, dlong nRows, dfloat* __restrict__ Aq) {
+  const size_t r0 = s * 4;
+  if (r0 + 4 <= (size_t)nRows) {
+    double2* d = reinterpret_cast<double2*>(Aq + r0);
+    d[0] = make_double2(0.0, 0.0);
+    d[1] = make_double2(0.0, 0.0);
+  } else {
+    for (size_t r = r0; r < (size_t)nRows; ++r) Aq[r] = 0.0;
+  }
+}
 __global__ void __launch_bounds__(256) zero_fill_kernel(size_t nSectors, dlong nRows, const uint32_t* __restrict__ zmask,
                                                         dfloat* __restrict__ Aq, const int* __restrict__ doneFlag) {
   if (doneFlag != nullptr && *doneFlag) return;
-  for (size_t s = (size_t)blockIdx.x * 256 + threadIdx.x; s < nSectors; s += (size_t)gridDim.x * 256) {
-    if (!((zmask[s >> 5] >> (s & 31)) & 1u)) continue;
-    const size_t r0 = s * 4;
-    if (r0 + 4 <= (size_t)nRows) {
-      double2* d = reinterpret_cast<double2*>(Aq + r0);
-      d[0] = make_double2(0.0, 0.0);
-      d[1] = make_double2(0.0, 0.0);
-    } else {
-      for (size_t r = r0; r < (size_t)nRows; ++r) Aq[r] = 0.0;
-    }
+  const size_t stride = (size_t)gridDim.x * 256;
+  size_t s = (size_t)blockIdx.x * 256 + threadIdx.x;
+  for (; s + 3 * stride < nSectors; s += 4 * stride) {
+    uint32_t m[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) m[u] = __ldg(zmask + ((s + u * stride) >> 5));
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if ((m[u] >> ((s + u * stride) & 31)) & 1u) zero_sector(s + u * stride, nRows, Aq);
   }
+  for (; s < nSectors; s += stride)
+    if ((__ldg(zmask + (s >> 5)) >> (s & 31)) & 1u) zero_sector(s, nRows, Aq);
 }
 
 int grid_for(size_t n) { return (int)std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 32); }

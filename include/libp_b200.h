@@ -296,6 +296,11 @@ int libp_elliptic_zero_ahead_errors(libp_elliptic_t op, int* errors);
 int libp_elliptic_set_chain(libp_elliptic_t op, int chainElements, int stages);
 int libp_elliptic_set_default_chain(int chainElements, int stages);
 int libp_elliptic_chain_stats(libp_elliptic_t op, libp_dfloat* Aq, long long* stats, void* stream);
+/* Host-side audit (no GPU needed) of the shared-memory geometry compiled into the element-chain kernel of order Nq:
+ * ok = every pencil of layouts A / B and every column of layout C is owned by exactly one lane and all offsets are in
+ * bounds; wavefronts[6] = {actual, ideal} shared wavefronts of one element step for layouts C, A, B under the bank model
+ * of DESIGN.md 4.1c (64-bit accesses per half-warp, 128-bit per quarter-warp). */
+int libp_ax_chain_layout_selftest(int Nq, int* ok, int* wavefronts);
 /* ELEMENT MAP = TRILINEAR (ellipticSetup.cpp:131-134 selects ellipticPartialAxTrilinearHex3D,
  * solvers/elliptic/okl/ellipticAxHex3D.okl:440-627): the operator recomputes the geometric factors from the element
  * vertices EXYZ (device, [Nelements][3][8], reference vertex order) and the GLL nodes / weights (host, Nq entries)

@@ -86,6 +86,7 @@ SIGNATURES = {
     "libp_ogs_free": (i32, [vp]),
     "libp_ogs_sort_selftest": (i32, [i32, i32, C.c_uint, P(i32)]),
     "libp_ogs_rand_selftest": (i32, [C.c_uint, i32, P(i32)]),
+    "libp_ax_chain_layout_selftest": (i32, [i32, P(i32), P(i32)]),
     "libp_ogs_info": (i32, [vp, P(OgsInfo)]),
     "libp_ogs_maps": (i32, [vp, i32, P(i32), P(i32), P(vp), P(vp), P(vp), P(vp)]),
     "libp_ogs_exchange_lists": (i32, [vp, i32, P(i32), P(vp), P(i32), P(vp), P(vp), P(vp), P(i32), P(vp), P(vp), P(vp)]),

@@ -217,7 +217,7 @@ struct ChIdx {
   int es, ij, a, b;
   bool valid, vA, vB;
   int uC, rC, sC, uA, rA, uB, sB;
-  __device__ __forceinline__ ChIdx(int t, const ChainPerm& pm) {
+  __host__ __device__ __forceinline__ ChIdx(int t, const ChainPerm& pm) {
     using C = ChT<Nq>;
     constexpr int Nq2 = C::Nq2, LD = C::LD;
     const bool inSlot = (C::Work == C::Threads) ? true : t < C::Work;  // folded away when the block has no idle lanes
@@ -1045,7 +1045,102 @@ int launch_chain_tri(const ChainArgs& A, const dfloat* EXYZ, const EoD& eo, cons
   return grid;
 }
 
+// Host-side audit of the compiled-in shared-memory geometry of order Nq (no GPU needed): every pencil of every element
+// slot is owned by exactly one lane in layouts A and B, all offsets stay inside the arrays, and the number of shared
+// wavefronts each access pattern costs under the bank model of DESIGN.md 4.1c (64-bit accesses per half-warp over 16
+// eight-byte banks, 128-bit accesses per quarter-warp over 8 sixteen-byte banks) next to the ideal number.
+template <int Nq>
+void layout_audit(int* ok, int* wf) {
+  using C = ChT<Nq>;
+  constexpr int Nq2 = C::Nq2, LD = C::LD;
+  const ChainPerm& pm = chain_perm<Nq>();
+  std::vector<ChIdx<Nq>> X;
+  for (int t = 0; t < C::Threads; ++t) X.emplace_back(t, pm);
+  bool good = true;
+  // ownership: (element slot, pencil) of layouts A / B exactly once
+  std::vector<int> ownA(C::EPB * Nq2, 0), ownB(C::EPB * Nq2, 0), ownC(C::EPB * Nq2, 0);
+  for (const auto& x : X) {
+    if (x.vA) {
+      const int e = x.rA / C::ESr, rem = x.rA - e * C::ESr, k = rem / C::SSr, j = (rem - k * C::SSr) / LD;
+      good = good && e < C::EPB && k < Nq && j < Nq && (rem - k * C::SSr) % LD == 0;
+      good = good && x.uA == e * C::ESu + k * C::SSu + j * LD;
+      if (good) ownA[e * Nq2 + k * Nq + j]++;
+    }
+    if (x.vB) {
+      const int e = x.sB / C::ESs, rem = x.sB - e * C::ESs, k = rem / C::SSs, i = rem - k * C::SSs;
+      good = good && e < C::EPB && k < Nq && i < Nq;
+      good = good && x.uB == e * C::ESu + k * C::SSu + i;
+      if (good) ownB[e * Nq2 + k * Nq + i]++;
+    }
+    if (x.valid) {
+      good = good && x.uC == x.es * C::ESu + x.b * LD + x.a && x.es < C::EPB;
+      if (good) ownC[x.es * Nq2 + x.ij]++;
+    }
+  }
+  for (int v : ownA) good = good && v == 1;
+  for (int v : ownB) good = good && v == 1;
+  for (int v : ownC) good = good && v == 1;
+  // bounds
+  good = good && (Nq - 1) * C::SSu + (Nq - 1) * LD + Nq - 1 < C::ESu && (Nq - 1) * C::SSr + (Nq - 1) * LD + Nq - 1 < C::ESr &&
+         (Nq - 1) * C::SSs + (Nq - 1) * LD + Nq - 1 < C::ESs;
+  auto cost = [&](int group, int unit_doubles, auto addr, auto on, int& actual, int& ideal) {
+    // one instruction: lanes of a `group` share a wavefront unless two of them hit the same bank with different words
+    const int nb = 128 / (8 * unit_doubles);
+    for (int g0 = 0; g0 < C::Threads; g0 += group) {
+      std::vector<std::vector<int>> words(nb);
+      bool any = false;
+      for (int t = g0; t < g0 + group; ++t) {
+        if (!on(X[t])) continue;
+        any = true;
+        const int w = addr(X[t]) / unit_doubles;
+        auto& b = words[w % nb];
+        if (std::find(b.begin(), b.end(), w) == b.end()) b.push_back(w);
+      }
+      if (!any) continue;
+      size_t mx = 1;
+      for (auto& b : words) mx = std::max(mx, b.size());
+      actual += (int)mx;
+      ideal += 1;
+    }
+  };
+  for (int i = 0; i < 6; ++i) wf[i] = 0;
+  // layout C: one 64-bit access per k on each of s_u, s_r, s_s and the factor slot (same pattern for every k)
+  cost(16, 1, [](const ChIdx<Nq>& x) { return x.uC; }, [](const ChIdx<Nq>& x) { return x.valid; }, wf[0], wf[1]);
+  cost(16, 1, [](const ChIdx<Nq>& x) { return x.rC; }, [](const ChIdx<Nq>& x) { return x.valid; }, wf[0], wf[1]);
+  cost(16, 1, [](const ChIdx<Nq>& x) { return x.sC; }, [](const ChIdx<Nq>& x) { return x.valid; }, wf[0], wf[1]);
+  cost(16, 1, [](const ChIdx<Nq>& x) { return x.es * C::slot_doubles(false) + x.ij; },
+       [](const ChIdx<Nq>& x) { return x.valid; }, wf[0], wf[1]);
+  // layout A: rows of s_u and s_r (128-bit pieces where load_row vectorises, 64-bit otherwise)
+  constexpr bool vec = !(Nq == 5 || Nq == 7 || Nq == 9);
+  for (int c = 0; c < (vec ? Nq / 2 : Nq); ++c) {
+    const int off = vec ? 2 * c : c;
+    cost(vec ? 8 : 16, vec ? 2 : 1, [off](const ChIdx<Nq>& x) { return x.uA + off; }, [](const ChIdx<Nq>& x) { return x.vA; }, wf[2], wf[3]);
+    cost(vec ? 8 : 16, vec ? 2 : 1, [off](const ChIdx<Nq>& x) { return x.rA + off; }, [](const ChIdx<Nq>& x) { return x.vA; }, wf[2], wf[3]);
+  }
+  if (vec && (Nq & 1)) {
+    cost(16, 1, [](const ChIdx<Nq>& x) { return x.uA + Nq - 1; }, [](const ChIdx<Nq>& x) { return x.vA; }, wf[2], wf[3]);
+    cost(16, 1, [](const ChIdx<Nq>& x) { return x.rA + Nq - 1; }, [](const ChIdx<Nq>& x) { return x.vA; }, wf[2], wf[3]);
+  }
+  // layout B: columns of s_u and s_s
+  for (int m = 0; m < Nq; ++m) {
+    cost(16, 1, [m](const ChIdx<Nq>& x) { return x.uB + m * C::LD; }, [](const ChIdx<Nq>& x) { return x.vB; }, wf[4], wf[5]);
+    cost(16, 1, [m](const ChIdx<Nq>& x) { return x.sB + m * C::LD; }, [](const ChIdx<Nq>& x) { return x.vB; }, wf[4], wf[5]);
+  }
+  *ok = good ? 1 : 0;
+}
+
 }  // namespace
+
+extern "C" int libp_ax_chain_layout_selftest(int Nq, int* ok, int* wavefronts) {
+  LIBP_API_BEGIN
+  LIBP_CHECK(Nq >= 2 && Nq <= 9 && ok && wavefronts, "bad argument");
+  switch (Nq) {
+#define CASE(n) case n: layout_audit<n>(ok, wavefronts); break;
+    CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9)
+#undef CASE
+  }
+  LIBP_API_END
+}
 
 namespace libp_b200 {
 

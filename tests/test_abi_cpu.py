@@ -141,3 +141,23 @@ def test_bulk_rand_draws_equal_glibc_rand():
         same = C.c_int(0)
         L.check(lib.libp_ogs_rand_selftest(seed, n, C.byref(same)))
         assert same.value == 1, (seed, n)
+
+
+def test_chain_kernel_shared_memory_layouts_are_consistent_and_conflict_free():
+    """Audit of the shared-memory geometry compiled into the element-chain kernel (csrc/ax_chain.cu: ChT / ChainPerm /
+    ChIdx), on the host: every column (layout C) and pencil (layouts A, B) has exactly one owner lane, offsets are in
+    bounds, and under the half-warp / quarter-warp bank model of DESIGN.md 4.1c the orders of the degree sweep cost
+    the ideal number of shared wavefronts (Nq = 5 keeps one two-way conflict on the s_u read of layout B; Nq = 2, 3 -
+    p-multigrid levels only - still use padded rows)"""
+    import ctypes as C
+    lib = L.load()
+    for Nq in range(2, 10):
+        ok, wf = C.c_int(0), (C.c_int * 6)()
+        L.check(lib.libp_ax_chain_layout_selftest(Nq, C.byref(ok), wf))
+        assert ok.value == 1, Nq
+        cA, cI, aA, aI, bA, bI = list(wf)
+        assert cA >= cI and aA >= aI and bA >= bI
+        if Nq in (4, 6, 7, 8, 9):
+            assert (cA, aA, bA) == (cI, aI, bI), (Nq, list(wf))
+        if Nq == 5:
+            assert cA == cI and aA == aI and bA <= 1.25 * bI, list(wf)

@@ -20,7 +20,19 @@ int instantiate(platform_t& platform, elliptic_t& elliptic, settings_t& settings
   ogs.Gather(o_r, o_x, 1, ogs::Add, ogs::Trans);
   ogs.ExchangeStart(o_x, 1);
   ogs.ExchangeFinish(o_x, 1);
+  A.UseTrilinearMap(platform, elliptic.mesh);
   return solver.Solve(A, M, o_x, o_r, 1e-8, 100, 0) + nb.Solve(A, M, o_x, o_r, 1e-8, 100, 0);
+}
+
+// DISCRETIZATION = IPDG: the operator handle from the reference's DG arrays, solved with the same pcg class
+int instantiate_ipdg(platform_t& platform, elliptic_t& elliptic, settings_t& settings, comm_t comm, b200::runtime_t& rt) {
+  b200::ellipticIpdgOperatorB200_t A;
+  A.Setup(elliptic, rt);
+  linearSolver_t solver;
+  solver.Setup<b200::pcgB200>(elliptic.Ndofs, elliptic.Nhalo, platform, settings, comm, rt);
+  deviceMemory<dfloat> o_x = platform.malloc<dfloat>(elliptic.Ndofs + elliptic.Nhalo);
+  deviceMemory<dfloat> o_r = platform.malloc<dfloat>(elliptic.Ndofs + elliptic.Nhalo);
+  return solver.Solve(A, elliptic.precon, o_x, o_r, 1e-8, 100, 0);
 }
 
 // what MultiGridPrecon::MultiGridPrecon does after parAlmond.AMGSetup(...): hand every level to the library

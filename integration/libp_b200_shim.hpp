@@ -172,12 +172,84 @@ class ellipticOperatorB200_t : public operator_t {
     d.mode = mode;  // 1: fused gather epilogue, 0: reference data flow (AqL + ogs gather)
     B200_CHECK(libp_elliptic_create(&d, &h));
   }
+  // ELEMENT MAP = TRILINEAR (ellipticSetup.cpp:131-134; the kernel's o_EXYZ argument, ellipticAxHex3D.okl:440-447):
+  // geometry from the element vertices instead of the stored factors.  This version of mesh_t keeps the vertices on
+  // the host (EX, EY, EZ, include/mesh.hpp:74-76), so the [Nelements][3][8] device array is packed here.
+  deviceMemory<dfloat> o_EXYZ;
+  void UseTrilinearMap(platform_t& platform, mesh_t& mesh) {
+    memory<dfloat> EXYZ(mesh.Nelements * 24);
+    for (dlong el = 0; el < mesh.Nelements; el++)
+      for (int v = 0; v < 8; v++) {
+        EXYZ[el * 24 + v] = mesh.EX[el * mesh.Nverts + v];
+        EXYZ[el * 24 + 8 + v] = mesh.EY[el * mesh.Nverts + v];
+        EXYZ[el * 24 + 16 + v] = mesh.EZ[el * mesh.Nverts + v];
+      }
+    o_EXYZ = platform.malloc<dfloat>(EXYZ);
+    B200_CHECK(libp_elliptic_set_trilinear(h, o_EXYZ.ptr(), mesh.gllz.ptr(), mesh.gllw.ptr()));
+  }
   void Operator(deviceMemory<dfloat>& o_q, deviceMemory<dfloat>& o_Aq) override {
     rt->enter();
     B200_CHECK(libp_elliptic_operator(h, o_q.ptr(), o_Aq.ptr(), rt->stream));
     rt->leave();
   }
   ~ellipticOperatorB200_t() { if (h) libp_elliptic_free(h); }
+};
+
+// ---------------------------------------------------------------------------------- elliptic_t::Operator (IPDG hex)
+// solvers/elliptic/src/ellipticOperator.cpp:108-160.  Every array is the reference's own device allocation; the trace
+// halo is set up through the C ABI from the ids mesh_t::HaloTraceSetup builds (libs/mesh/meshHaloTraceSetup.cpp:38-83),
+// repeated here because the reference keeps them local to that function.
+class ellipticIpdgOperatorB200_t : public operator_t {
+ public:
+  libp_elliptic_t h = nullptr;
+  runtime_t* rt = nullptr;
+  ogsB200_t traceHalo;
+
+  void Setup(elliptic_t& e, runtime_t& rt_) {
+    rt = &rt_;
+    mesh_t& mesh = e.mesh;
+    const dlong Np = mesh.Np;
+    if (mesh.totalHaloPairs > 0) {
+      hlong localNelements = mesh.Nelements, globalOffset = mesh.Nelements;
+      mesh.comm.Scan(localNelements, globalOffset);
+      globalOffset -= localNelements;
+      memory<hlong> ids((mesh.Nelements + mesh.totalHaloPairs) * Np, 0);
+      for (dlong el = 0; el < mesh.Nelements; el++)
+        for (int n = 0; n < Np; n++) ids[el * Np + n] = (el + globalOffset) * Np + n + 1;
+      mesh.halo.Exchange(ids, Np);
+      for (dlong id = 0; id < mesh.Nelements * mesh.Nfp * mesh.Nfaces; id++) {
+        const dlong idP = mesh.vmapP[id];
+        if (idP / Np >= mesh.Nelements && ids[idP] > 0) ids[idP] *= -1;  // flag the trace ids we need
+      }
+      for (dlong n = mesh.Nelements * Np; n < (mesh.Nelements + mesh.totalHaloPairs) * Np; n++)
+        if (ids[n] > 0) ids[n] = 0;
+      traceHalo.Setup((mesh.Nelements + mesh.totalHaloPairs) * Np, ids, rt_, ogs::Halo, false, false);
+    }
+    libp_ipdg_desc_t d{};
+    d.Nq = mesh.Nq;
+    d.Nelements = mesh.Nelements;
+    d.NhaloElementsTotal = mesh.totalHaloPairs;
+    d.NinternalElements = mesh.NinternalElements;
+    d.NhaloElements = mesh.NhaloElements;
+    d.internalElementIds = mesh.NinternalElements ? mesh.o_internalElementIds.ptr() : nullptr;
+    d.haloElementIds = mesh.NhaloElements ? mesh.o_haloElementIds.ptr() : nullptr;
+    d.vmapM = mesh.o_vmapM.ptr();
+    d.vmapP = mesh.o_vmapP.ptr();
+    d.vgeo = mesh.o_vgeo.ptr();
+    d.sgeo = mesh.o_sgeo.ptr();
+    d.EToB = e.o_EToB.ptr();
+    d.D = mesh.o_D.ptr();
+    d.lambda = e.lambda;
+    d.tau = e.tau;
+    d.traceHalo = traceHalo.h;
+    B200_CHECK(libp_elliptic_create_ipdg(&d, &h));
+  }
+  void Operator(deviceMemory<dfloat>& o_q, deviceMemory<dfloat>& o_Aq) override {
+    rt->enter();
+    B200_CHECK(libp_elliptic_operator(h, o_q.ptr(), o_Aq.ptr(), rt->stream));
+    rt->leave();
+  }
+  ~ellipticIpdgOperatorB200_t() { if (h) libp_elliptic_free(h); }
 };
 
 // ---------------------------------------------------------------------------------- JacobiPrecon

@@ -149,8 +149,51 @@ class MultigridRef:
         x = L.prolongate(xC, x)
         return L.smooth(rhs, x, False)
 
+    # ---- PARALMOND CYCLE = KCYCLE (libs/parAlmond/parAlmondKcycle.cpp:33-133): on the first NUMKCYCLES coarse levels the
+    # coarse correction is improved by up to two steps of a flexible Krylov iteration preconditioned by the cycle itself
+    NUMKCYCLES, KCYCLETOL = 3, 0.2   # include/parAlmond/parAlmondDefines.hpp:35-36
+
+    def level_operator(self, k, x):
+        L = self.levels[k]
+        return L.F.operator(x) if isinstance(L, MGLevelRef) else L.A @ x
+
+    def kcycle(self, k, rhs):
+        if k == len(self.levels):
+            return self.coarse_inv @ rhs
+        L = self.levels[k]
+        x = L.smooth(rhs, None, True)
+        res = L.residual(rhs, x)
+        rhsC = L.coarsen(res)
+        if k + 1 > self.NUMKCYCLES:
+            xC = self.vcycle(k + 1, rhsC)
+        elif k + 1 == len(self.levels):
+            # the exact coarse solve is next: its Krylov step is the identity (alpha1/rho1 = 1, zero residual)
+            xC = self.kcycle(k + 1, rhsC)
+        else:
+            xC = self.kcycle(k + 1, rhsC)                      # first inner iteration
+            ck = xC.copy()                                      # kcycleOp1 (:89-112)
+            vk = self.level_operator(k + 1, ck)
+            alpha1, rho1, norm_rhs = float(ck @ rhsC), float(ck @ vk), np.sqrt(float(rhsC @ rhsC))
+            rhsC = rhsC - (alpha1 / rho1) * vk
+            norm_rhstilde = np.sqrt(float(rhsC @ rhsC))
+            if norm_rhstilde < self.KCYCLETOL * norm_rhs:
+                xC = (alpha1 / rho1) * xC
+            else:
+                xC = self.kcycle(k + 1, rhsC)                  # second inner iteration
+                if abs(rho1) > 1e-20:                           # kcycleOp2 (:114-141)
+                    wk = self.level_operator(k + 1, xC)
+                    gamma, beta, alpha2 = float(xC @ vk), float(xC @ wk), float(xC @ rhsC)
+                    rho2 = beta - gamma * gamma / rho1
+                    if abs(rho2) > 1e-20:
+                        xC = (alpha1 / rho1 - gamma * alpha2 / (rho1 * rho2)) * ck + (alpha2 / rho2) * xC
+        x = L.prolongate(xC, x)
+        return L.smooth(rhs, x, False)
+
     def apply(self, r):
         return self.vcycle(0, r)
+
+    def apply_kcycle(self, r):
+        return self.kcycle(0, r)
 
 
 def pcg(A, M, x, r, tol=1e-8, maxit=5000):
@@ -204,6 +247,45 @@ def nbpcg(A, M, x, r, tol=1e-8, maxit=5000):
         x = x + alpha * p
         Z = A(z)
         beta = gamma0 / gamma1
+        hist.append(np.sqrt(rdotr))
+        it += 1
+    return it, x, np.array(hist)
+
+
+def nbfpcg(A, M, x, r, tol=1e-8, maxit=5000):
+    """LinearSolver::nbfpcg::Solve (libs/linearSolver/linearSolverNBFPCG.cpp:71-171), the non-blocking flexible PCG of
+    Sanan et al. with callable operator / preconditioner; Update0NBFPCG / Update1NBFPCG (:174-246) are the fused
+    vector-update + dot-product kernels.  Returns (iterations, x, residual norms [iterations+1])."""
+    x, r = x.copy(), r - A(x)
+    u = M(r)
+    p = u.copy()
+    w = A(p)
+    gamma, delta, rdotr = float(u @ r), float(u @ w), float(r @ r)   # Update0NBFPCG
+    m = M(w)
+    n = A(m)
+    s, q, z = w.copy(), m.copy(), n.copy()
+    eta = delta
+    alpha = gamma / eta
+    TOL = max(tol * tol * rdotr, tol * tol)
+    hist = [np.sqrt(rdotr)]
+    it = 0
+    while it < maxit:
+        if rdotr <= TOL:
+            break
+        x = x + alpha * p                                             # Update1NBFPCG
+        r = r - alpha * s
+        u = u - alpha * q
+        w = w - alpha * z
+        gamma, uds, delta, rdotr = float(u @ r), float(u @ s), float(u @ w), float(r @ r)
+        m = u + M(w - r)
+        n = A(m)
+        beta = -uds / eta
+        p = u + beta * p
+        s = w + beta * s
+        q = m + beta * q
+        z = n + beta * z
+        eta = delta - beta * beta * eta
+        alpha = gamma / eta
         hist.append(np.sqrt(rdotr))
         it += 1
     return it, x, np.array(hist)

@@ -325,9 +325,13 @@ class BoxMesh:
     def dg_connectivity(self):
         """(vmapM, vmapP, mapP [E, 6*Nq^2] int32, EToB [E, 6] int32 mesh boundary flag, -1 = interior face).
         Neighbouring box elements see a shared face with the same (a, b) face-node numbering, so face node n of face f
-        meets face node n of the opposite face of the neighbour; a boundary face maps to itself."""
-        assert self.size == 1, "single-rank harness (multi-rank IPDG runs use the reference's own connectivity)"
+        meets face node n of the opposite face of the neighbour; a boundary face maps to itself.  On several ranks a
+        neighbour on another rank becomes a halo element: slots Nelements, Nelements+1, ... in (element, face) order,
+        one per (element, face) pair, as mesh_t::HaloSetup numbers them (libs/mesh/meshHaloSetup.cpp:97-111); the
+        details of that halo are kept in self.dg_halo (see dg_halo_info)."""
         nx, ny, nz = self.nloc
+        ox, oy, oz = self.off
+        NX, NY, NZ = self.NX, self.NY, self.NZ
         E, Np, Nfp = self.Nelements, self.Np, self.Nq * self.Nq
         dev = self.device
         e = torch.arange(E, device=dev)
@@ -336,25 +340,73 @@ class BoxMesh:
         periodic = self.boundary_flag == -1
         shifts = [(0, 0, -1, 5), (0, -1, 0, 3), (1, 0, 0, 4), (0, 1, 0, 1), (-1, 0, 0, 2), (0, 0, 1, 0)]
         n = torch.arange(Nfp, device=dev)
+        # owner rank, local element number and first global element of every element of the global box
+        owner = torch.empty((NZ, NY, NX), dtype=torch.int64, device=dev)
+        local = torch.empty((NZ, NY, NX), dtype=torch.int64, device=dev)
+        goff = [0]
+        for rr in range(self.size):
+            (mx, my, mz), (px, py, pz) = local_box(NX, NY, NZ, self.size, rr)
+            owner[pz:pz + mz, py:py + my, px:px + mx] = rr
+            local[pz:pz + mz, py:py + my, px:px + mx] = torch.arange(mx * my * mz, device=dev).reshape(mz, my, mx)
+            goff.append(goff[-1] + mx * my * mz)
+        goff = torch.tensor(goff, dtype=torch.int64, device=dev)
+        # neighbour of every (element, face): global coordinates, owner, boundary
+        gP = torch.empty((E, 6, 3), dtype=torch.int64, device=dev)
+        bnd = torch.empty((E, 6), dtype=torch.bool, device=dev)
+        for f, (sx, sy, sz, _) in enumerate(shifts):
+            qx, qy, qz = ex + ox + sx, ey + oy + sy, ez + oz + sz
+            outside = (qx < 0) | (qx >= NX) | (qy < 0) | (qy >= NY) | (qz < 0) | (qz >= NZ)
+            bnd[:, f] = outside & (not periodic)
+            gP[:, f, 0], gP[:, f, 1], gP[:, f, 2] = qx % NX, qy % NY, qz % NZ
+        rP = owner[gP[..., 2], gP[..., 1], gP[..., 0]]                  # [E, 6]
+        lP = local[gP[..., 2], gP[..., 1], gP[..., 0]]
+        remote = (rP != self.rank) & ~bnd
+        slot = torch.cumsum(remote.reshape(-1).to(torch.int64), 0).reshape(E, 6) - 1   # (element, face) order
+        eP = torch.where(remote, E + slot, lP)                           # element index in the (local + halo) numbering
         vmapM = (e[:, None, None] * Np + fn[None]).reshape(E, 6 * Nfp)
         vmapP = torch.empty((E, 6, Nfp), dtype=torch.int64, device=dev)
         mapP = torch.empty((E, 6, Nfp), dtype=torch.int64, device=dev)
         EToB = torch.full((E, 6), -1, dtype=torch.int32, device=dev)
-        for f, (sx, sy, sz, fP) in enumerate(shifts):
-            px, py, pz = ex + sx, ey + sy, ez + sz
-            outside = (px < 0) | (px >= nx) | (py < 0) | (py >= ny) | (pz < 0) | (pz >= nz)
-            eP = (px % nx) + (py % ny) * nx + (pz % nz) * nx * ny
-            bnd = outside & (not periodic)
-            vP = eP[:, None] * Np + fn[fP][None]
-            mP = eP[:, None] * 6 * Nfp + fP * Nfp + n[None]
+        for f, (_, _, _, fP) in enumerate(shifts):
+            vP = eP[:, f, None] * Np + fn[fP][None]
+            mP = eP[:, f, None] * 6 * Nfp + fP * Nfp + n[None]
             vM = e[:, None] * Np + fn[f][None]
             mM = e[:, None] * 6 * Nfp + f * Nfp + n[None]
-            vmapP[:, f] = torch.where(bnd[:, None], vM, vP)
-            mapP[:, f] = torch.where(bnd[:, None], mM, mP)
-            EToB[:, f] = torch.where(bnd, torch.tensor(self.boundary_flag, dtype=torch.int32, device=dev),
+            b = bnd[:, f, None]
+            vmapP[:, f] = torch.where(b, vM, vP)
+            mapP[:, f] = torch.where(b, mM, mP)
+            EToB[:, f] = torch.where(bnd[:, f], torch.tensor(self.boundary_flag, dtype=torch.int32, device=dev),
                                      torch.tensor(-1, dtype=torch.int32, device=dev))
+        is_halo = remote.any(dim=1)
+        self.dg_halo = dict(totalHaloPairs=int(remote.sum()), remote=remote, neighbourRank=rP, neighbourLocal=lP,
+                            slot=slot, elementOffsets=goff,
+                            internalElementIds=torch.nonzero(~is_halo).reshape(-1).to(torch.int32),
+                            haloElementIds=torch.nonzero(is_halo).reshape(-1).to(torch.int32))
         return (vmapM.to(torch.int32).contiguous(), vmapP.reshape(E, 6 * Nfp).to(torch.int32).contiguous(),
                 mapP.reshape(E, 6 * Nfp).to(torch.int32).contiguous(), EToB.contiguous())
+
+    def dg_trace_halo_ids(self):
+        """ids mesh_t::HaloTraceSetup(1) hands to halo_t::Setup (libs/mesh/meshHaloTraceSetup.cpp:38-83), int64
+        [(Nelements + totalHaloPairs) * Np]: own nodes carry (global element * Np + node + 1), the face nodes of the
+        halo elements this rank's faces look at carry the negative id of the remote node, everything else 0.
+        Call after dg_connectivity()."""
+        h = self.dg_halo
+        E, Np, Nfp = self.Nelements, self.Np, self.Nq * self.Nq
+        dev = self.device
+        Eh = h["totalHaloPairs"]
+        ids = torch.zeros((E + Eh) * Np, dtype=torch.int64, device=dev)
+        ids[: E * Np] = int(h["elementOffsets"][self.rank]) * Np + torch.arange(E * Np, device=dev) + 1
+        if Eh:
+            fn = self.face_nodes()
+            opposite = [5, 3, 4, 1, 2, 0]
+            ef = torch.nonzero(h["remote"])                                # rows (element, face) in slot order
+            el, fa = ef[:, 0], ef[:, 1]
+            gl = h["neighbourLocal"][el, fa] + h["elementOffsets"][h["neighbourRank"][el, fa]]
+            fP = torch.tensor(opposite, device=dev)[fa]
+            nodes = fn[fP]                                                 # [Eh, Nfp] nodes of the neighbour's face
+            slots = E + torch.arange(Eh, device=dev)
+            ids[(slots[:, None] * Np + nodes).reshape(-1)] = -(gl[:, None] * Np + nodes + 1).reshape(-1)
+        return ids
 
     def masked_global_ids(self, bc_type=(0, 1, 2)):
         """(elliptic mapB, maskedGlobalIds): Dirichlet nodes get id 0 (ellipticBoundarySetup.cpp:55-86)."""

@@ -81,3 +81,27 @@ def test_ipdg_oracle_vs_reference_multi_rank(name):
         assert rel(Aq, g[f"r{r}_Aq"]) < 1e-13
         assert rel(ip.diagonal(Nq, g[f"r{r}_vgeo"], g[f"r{r}_sgeo"], g[f"r{r}_EToB"], g[f"r{r}_D"], lam, tau),
                    g[f"r{r}_diagA"]) < 1e-13
+
+
+@pytest.mark.parametrize("name", SINGLE[:3] + MULTI)
+def test_harness_dg_connectivity_matches_reference(name):
+    """BoxMesh.dg_connectivity / dg_trace_halo_ids (the harness' stand-in for mesh_t::ConnectFaceNodes, HaloSetup and
+    HaloTraceSetup on the box) against the reference's arrays on every rank: vmapM, vmapP, mapP, boundary flags, the
+    element halo (slots in (element, face) order), internal / halo element lists and the trace-halo ids - bit for bit"""
+    from libparanumal_b200.box_mesh import BoxMesh
+    g = load(name)
+    N, box, flag, P = int(g["config_N"]), [int(v) for v in g["config_box"]], int(g["config_flag"]), int(g["config_P"])
+    for r in range(P):
+        k = f"r{r}_"
+        m = BoxMesh(N, box[0], box[1], box[2], rank=r, size=P, boundary_flag=flag, device="cpu", geometry=False)
+        vM, vP, mP, EB = m.dg_connectivity()
+        h = m.dg_halo
+        assert np.array_equal(vM.numpy().reshape(-1), g[k + "vmapM"])
+        assert np.array_equal(vP.numpy().reshape(-1), g[k + "vmapP"])
+        assert np.array_equal(mP.numpy().reshape(-1), g[k + "mapP"])
+        assert np.array_equal(EB.numpy().reshape(-1), g[k + "meshEToB"])
+        assert h["totalHaloPairs"] == int(g[k + "meta"][4])
+        assert np.array_equal(h["internalElementIds"].numpy(), g[k + "internalElementIds"])
+        assert np.array_equal(h["haloElementIds"].numpy(), g[k + "haloElementIds"])
+        assert np.array_equal(m.dg_trace_halo_ids().numpy(), g[k + "traceGlobalIds"])
+        assert int(h["elementOffsets"][r]) == int(g[k + "elementOffset"][0])

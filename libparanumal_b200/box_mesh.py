@@ -322,6 +322,37 @@ class BoxMesh:
         return torch.stack([a + b * Nq, a + b * Nq * Nq, N + a * Nq + b * Nq * Nq, a + N * Nq + b * Nq * Nq,
                             a * Nq + b * Nq * Nq, a + b * Nq + N * Nq * Nq]).to(torch.int64)
 
+    def _dg_connectivity_one_rank(self):
+        """dg_connectivity on one rank (no halo elements; wrap-around neighbours of a periodic box are local)"""
+        nx, ny, nz = self.nloc
+        E, Np, Nfp = self.Nelements, self.Np, self.Nq * self.Nq
+        dev = self.device
+        e = torch.arange(E, device=dev)
+        ex, ey, ez = e % nx, (e // nx) % ny, e // (nx * ny)
+        fn = self.face_nodes()
+        periodic = self.boundary_flag == -1
+        shifts = [(0, 0, -1, 5), (0, -1, 0, 3), (1, 0, 0, 4), (0, 1, 0, 1), (-1, 0, 0, 2), (0, 0, 1, 0)]
+        n = torch.arange(Nfp, device=dev)
+        vmapM = (e[:, None, None] * Np + fn[None]).reshape(E, 6 * Nfp)
+        vmapP = torch.empty((E, 6, Nfp), dtype=torch.int64, device=dev)
+        mapP = torch.empty((E, 6, Nfp), dtype=torch.int64, device=dev)
+        EToB = torch.full((E, 6), -1, dtype=torch.int32, device=dev)
+        for f, (sx, sy, sz, fP) in enumerate(shifts):
+            px, py, pz = ex + sx, ey + sy, ez + sz
+            outside = (px < 0) | (px >= nx) | (py < 0) | (py >= ny) | (pz < 0) | (pz >= nz)
+            eP = (px % nx) + (py % ny) * nx + (pz % nz) * nx * ny
+            bnd = outside & (not periodic)
+            vP = eP[:, None] * Np + fn[fP][None]
+            mP = eP[:, None] * 6 * Nfp + fP * Nfp + n[None]
+            vM = e[:, None] * Np + fn[f][None]
+            mM = e[:, None] * 6 * Nfp + f * Nfp + n[None]
+            vmapP[:, f] = torch.where(bnd[:, None], vM, vP)
+            mapP[:, f] = torch.where(bnd[:, None], mM, mP)
+            EToB[:, f] = torch.where(bnd, torch.tensor(self.boundary_flag, dtype=torch.int32, device=dev),
+                                     torch.tensor(-1, dtype=torch.int32, device=dev))
+        return (vmapM.to(torch.int32).contiguous(), vmapP.reshape(E, 6 * Nfp).to(torch.int32).contiguous(),
+                mapP.reshape(E, 6 * Nfp).to(torch.int32).contiguous(), EToB.contiguous())
+
     def dg_connectivity(self):
         """(vmapM, vmapP, mapP [E, 6*Nq^2] int32, EToB [E, 6] int32 mesh boundary flag, -1 = interior face).
         Neighbouring box elements see a shared face with the same (a, b) face-node numbering, so face node n of face f
@@ -329,6 +360,16 @@ class BoxMesh:
         neighbour on another rank becomes a halo element: slots Nelements, Nelements+1, ... in (element, face) order,
         one per (element, face) pair, as mesh_t::HaloSetup numbers them (libs/mesh/meshHaloSetup.cpp:97-111); the
         details of that halo are kept in self.dg_halo (see dg_halo_info)."""
+        if self.size == 1:
+            out = self._dg_connectivity_one_rank()
+            E = self.Nelements
+            z = torch.zeros((E, 6), dtype=torch.int64, device=self.device)
+            self.dg_halo = dict(totalHaloPairs=0, remote=torch.zeros((E, 6), dtype=torch.bool, device=self.device),
+                                neighbourRank=z, neighbourLocal=z, slot=z - 1,
+                                elementOffsets=torch.tensor([0, E], dtype=torch.int64, device=self.device),
+                                internalElementIds=torch.arange(E, dtype=torch.int32, device=self.device),
+                                haloElementIds=torch.zeros(0, dtype=torch.int32, device=self.device))
+            return out
         nx, ny, nz = self.nloc
         ox, oy, oz = self.off
         NX, NY, NZ = self.NX, self.NY, self.NZ

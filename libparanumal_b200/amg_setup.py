@@ -56,7 +56,8 @@ def arnoldi_rho(apply, v0, n_total, dot=None, k=10):
     (must return a new vector), v0 = start vector (numpy or torch), dot(a, b) = global inner product."""
     k = int(min(k, n_total))
     if dot is None:
-        dot = lambda a, b: float(np.dot(a, b))
+        # einsum, not np.dot: a threaded BLAS-1 call on a busy host costs tens of ms for what is a 1 ms loop
+        dot = lambda a, b: float(np.einsum("i,i->", a, b))
     H = np.zeros((k, k))
     V = [v0 * (1.0 / np.sqrt(dot(v0, v0)))]
     for j in range(k):
